@@ -1,0 +1,269 @@
+/*
+ * sapt.h — C-ABI of the B200-native surrogate-assisted parallel-tempering hot path.
+ *
+ * The reference (sydney-machine-learning/surrogate-assisted-parallel-tempering) has no
+ * plugin / FFI layer: its boundary is the Python class surface. Each entry
+ * point below names the reference function(s) it replaces, batched over the R replicas
+ * (chains) a GPU hosts. File abbreviations: RV=_revamp.py,
+ * RW=misc_codeapril2020/surrogate_rw_common_interval.py,
+ * LG=misc_codeapril2020/surrogate_pt_classifier_langevingrad.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SAPT_ERR_* otherwise; no exception
+ *     crosses the boundary; sapt_last_error() gives a thread-local message.
+ *   - pointers are DEVICE pointers unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream). Nothing here
+ *     synchronises the host except sapt_problem_create / *_host entry points.
+ *   - theta is fp32 [R][ld_theta], one chain per row, element order of Network.encode
+ *     (RV:120-127): W1 row-major [D][H], W2 row-major [H][O], B1[H], B2[O].
+ *   - "slot" = chain identity (temperature ladder position, RNG stream, history row);
+ *     "row" = where a parameter vector lives. Replica exchange re-binds slots to rows
+ *     instead of moving parameter vectors.
+ */
+#ifndef SAPT_H_
+#define SAPT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAPT_ABI_VERSION 1
+
+enum {
+  SAPT_OK = 0,
+  SAPT_ERR_INVALID = -1,     /* bad argument (NULL, negative size, label out of range ...) */
+  SAPT_ERR_UNSUPPORTED = -2, /* topology outside the compiled kernel envelope */
+  SAPT_ERR_CUDA = -3,        /* a CUDA runtime call failed; see sapt_last_error() */
+  SAPT_ERR_NOMEM = -4
+};
+
+/* likelihood kernel selection */
+enum {
+  SAPT_PATH_AUTO = 0, /* tcgen05 path when the topology fits it, else fp32 */
+  SAPT_PATH_F32 = 1,  /* fp32 CUDA-core tiles */
+  SAPT_PATH_TC = 2    /* tcgen05/TMEM stacked GEMM (bf16x3 split, fp32 accumulate) */
+};
+
+/* random stream kinds (counter word 2 of the Philox4x32-10 block); oracle/sapt_oracle.py KIND_* */
+enum {
+  SAPT_STREAM_Z1 = 0,  /* first proposal normals           np.random.normal  LG:551 */
+  SAPT_STREAM_Z2 = 1,  /* redraw / Langevin proposal noise np.random.normal  LG:560,651 */
+  SAPT_STREAM_LX1 = 2, /* unused uniform                   np.random.uniform LG:530 */
+  SAPT_STREAM_KU = 3,  /* surrogate coin                   random.uniform    LG:553 */
+  SAPT_STREAM_LX2 = 4, /* Langevin coin                    np.random.uniform LG:647 */
+  SAPT_STREAM_U = 5,   /* Metropolis-Hastings coin         random.uniform    LG:704 */
+  SAPT_STREAM_SWAP = 6 /* exchange coin                    np.random.uniform RW:888 */
+};
+
+/* behaviour switches of the reference's forks (SURVEY.md §2 "variant differences") */
+enum {
+  SAPT_F_POST_TEMPERED = 1 << 0,   /* exchange message carries tempered L (LG:805), else L*T (RW:623) */
+  SAPT_F_TAKE_POST_LIK = 1 << 1,   /* `likelihood = result[P+1]` after the exchange (LG:813-815) */
+  SAPT_F_DENORM_HALF_MIN = 1 << 2, /* surrogate de-normalisation s*minY/2 (LG:325), else s*(maxY-minY)+minY (RV:320) */
+  SAPT_F_COMPARE_SURROGATE = 1 << 3, /* also evaluate the true train likelihood on surrogate steps (RV:543-544) */
+  SAPT_F_REDRAW_ON_SURROGATE = 1 << 4, /* surrogate branch redraws the proposal from stream Z2 (LG:560) */
+  SAPT_F_RECORD_POS = 1 << 5       /* keep the full pos_w history on the device */
+};
+
+typedef struct sapt_problem sapt_problem_t; /* opaque: topology + device-resident data sets */
+
+/* ---- library ------------------------------------------------------------------------ */
+int sapt_abi_version(void);
+const char* sapt_last_error(void);
+/* number of kernels this library has launched since load / since the last reset
+ * (bench.py's "gpu_launches" is read from here, not guessed) */
+long long sapt_launch_count(void);
+void sapt_launch_count_reset(void);
+/* sizeof() of sapt_propose_args, sapt_chain_state, sapt_history, sapt_accept_args,
+ * sapt_lg_first_args — lets an FFI binding verify its struct mirrors at load time */
+int sapt_struct_sizes(int32_t out[5]);
+
+/* ---- data + topology: replaces Network.__init__(Topo, Train, Test, lr) RV:49-60 -------
+ * train_host/test_host: row-major float64 [n][D+1], features then the class index as a
+ * float in column D — exactly the reference's `traindata` / `testdata` arrays (RV:1425-1519).
+ * Copies to HBM once (fp32 features padded to a 16-byte multiple, int32 labels, and the
+ * bf16-split operand image for the tcgen05 path). Labels must be integers in [0, O). */
+int sapt_problem_create(sapt_problem_t** out, int D, int H, int O,
+                        const double* train_host, int64_t n_train,
+                        const double* test_host, int64_t n_test, int device);
+/* same, from float32 features [n][D] and int32 labels (synthetic benchmark shapes) */
+int sapt_problem_create_f32(sapt_problem_t** out, int D, int H, int O,
+                            const float* xtrain_host, const int32_t* ytrain_host, int64_t n_train,
+                            const float* xtest_host, const int32_t* ytest_host, int64_t n_test, int device);
+int sapt_problem_destroy(sapt_problem_t* p);
+int sapt_problem_num_param(const sapt_problem_t* p); /* P = D*H + H*O + H + O */
+int64_t sapt_problem_rows(const sapt_problem_t* p, int which);
+/* 1 if the tcgen05 path supports this topology */
+int sapt_problem_tc_supported(const sapt_problem_t* p);
+
+/* ---- batched likelihood: replaces ptReplica.likelihood_func RV:391-402 -> Network.evaluate_proposal
+ * RV:155-174 -> ForwardPass RV:70-76 + softmax RV:129-131, for R chains at once ------------
+ * which: 0 = train set, 1 = test set.
+ * rows/n_rows (device, nullable): evaluate only theta rows rows[0..*n_rows); others untouched.
+ * Outputs, indexed by theta row: L = sum_i log softmax(out_i)[y_i] (UNtempered, fp64
+ * accumulation), ncorrect = #{argmax(out_i) == y_i} (first max on ties, like np.argmax),
+ * sqerr = sum_i (argmax_i - y_i)^2 (rmse^2 * n of RV:380-382). */
+int sapt_loglik(sapt_problem_t* p, int which, const float* theta, int64_t ld_theta, int R,
+                const int32_t* rows, const int32_t* n_rows,
+                double* L, int32_t* ncorrect, double* sqerr, int path, void* stream);
+/* host-buffer convenience (the e2e path): H2D of theta, kernel, D2H of the three outputs */
+int sapt_loglik_host(sapt_problem_t* p, int which, const float* theta_host, int64_t ld_theta, int R,
+                     double* L_host, int32_t* ncorrect_host, double* sqerr_host, int path);
+/* per-row outputs of Network.evaluate_proposal for ONE theta (RV:155-174):
+ * fx[n] = argmax class, prob[n][O] = softmax over the sigmoid outputs */
+int sapt_evaluate_proposal(sapt_problem_t* p, int which, const float* theta,
+                           int32_t* fx, float* prob, void* stream);
+
+/* ---- prior: replaces ptReplica.prior_likelihood RV:404-410 ----------------------------- */
+int sapt_prior(const float* theta, int64_t ld_theta, int R, int P, double sigma_squared,
+               double* prior, void* stream);
+
+/* ---- proposal: replaces `np.random.normal(w, step_w, w_size)` RV:521 / LG:551,560,651 and
+ * the surrogate coin `ku < surrogate_prob and i >= interval + 1` RV:525 -----------------------
+ * For each listed row r (rows/n_rows nullable = all R): slot s = slot_of_row[r];
+ *   proposal[r] = base[r] + step_w * z,  z = z_inject[s][:] if z_inject else Philox(seed, kind, step, s)
+ *   prior_prop[r] = prior_likelihood(sigma_squared, proposal[r])
+ * If decide != 0 the surrogate coin is also thrown (ku_inject[s] or Philox KU):
+ *   is_sur[r] = surrogate_ready && ku < surrogate_prob && step >= gate + 1
+ *   rows with is_sur==0 are appended to true_rows (count *n_true), the others to sur_rows.
+ *   With redraw != 0 surrogate rows use z2_inject / stream Z2 instead (LG:560). */
+typedef struct {
+  const float* base;        /* [R][ld] current theta (or theta_gd for the Langevin proposal) */
+  float* proposal;          /* [R][ld] */
+  int64_t ld;
+  int R, P;
+  const int32_t* slot_of_row; /* [R] (nullable = identity) */
+  int slot_offset;          /* added to the local slot id to form the global chain id */
+  const int32_t* rows;      /* nullable */
+  const int32_t* n_rows;    /* nullable */
+  double step_w, sigma_squared;
+  double* prior_prop;       /* [R] */
+  uint32_t seed; int kind; int step;
+  const float* z_inject;    /* [R_slots][P] or NULL */
+  /* surrogate decision */
+  int decide; int redraw; int surrogate_ready; double surrogate_prob; int gate;
+  const float* z2_inject;   /* [R_slots][P] or NULL */
+  const double* ku_inject;  /* [R_slots] or NULL */
+  int32_t* is_sur;          /* [R] */
+  int32_t* true_rows; int32_t* n_true; int32_t* sur_rows; int32_t* n_sur;
+} sapt_propose_args;
+int sapt_propose(const sapt_propose_args* a, void* stream);
+
+/* ---- Langevin "gradient": replaces Network.langevin_gradient LG:138-156 + BackwardPass
+ * LG:96-106 (one epoch of per-row online SGD, sequential over the train rows) for the listed
+ * rows. mode 0 = "sgd_exact" (reference semantics); mode 1 = "batch": theta + lr * scale *
+ * sum_i g_i(theta) with g_i the LG:100-106 increments at FIXED theta. */
+int sapt_langevin(sapt_problem_t* p, const float* theta, float* theta_gd, int64_t ld, int R,
+                  const int32_t* rows, const int32_t* n_rows, double lrate, int mode,
+                  double batch_scale, void* stream);
+
+/* ---- surrogate predict: replaces surrogate.predict RV:297-322 (Keras MLP P->h1->h2->1,
+ * relu/relu/sigmoid, RV:217-233) for the listed rows; s[r] = raw network output in (0,1).
+ * Weights in Keras Dense layout: W1[P][h1], b1[h1], W2[h1][h2], b2[h2], W3[h2], b3[1]. */
+int sapt_surrogate_predict(const float* theta, int64_t ld, int R, int P,
+                           const int32_t* rows, const int32_t* n_rows,
+                           const float* W1, const float* b1, int h1,
+                           const float* W2, const float* b2, int h2,
+                           const float* W3, const float* b3, float* s, void* stream);
+
+/* ---- chain state: scalars of the reference's ptReplica.run locals. Indexed by GLOBAL chain id
+ * ("slot") except slot_of_row, which maps the rank-local theta rows to the chain each hosts.
+ * Every rank keeps full-size arrays and only touches the slots its rows host; the caller
+ * re-synchronises them across ranks before an exchange (a masked all-reduce of scalars). */
+typedef struct {
+  int32_t* slot_of_row;   /* [R local rows] global chain id hosted by that row */
+  double* temperature;    /* [n_slots] T of the chain (adapttemp == temperature, RV:513-514) */
+  double* lik_cur;        /* `likelihood_copy` — what MH reads (RV:586-587) */
+  double* lik_post;       /* `likelihood` — what the exchange message carries (RW:623 / LG:805) */
+  double* prior_cur;      /* `prior_current` (RV:588) */
+  double* mov;            /* [n_slots][3] last three surg_likeh_list[:,2] entries, newest first (RV:541) */
+  double* likl_wo_temp;   /* `likl_without_temp` of the last true train evaluation */
+  double* last_rmse_train; double* last_rmse_test; double* last_acc_train; double* last_acc_test; /* history row i */
+  int32_t* naccept;       /* [n_slots] */
+} sapt_chain_state;
+
+/* per-step history, indexed [step][slot] with slot = GLOBAL chain id; any pointer may be NULL */
+typedef struct {
+  int n_slots;            /* R_global */
+  double* lhood_list; double* rmse_train; double* rmse_test; double* acc_train; double* acc_test;
+  double* surg;           /* [step][slot][3] */
+  double* likeh;          /* likeh_list[:,0] */
+  double* accept_list;    /* naccept before the step (RV:578) */
+  uint8_t* accepted; uint8_t* is_sur;
+  float* pos_w;           /* [step][slot][P] when SAPT_F_RECORD_POS */
+} sapt_history;
+
+/* ---- Metropolis-Hastings accept + bookkeeping: replaces RV:525-642 after the evaluations ---
+ * For every row: builds likelihood_proposal (true: L_train/T; surrogate: 0.5*denorm(s)/T +
+ * 0.5*mean(mov), RV:540-542), mh = min(1, exp((L' - lik_cur) + (prior' - prior_cur))) with
+ * overflow -> 1 (RV:571-577), u = u_inject[slot] or Philox U; on accept copies proposal -> theta
+ * and commits the scalars; writes history row step+1; appends (proposal, L_untempered) of true
+ * steps to the surrogate training set (RW:540-545). */
+typedef struct {
+  float* theta; const float* proposal; int64_t ld; int R, P;
+  sapt_chain_state st;
+  sapt_history hist;
+  int step;                 /* i of the reference loop; history row written = step + 1 */
+  uint32_t flags;           /* SAPT_F_* */
+  const int32_t* is_sur;    /* [R] from sapt_propose (NULL = all true) */
+  const double* L_train; const int32_t* nc_train; const double* sq_train; /* [R] from sapt_loglik */
+  const double* L_test; const int32_t* nc_test; const double* sq_test;
+  int64_t n_train, n_test;
+  const double* prior_prop; /* [R] */
+  const float* sur_s;       /* [R] surrogate outputs */
+  double min_y, max_y;
+  uint32_t seed; const double* u_inject; /* [n_slots] or NULL */
+  /* surrogate training-set capture (true steps): rows appended per slot; NULL = off */
+  float* train_theta;       /* [n_slots][train_cap][P] */
+  double* train_L;          /* [n_slots][train_cap] */
+  int32_t* train_count;     /* [n_slots] */
+  int train_cap;
+  int capture;              /* 1: capture here (RW/RV). 0: already captured by sapt_lg_first_eval */
+  /* LG: the first evaluation's tempered likelihood feeds surg[:,0/2] and the window */
+  const double* surg_first; /* [R] or NULL */
+} sapt_accept_args;
+int sapt_mh_accept(const sapt_accept_args* a, void* stream);
+
+/* ---- LG only: after the FIRST true evaluation (LG:622-645): capture (proposal, L) into the
+ * training set, remember L/T for surg[:,0/2], throw the Langevin coin lx2 < l_prob (LG:647-649)
+ * and list the rows that take a Langevin proposal. */
+typedef struct {
+  const float* proposal; int64_t ld; int R, P;
+  sapt_chain_state st; int step; uint32_t seed;
+  const int32_t* true_rows; const int32_t* n_true;
+  const double* L_train;    /* [R] first evaluation */
+  double* surg_first;       /* [R] out: L/T */
+  int use_langevin; double l_prob; const double* lx2_inject;
+  int32_t* lang_rows; int32_t* n_lang;
+  float* train_theta; double* train_L; int32_t* train_count; int train_cap;
+} sapt_lg_first_args;
+int sapt_lg_first_eval(const sapt_lg_first_args* a, void* stream);
+
+/* ---- replica exchange: replaces ParallelTempering.swap_procedure RW:869-898 and the sequential
+ * sweep RW:1095-1099 over ALL R_global chains. lik_post / temperature are the slot-indexed,
+ * rank-synchronised arrays; row_of_slot[s] says which GLOBAL theta row hosts chain s.
+ * The sweep runs k = 0..R-2 with a = min(1, 0.5*exp(min(709, L[k+1]-L[k]))), L = lik_post
+ * (SAPT_F_POST_TEMPERED, LG:805) or lik_post*T (RW:623), u = u_inject[k] or Philox SWAP(sweep, k).
+ * Whole messages swap, so the pair k+1 competes with whatever pair k left behind. Every rank
+ * runs the identical sweep (counter-based uniforms), so no second collective is needed.
+ * Effects: row_of_slot is re-bound (parameter vectors never move); with SAPT_F_TAKE_POST_LIK
+ * lik_post[k] takes the received message's value (LG:813-815); swapped[k] = decision of pair k;
+ * *num_swap += accepted pairs; src_slot[k] = chain whose message chain k received; for the
+ * rank-local rows [row0, row0+R_local) slot_of_row_local is refreshed. */
+int sapt_swap_sweep(int R_global, double* lik_post, const double* temperature, int32_t* row_of_slot,
+                    uint32_t flags, uint32_t seed, int sweep, const double* u_inject,
+                    uint8_t* swapped, int32_t* num_swap, int32_t* src_slot,
+                    int row0, int R_local, int32_t* slot_of_row_local, void* stream);
+
+/* ---- Philox4x32-10 exposed for the known-answer test */
+int sapt_philox_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* fills u[n] (kind uniform) or z[n] (normals) on the device exactly as the kernels draw them */
+int sapt_philox_fill(uint32_t seed, int kind, int step, int chain, int n, int normal, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAPT_H_ */

@@ -1,0 +1,346 @@
+// Per-chain MCMC kernels: proposal (+prior, +surrogate coin), Metropolis-Hastings accept with
+// the reference's bookkeeping, the LG mid-step, and the sequential replica-exchange sweep.
+// Reference lines are cited per kernel (RV=_revamp.py, RW/LG = the two misc_codeapril2020 forks).
+#include <math.h>
+
+#include "sapt_device.cuh"
+#include "sapt_internal.h"
+
+namespace sapt {
+
+// -------------------------------------------------------------------------------------------
+// prior: -(P/2) ln s2 - sum(w^2)/(2 s2)                                        RV:404-410
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ double prior_from_sumsq(double sumsq, int P, double s2) {
+  return -1.0 * ((double)P / 2.0) * log(s2) - (1.0 / (2.0 * s2)) * sumsq;
+}
+
+__global__ void prior_kernel(const float* theta, int64_t ld, int P, double s2, double* prior) {
+  __shared__ double scratch[32];
+  const float* w = theta + (int64_t)blockIdx.x * ld;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { const double v = (double)w[i]; acc += v * v; }
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) prior[blockIdx.x] = prior_from_sumsq(acc, P, s2);
+}
+
+// -------------------------------------------------------------------------------------------
+// proposal                                                       RV:521,525 / LG:551-560,651
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) propose_kernel(sapt_propose_args a) {
+  __shared__ double scratch[32];
+  __shared__ int s_sur;
+  const int nrows = a.n_rows ? *a.n_rows : a.R;
+  if ((int)blockIdx.x >= nrows) return;
+  const int row = a.rows ? a.rows[blockIdx.x] : (int)blockIdx.x;
+  const int slot = a.slot_of_row ? a.slot_of_row[row] : (row + a.slot_offset);
+  if (threadIdx.x == 0) {
+    int sur = 0;
+    if (a.decide) {
+      const double ku = a.ku_inject ? a.ku_inject[slot] : (double)philox_uniform(a.seed, SAPT_STREAM_KU, a.step, (uint32_t)slot, 0);
+      sur = (a.surrogate_ready && ku < a.surrogate_prob && a.step >= a.gate + 1) ? 1 : 0;
+      a.is_sur[row] = sur;
+      if (sur) { const int k = atomicAdd(a.n_sur, 1); a.sur_rows[k] = row; }
+      else     { const int k = atomicAdd(a.n_true, 1); a.true_rows[k] = row; }
+    }
+    s_sur = sur;
+  }
+  __syncthreads();
+  const bool second = a.decide && a.redraw && s_sur;
+  const float* zin = second ? a.z2_inject : a.z_inject;
+  const int kind = second ? SAPT_STREAM_Z2 : a.kind;
+  const float* __restrict__ b = a.base + (int64_t)row * a.ld;
+  float* __restrict__ o = a.proposal + (int64_t)row * a.ld;
+  const float step = (float)a.step_w;
+  double acc = 0.0;
+  if (zin) {
+    const float* z = zin + (int64_t)slot * a.P;
+    for (int i = threadIdx.x; i < a.P; i += blockDim.x) {
+      const float v = fmaf(step, z[i], b[i]);
+      o[i] = v;
+      acc += (double)v * (double)v;
+    }
+  } else {
+    const int nblk = (a.P + 3) >> 2;
+    for (int q = threadIdx.x; q < nblk; q += blockDim.x) {
+      float z[4];
+      philox_normal4(a.seed, kind, a.step, (uint32_t)slot, (uint32_t)q, z);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = 4 * q + j;
+        if (i < a.P) {
+          const float v = fmaf(step, z[j], b[i]);
+          o[i] = v;
+          acc += (double)v * (double)v;
+        }
+      }
+    }
+  }
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) a.prior_prop[row] = prior_from_sumsq(acc, a.P, a.sigma_squared);
+}
+
+// -------------------------------------------------------------------------------------------
+// LG: bookkeeping after the FIRST true evaluation + Langevin coin               LG:622-649
+// -------------------------------------------------------------------------------------------
+__global__ void lg_first_kernel(sapt_lg_first_args a) {
+  const int n = a.n_true ? *a.n_true : a.R;
+  if ((int)blockIdx.x >= n) return;
+  const int row = a.true_rows ? a.true_rows[blockIdx.x] : (int)blockIdx.x;
+  const int slot = a.st.slot_of_row[row];
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) {
+    const double L = a.L_train[row];
+    a.surg_first[row] = L / a.st.temperature[slot];
+    int cnt = -1;
+    if (a.train_count) {
+      cnt = a.train_count[slot];
+      if (cnt < a.train_cap) { a.train_L[(int64_t)slot * a.train_cap + cnt] = L; a.train_count[slot] = cnt + 1; }
+      else cnt = -1;
+    }
+    s_cnt = cnt;
+    if (a.use_langevin) {
+      const double lx = a.lx2_inject ? a.lx2_inject[slot] : (double)philox_uniform(a.seed, SAPT_STREAM_LX2, a.step, (uint32_t)slot, 0);
+      if (lx < a.l_prob) { const int k = atomicAdd(a.n_lang, 1); a.lang_rows[k] = row; }
+    }
+  }
+  __syncthreads();
+  if (s_cnt >= 0 && a.train_theta) {
+    const float* src = a.proposal + (int64_t)row * a.ld;
+    float* dst = a.train_theta + ((int64_t)slot * a.train_cap + s_cnt) * a.P;
+    for (int i = threadIdx.x; i < a.P; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Metropolis-Hastings accept + bookkeeping                                      RV:525-642
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mh_accept_kernel(sapt_accept_args a) {
+  const int row = blockIdx.x;
+  const int slot = a.st.slot_of_row[row];
+  const int S = a.hist.n_slots;
+  __shared__ int s_accept, s_cnt;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const double NANV = __longlong_as_double(0x7ff8000000000000LL);
+  const int64_t hi = (int64_t)a.step * S + slot;        // history row i
+  const int64_t ho = (int64_t)(a.step + 1) * S + slot;  // history row i+1
+  if (threadIdx.x == 0) {
+    const double T = a.st.temperature[slot];
+    const bool sur = a.is_sur && a.is_sur[row];
+    double Lprop, s0, s1, s2;
+    double rmse_tr = a.st.last_rmse_train[slot], rmse_te = a.st.last_rmse_test[slot];
+    double acc_tr = a.st.last_acc_train[slot], acc_te = a.st.last_acc_test[slot];
+    double rm_tr_new = 0, rm_te_new = 0, ac_tr_new = 0, ac_te_new = 0;
+    int cnt = -1;
+    if (sur) {
+      // RV:319-320 / LG:325: float32 network output times float64 scalars
+      const double s = (double)a.sur_s[row];
+      double pred = (a.flags & SAPT_F_DENORM_HALF_MIN) ? (s * a.min_y / 2.0) : (s * (a.max_y - a.min_y) + a.min_y);
+      const double surl = pred * (1.0 / T);                                  // RV:540
+      const double* m = a.st.mov + (int64_t)slot * 3;
+      const double mov = (m[0] + m[1] + m[2]) / 3.0;                         // RV:541
+      Lprop = (surl * 0.5) + (mov * 0.5);                                    // RV:542
+      double ltrue = 0.0;
+      if (a.flags & SAPT_F_COMPARE_SURROGATE) {                              // RV:543-544
+        ltrue = a.L_train[row] / T;
+        a.st.likl_wo_temp[slot] = a.L_train[row];
+      }
+      s0 = ltrue; s1 = Lprop; s2 = mov;                                      // RV:549-551
+    } else {
+      const double L = a.L_train[row];
+      Lprop = L / T;
+      s0 = Lprop; s1 = NANV; s2 = Lprop;                                     // RV:555,564-565
+      if (a.surg_first) { s2 = a.surg_first[row]; }                          // LG:644-645 then LG:678-679
+      a.st.likl_wo_temp[slot] = L;
+      rm_tr_new = sqrt(a.sq_train[row] / (double)a.n_train);                 // RV:380-382
+      ac_tr_new = 100.0 * ((double)a.nc_train[row] / (double)a.n_train);     // RV:384-389
+      if (a.n_test > 0) {
+        rm_te_new = sqrt(a.sq_test[row] / (double)a.n_test);
+        ac_te_new = 100.0 * ((double)a.nc_test[row] / (double)a.n_test);
+      }
+      if (a.capture && a.train_count) {                                      // RW:540-545
+        cnt = a.train_count[slot];
+        if (cnt < a.train_cap) { a.train_L[(int64_t)slot * a.train_cap + cnt] = L; a.train_count[slot] = cnt + 1; }
+        else cnt = -1;
+      }
+    }
+    s_cnt = cnt;
+    // moving-average window: newest first
+    double* m = a.st.mov + (int64_t)slot * 3;
+    m[2] = m[1]; m[1] = m[0]; m[0] = s2;
+    const double prior_prop = a.prior_prop[row];
+    const double diff = (Lprop - a.st.lik_cur[slot]) + (prior_prop - a.st.prior_cur[slot]);
+    // min(1, exp(diff)); OverflowError -> 1 (RV:571-577); Python's min(1, nan) is 1 as well
+    double mh;
+    if (diff != diff) mh = 1.0;
+    else if (diff >= 0.0) mh = 1.0;
+    else mh = exp(diff);
+    const double u = a.u_inject ? a.u_inject[slot] : (double)philox_uniform(a.seed, SAPT_STREAM_U, a.step, (uint32_t)slot, 0);
+    const int nacc = a.st.naccept[slot];
+    const bool acc = u < mh;
+    double h_lhood, h_rtr, h_rte, h_atr, h_ate;
+    if (acc) {
+      a.st.naccept[slot] = nacc + 1;
+      a.st.lik_cur[slot] = Lprop; a.st.lik_post[slot] = Lprop; a.st.prior_cur[slot] = prior_prop;
+      if (!sur) { h_lhood = Lprop * T; h_rtr = rm_tr_new; h_rte = rm_te_new; h_atr = ac_tr_new; h_ate = ac_te_new; }
+      else { h_lhood = h_rtr = h_rte = h_atr = h_ate = INF; }
+    } else {
+      if (!sur) { h_lhood = Lprop * T; h_rtr = rmse_tr; h_rte = rmse_te; h_atr = acc_tr; h_ate = acc_te; }
+      else { h_lhood = h_rtr = h_rte = h_atr = h_ate = INF; }
+    }
+    a.st.last_rmse_train[slot] = h_rtr; a.st.last_rmse_test[slot] = h_rte;
+    a.st.last_acc_train[slot] = h_atr; a.st.last_acc_test[slot] = h_ate;
+    if (a.hist.lhood_list) a.hist.lhood_list[ho] = h_lhood;
+    if (a.hist.rmse_train) a.hist.rmse_train[ho] = h_rtr;
+    if (a.hist.rmse_test) a.hist.rmse_test[ho] = h_rte;
+    if (a.hist.acc_train) a.hist.acc_train[ho] = h_atr;
+    if (a.hist.acc_test) a.hist.acc_test[ho] = h_ate;
+    if (a.hist.surg) { double* sg = a.hist.surg + ho * 3; sg[0] = s0; sg[1] = s1; sg[2] = s2; }
+    if (a.hist.likeh) a.hist.likeh[ho] = a.st.likl_wo_temp[slot];
+    if (a.hist.accept_list) a.hist.accept_list[ho] = (double)nacc;
+    if (a.hist.accepted) a.hist.accepted[ho] = acc ? 1 : 0;
+    if (a.hist.is_sur) a.hist.is_sur[ho] = sur ? 1 : 0;
+    s_accept = acc ? 1 : 0;
+  }
+  __syncthreads();
+  const bool acc = s_accept != 0;
+  const float* __restrict__ prop = a.proposal + (int64_t)row * a.ld;
+  float* __restrict__ th = a.theta + (int64_t)row * a.ld;
+  float* tr = (s_cnt >= 0 && a.train_theta) ? a.train_theta + ((int64_t)slot * a.train_cap + s_cnt) * a.P : nullptr;
+  float* pw_out = ((a.flags & SAPT_F_RECORD_POS) && a.hist.pos_w) ? a.hist.pos_w + ho * a.P : nullptr;
+  const float* pw_in = pw_out ? a.hist.pos_w + hi * a.P : nullptr;
+  for (int i = threadIdx.x; i < a.P; i += blockDim.x) {
+    const float v = prop[i];
+    if (tr) tr[i] = v;
+    if (acc) th[i] = v;
+    if (pw_out) pw_out[i] = acc ? v : pw_in[i];  // RV:590 / RV:608: reject copies HISTORY row i
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// replica exchange: sequential sweep over all chains                 RW:869-898, RW:1095-1099
+// -------------------------------------------------------------------------------------------
+__global__ void swap_sweep_kernel(int R, double* lik_post, const double* temperature, int32_t* row_of_slot, uint32_t flags,
+                                  uint32_t seed, int sweep, const double* u_inject, uint8_t* swapped, int32_t* num_swap,
+                                  int32_t* src_slot, int row0, int R_local, int32_t* slot_of_row_local) {
+  extern __shared__ double sh[];
+  double* post = sh;                                   // [R] message likelihoods
+  double* uu = sh + R;                                 // [R-1]
+  int32_t* src = reinterpret_cast<int32_t*>(uu + R);   // [R]
+  int32_t* rows = src + R;                             // [R]
+  for (int k = threadIdx.x; k < R; k += blockDim.x) {
+    // RW:623 posts likelihood*adapttemp ; LG:805 posts the tempered value
+    post[k] = (flags & SAPT_F_POST_TEMPERED) ? lik_post[k] : lik_post[k] * temperature[k];
+    src[k] = k;
+    rows[k] = row_of_slot[k];
+    if (k < R - 1) uu[k] = u_inject ? u_inject[k] : (double)philox_uniform(seed, SAPT_STREAM_SWAP, sweep, 0u, (uint32_t)k);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ns = 0;
+    for (int k = 0; k < R - 1; ++k) {
+      const double d = fmin(709.0, post[k + 1] - post[k]);
+      double pr = 0.5 * exp(d);
+      if (d != d) pr = 1.0;  // min(1, nan) == 1 in Python
+      pr = fmin(1.0, pr);
+      const bool sw = uu[k] < pr;
+      if (sw) {
+        const double t = post[k]; post[k] = post[k + 1]; post[k + 1] = t;
+        const int s = src[k]; src[k] = src[k + 1]; src[k + 1] = s;
+        ++ns;
+      }
+      if (swapped) swapped[k] = sw ? 1 : 0;
+    }
+    if (num_swap) *num_swap += ns;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < R; k += blockDim.x) {
+    const int newrow = rows[src[k]];  // chain k now holds the vector chain src[k] posted
+    row_of_slot[k] = newrow;
+    if (src_slot) src_slot[k] = src[k];
+    if (flags & SAPT_F_TAKE_POST_LIK) lik_post[k] = post[k];  // LG:813-815
+    if (slot_of_row_local && newrow >= row0 && newrow < row0 + R_local) slot_of_row_local[newrow - row0] = k;
+  }
+}
+
+__global__ void philox_fill_kernel(uint32_t seed, int kind, int step, int chain, int n, int normal, float* out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (normal) {
+    if (4 * q >= n) return;
+    float z[4];
+    philox_normal4(seed, kind, step, (uint32_t)chain, (uint32_t)q, z);
+    for (int j = 0; j < 4; ++j) if (4 * q + j < n) out[4 * q + j] = z[j];
+  } else {
+    if (q < n) out[q] = philox_uniform(seed, kind, step, (uint32_t)chain, (uint32_t)q);
+  }
+}
+
+}  // namespace sapt
+
+using namespace sapt;
+
+extern "C" int sapt_prior(const float* theta, int64_t ld_theta, int R, int P, double sigma_squared, double* prior, void* stream) {
+  SAPT_REQUIRE(theta && prior && R >= 0 && P > 0 && ld_theta >= P, "sapt_prior");
+  if (R == 0) return SAPT_OK;
+  prior_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(theta, ld_theta, P, sigma_squared, prior);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}
+
+extern "C" int sapt_propose(const sapt_propose_args* a, void* stream) {
+  SAPT_REQUIRE(a && a->base && a->proposal && a->prior_prop && a->R >= 0 && a->P > 0 && a->ld >= a->P, "sapt_propose");
+  if (a->decide) SAPT_REQUIRE(a->is_sur && a->true_rows && a->n_true && a->sur_rows && a->n_sur, "sapt_propose: decision outputs");
+  if (a->R == 0) return SAPT_OK;
+  propose_kernel<<<a->R, 256, 0, (cudaStream_t)stream>>>(*a);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}
+
+extern "C" int sapt_lg_first_eval(const sapt_lg_first_args* a, void* stream) {
+  SAPT_REQUIRE(a && a->proposal && a->L_train && a->surg_first && a->st.slot_of_row && a->st.temperature, "sapt_lg_first_eval");
+  if (a->use_langevin) SAPT_REQUIRE(a->lang_rows && a->n_lang, "sapt_lg_first_eval: langevin outputs");
+  if (a->R == 0) return SAPT_OK;
+  lg_first_kernel<<<a->R, 128, 0, (cudaStream_t)stream>>>(*a);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}
+
+extern "C" int sapt_mh_accept(const sapt_accept_args* a, void* stream) {
+  SAPT_REQUIRE(a && a->theta && a->proposal && a->prior_prop && a->L_train, "sapt_mh_accept");
+  SAPT_REQUIRE(a->st.slot_of_row && a->st.temperature && a->st.lik_cur && a->st.lik_post && a->st.prior_cur && a->st.mov &&
+               a->st.likl_wo_temp && a->st.naccept && a->st.last_rmse_train && a->st.last_rmse_test &&
+               a->st.last_acc_train && a->st.last_acc_test, "sapt_mh_accept: chain state");
+  SAPT_REQUIRE(a->nc_train && a->sq_train && a->n_train > 0, "sapt_mh_accept: train stats");
+  if (a->n_test > 0) SAPT_REQUIRE(a->L_test && a->nc_test && a->sq_test, "sapt_mh_accept: test stats");
+  if (a->R == 0) return SAPT_OK;
+  mh_accept_kernel<<<a->R, 128, 0, (cudaStream_t)stream>>>(*a);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}
+
+extern "C" int sapt_swap_sweep(int R_global, double* lik_post, const double* temperature, int32_t* row_of_slot, uint32_t flags,
+                               uint32_t seed, int sweep, const double* u_inject, uint8_t* swapped, int32_t* num_swap,
+                               int32_t* src_slot, int row0, int R_local, int32_t* slot_of_row_local, void* stream) {
+  SAPT_REQUIRE(R_global >= 1 && lik_post && temperature && row_of_slot, "sapt_swap_sweep");
+  const size_t smem = (size_t)R_global * (2 * sizeof(double) + 2 * sizeof(int32_t));
+  if (smem > 200 * 1024) { set_error("sapt_swap_sweep: %d chains exceed the single-CTA sweep capacity", R_global); return SAPT_ERR_UNSUPPORTED; }
+  if (smem > 48 * 1024) SAPT_CUDA(cudaFuncSetAttribute(swap_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  swap_sweep_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(R_global, lik_post, temperature, row_of_slot, flags, seed, sweep, u_inject,
+                                                            swapped, num_swap, src_slot, row0, R_local, slot_of_row_local);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}
+
+extern "C" int sapt_philox_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  philox4x32_10(ctr, key[0], key[1], out);
+  return SAPT_OK;
+}
+
+extern "C" int sapt_philox_fill(uint32_t seed, int kind, int step, int chain, int n, int normal, float* out, void* stream) {
+  SAPT_REQUIRE(out && n >= 0, "sapt_philox_fill");
+  if (n == 0) return SAPT_OK;
+  const int work = normal ? (n + 3) / 4 : n;
+  philox_fill_kernel<<<(work + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, kind, step, chain, n, normal, out);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}

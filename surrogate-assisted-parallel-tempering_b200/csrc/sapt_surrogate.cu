@@ -1,0 +1,99 @@
+// Batched surrogate predict: replaces surrogate.predict (_revamp.py:297-322), i.e. a Keras MLP
+// P -> h1 (relu) -> h2 (relu) -> 1 (sigmoid) (_revamp.py:217-233) called on ONE theta per step per
+// process, by one launch over every chain that took the surrogate branch this step.
+//
+// A CTA owns TR listed rows. Layer 1 is the only sizeable contraction ([TR x P] . [P x h1]):
+// theta is staged in shared memory P-chunk by P-chunk, thread j owns hidden unit j and streams
+// column j of W1 (coalesced across j) against the TR staged rows (broadcast LDS), fp32 FMA like
+// Keras. Layers 2 and 3 are tiny and stay in shared memory.
+#include "sapt_device.cuh"
+#include "sapt_internal.h"
+
+namespace sapt {
+
+constexpr int kTR = 8;       // rows per CTA
+constexpr int kPC = 512;     // P chunk staged in shared memory
+constexpr int kSurThreads = 256;
+
+__global__ void __launch_bounds__(kSurThreads) surrogate_predict_kernel(const float* theta, int64_t ld, int R, int P, const int32_t* rows,
+                                                                        const int32_t* n_rows, const float* W1, const float* b1, int h1,
+                                                                        const float* W2, const float* b2, int h2, const float* W3,
+                                                                        const float* b3, float* s) {
+  const int nact = n_rows ? *n_rows : R;
+  const int r0 = blockIdx.x * kTR;
+  if (r0 >= nact) return;
+  const int nr = min(kTR, nact - r0);
+  extern __shared__ float sh[];
+  float* ts = sh;                 // [kTR][kPC]
+  float* a1 = ts + kTR * kPC;     // [kTR][h1]
+  float* a2 = a1 + kTR * h1;      // [kTR][h2]
+  __shared__ int srow[kTR];
+  const int tid = threadIdx.x;
+  if (tid < kTR) srow[tid] = (tid < nr) ? (rows ? rows[r0 + tid] : r0 + tid) : -1;
+  __syncthreads();
+  // ---- layer 1 ----
+  for (int j0 = 0; j0 < h1; j0 += kSurThreads) {
+    const int j = j0 + tid;
+    float acc[kTR];
+#pragma unroll
+    for (int r = 0; r < kTR; ++r) acc[r] = 0.f;
+    for (int p0 = 0; p0 < P; p0 += kPC) {
+      const int pc = min(kPC, P - p0);
+      __syncthreads();
+      for (int i = tid; i < kTR * pc; i += kSurThreads) {
+        const int r = i / pc, q = i - r * pc;
+        ts[r * kPC + q] = (srow[r] >= 0) ? theta[(int64_t)srow[r] * ld + p0 + q] : 0.f;
+      }
+      __syncthreads();
+      if (j < h1) {
+        const float* wcol = W1 + (int64_t)p0 * h1 + j;
+#pragma unroll 4
+        for (int q = 0; q < pc; ++q) {
+          const float w = __ldg(wcol + (int64_t)q * h1);
+#pragma unroll
+          for (int r = 0; r < kTR; ++r) acc[r] = fmaf(ts[r * kPC + q], w, acc[r]);
+        }
+      }
+    }
+    if (j < h1) {
+      const float bb = b1[j];
+#pragma unroll
+      for (int r = 0; r < kTR; ++r) a1[r * h1 + j] = fmaxf(acc[r] + bb, 0.f);
+    }
+  }
+  __syncthreads();
+  // ---- layer 2 ----
+  for (int i = tid; i < kTR * h2; i += kSurThreads) {
+    const int r = i / h2, j = i - r * h2;
+    float acc = 0.f;
+    for (int k = 0; k < h1; ++k) acc = fmaf(a1[r * h1 + k], __ldg(W2 + k * h2 + j), acc);
+    a2[i] = fmaxf(acc + b2[j], 0.f);
+  }
+  __syncthreads();
+  // ---- layer 3 + sigmoid: one warp per row ----
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int r = warp; r < nr; r += kSurThreads / 32) {
+    float acc = 0.f;
+    for (int k = lane; k < h2; k += 32) acc = fmaf(a2[r * h2 + k], __ldg(W3 + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s[srow[r]] = 1.0f / (1.0f + expf(-(acc + b3[0])));
+  }
+}
+
+}  // namespace sapt
+
+using namespace sapt;
+
+extern "C" int sapt_surrogate_predict(const float* theta, int64_t ld, int R, int P, const int32_t* rows, const int32_t* n_rows,
+                                      const float* W1, const float* b1, int h1, const float* W2, const float* b2, int h2,
+                                      const float* W3, const float* b3, float* s, void* stream) {
+  SAPT_REQUIRE(theta && W1 && b1 && W2 && b2 && W3 && b3 && s && R >= 0 && P > 0 && h1 > 0 && h2 > 0 && ld >= P, "sapt_surrogate_predict");
+  if (R == 0) return SAPT_OK;
+  const size_t smem = (size_t)(kTR * kPC + kTR * h1 + kTR * h2) * sizeof(float);
+  if (smem > 200 * 1024) { set_error("sapt_surrogate_predict: hidden sizes too large"); return SAPT_ERR_UNSUPPORTED; }
+  if (smem > 48 * 1024) SAPT_CUDA(cudaFuncSetAttribute(surrogate_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  surrogate_predict_kernel<<<(R + kTR - 1) / kTR, kSurThreads, smem, (cudaStream_t)stream>>>(theta, ld, R, P, rows, n_rows, W1, b1, h1, W2, b2, h2,
+                                                                                              W3, b3, s);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}

@@ -1,0 +1,473 @@
+"""Device-resident parallel-tempering engine.
+
+Replaces R x ``ptReplica.run`` (one OS process per chain, _revamp.py:412-780 /
+surrogate_rw_common_interval.py:413-704 / surrogate_pt_classifier_langevingrad.py:428-908) plus
+the coordinator loop of ``ParallelTempering.run_chains`` (RW:1068-1129) by one host thread per
+GPU issuing a handful of kernels per MCMC step through the C-ABI (include/sapt.h). All chain
+state (theta, temperatures, likelihoods, priors, windows, counters, histories, surrogate
+training sets) lives in HBM; the host never reads it inside the loop.
+
+Multi-GPU: chains (theta rows) are sharded contiguously over ranks; an exchange moves only the
+slot binding, after a masked all-reduce of the per-chain scalars (torch.distributed, NCCL on
+GPUs / gloo in the CPU tests of the host logic).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .problem import Problem, _ptr, current_stream_ptr
+
+SURROGATE_HIDDEN = {1: (64, 16), 2: (120, 40), 3: (200, 50)}  # _revamp.py:221-229
+
+
+@dataclass
+class VariantSpec:
+    """Behavioural switches that differ between the reference's forks."""
+    name: str
+    swap: bool
+    swap_at_zero: bool          # LG:804 swaps at i % swap_interval == 0 including i == 0
+    post_tempered: bool         # LG:805 vs RW:623
+    take_post_lik: bool         # LG:813-815
+    gate_on_swap_interval: bool  # RW:507
+    common_interval: bool       # RW: swap + surrogate rendezvous share i % swap_interval == 0, i != 0
+    denorm_half_min: bool       # LG:325 vs RV:320
+    compare_surrogate: bool     # RW:371 / RV:370 True, LG:381 False
+    lg_flow: bool               # LG: redraw on surrogate, Langevin re-proposal, first-eval bookkeeping
+    ship_zero_row: bool         # RW:496,626 / LG:543,822 ship surr_train_set with its all-zero first row
+
+
+VARIANTS = {
+    "rw": VariantSpec("rw", True, False, False, False, True, True, False, True, False, True),
+    "lg": VariantSpec("lg", True, True, True, True, False, False, True, False, True, True),
+    "rv": VariantSpec("rv", False, False, False, False, False, False, False, True, False, False),
+}
+
+
+@dataclass
+class EngineConfig:
+    variant: str = "rw"
+    samples: int = 100                 # per chain (= int(NumSample / num_chains), _revamp.py:800)
+    swap_interval: int = 50
+    surrogate_interval: int = 50
+    surrogate_prob: float = 0.5
+    use_surrogate: bool = True
+    use_langevin: bool = False
+    learn_rate: float = 0.5
+    langevin_mode: str = "sgd_exact"   # or "batch" 
+    langevin_batch_scale: float = 1.0  # "sum": 1.0, "mean": 1/N
+    surrogate_topology: int = 1
+    seed: int = 1
+    step_w: float = 0.025              # _revamp.py:449
+    sigma_squared: float = 25.0        # _revamp.py:456
+    l_prob: float = 0.5                # LG:385
+    record_history: bool = True
+    record_pos: bool = True
+    train_cap: Optional[int] = None    # rows kept per chain per interval (default: the interval length)
+    path: int = _lib.PATH_AUTO
+    rank: int = 0
+    world: int = 1
+
+
+class Surrogate:
+    """Device copy of the global surrogate MLP + the de-normalisation constants the workers hold."""
+
+    def __init__(self, P: int, topology_id: int, device):
+        self.h1, self.h2 = SURROGATE_HIDDEN[int(topology_id)]
+        self.P = P
+        self.device = device
+        self.weights: Optional[Dict[str, torch.Tensor]] = None
+        self.min_y = 0.0
+        self.max_y = 0.0
+        self.signature = 0
+
+    def set_weights(self, w: Dict[str, np.ndarray]):
+        self.weights = {k: torch.as_tensor(np.ascontiguousarray(v, dtype=np.float32)).reshape(-1).to(self.device)
+                        for k, v in w.items()}
+
+    @property
+    def ready(self) -> bool:
+        return self.weights is not None
+
+
+class PTEngine:
+    def __init__(self, problem: Problem, temperatures, cfg: EngineConfig, inject: Optional[dict] = None,
+                 surrogate_trainer=None, process_group=None):
+        self.p = problem
+        self.cfg = cfg
+        self.spec = VARIANTS[cfg.variant]
+        self.dev = problem.device
+        self.L = _lib.lib()
+        self.Rg = int(len(temperatures))
+        assert self.Rg % cfg.world == 0, "num_chains must divide evenly over ranks"
+        self.R = self.Rg // cfg.world
+        self.row0 = cfg.rank * self.R
+        self.P = problem.P
+        self.ld = (self.P + 3) & ~3
+        self.pg = process_group
+        self.trainer = surrogate_trainer
+        S = cfg.samples
+        dev = self.dev
+        f64 = dict(dtype=torch.float64, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.theta = torch.zeros((self.R, self.ld), dtype=torch.float32, device=dev)
+        self.prop = torch.zeros_like(self.theta)
+        self.theta_gd = torch.zeros_like(self.theta) if cfg.use_langevin else None
+        self.T = torch.as_tensor(np.asarray(temperatures, dtype=np.float64)).to(dev)
+        self.lik_cur = torch.zeros(self.Rg, **f64)
+        self.lik_post = torch.zeros(self.Rg, **f64)
+        self.prior_cur = torch.zeros(self.Rg, **f64)
+        self.mov = torch.zeros((self.Rg, 3), **f64)
+        self.likl_wo_temp = torch.zeros(self.Rg, **f64)
+        self.last = torch.zeros((4, self.Rg), **f64)
+        self.naccept = torch.zeros(self.Rg, **i32)
+        self.slot_of_row = torch.arange(self.row0, self.row0 + self.R, **i32)
+        self.row_of_slot = torch.arange(self.Rg, **i32)
+        # per-row scratch
+        self.L_train = torch.zeros(self.R, **f64); self.nc_train = torch.zeros(self.R, **i32); self.sq_train = torch.zeros(self.R, **f64)
+        self.L_test = torch.zeros(self.R, **f64); self.nc_test = torch.zeros(self.R, **i32); self.sq_test = torch.zeros(self.R, **f64)
+        self.prior_prop = torch.zeros(self.R, **f64)
+        self.sur_s = torch.zeros(self.R, dtype=torch.float32, device=dev)
+        self.is_sur = torch.zeros(self.R, **i32)
+        self.surg_first = torch.zeros(self.R, **f64)
+        self.true_rows = torch.zeros(self.R, **i32); self.sur_rows = torch.zeros(self.R, **i32); self.lang_rows = torch.zeros(self.R, **i32)
+        self.counters = torch.zeros(4, **i32)  # n_true, n_sur, n_lang, num_swap
+        # history [S][Rg]
+        self.hist = None
+        if cfg.record_history:
+            self.hist = {k: torch.zeros((S, self.Rg), **f64) for k in
+                         ("lhood_list", "rmse_train", "rmse_test", "acc_train", "acc_test", "likeh", "accept_list")}
+            self.hist["surg"] = torch.zeros((S, self.Rg, 3), **f64)
+            self.hist["accepted"] = torch.zeros((S, self.Rg), dtype=torch.uint8, device=dev)
+            self.hist["is_sur"] = torch.zeros((S, self.Rg), dtype=torch.uint8, device=dev)
+            if cfg.record_pos:
+                self.hist["pos_w"] = torch.zeros((S, self.Rg, self.P), dtype=torch.float32, device=dev)
+        # surrogate
+        self.surrogate = Surrogate(self.P, cfg.surrogate_topology, dev)
+        self.sweep_count = 0
+        self.swap_log: List[torch.Tensor] = []
+        self.total_swap_proposals = 0
+        self.train_cap = 0
+        self.train_theta = self.train_L = self.train_count = None
+        if cfg.use_surrogate:
+            interval = cfg.swap_interval if self.spec.common_interval else cfg.surrogate_interval
+            self.train_cap = int(cfg.train_cap if cfg.train_cap is not None else min(interval + 1, S))
+            self.train_theta = torch.zeros((self.Rg, self.train_cap, self.P), dtype=torch.float32, device=dev)
+            self.train_L = torch.zeros((self.Rg, self.train_cap), **f64)
+            self.train_count = torch.zeros(self.Rg, **i32)
+        self.surr_batches: List[np.ndarray] = []
+        # injected streams (parity tests): numpy arrays indexed [step, chain(, P)]
+        self.inj = None
+        if inject is not None:
+            self.inj = {}
+            for k in ("z1", "z2"):
+                if inject.get(k) is not None:
+                    self.inj[k] = torch.as_tensor(np.ascontiguousarray(inject[k], dtype=np.float32)).to(dev)
+            for k in ("ku", "u", "lx2", "swap_u"):
+                if inject.get(k) is not None:
+                    self.inj[k] = torch.as_tensor(np.ascontiguousarray(inject[k], dtype=np.float64)).to(dev)
+            self.inj_weights = inject.get("surrogate_weights_per_signature")
+        self.flags = 0
+        sp = self.spec
+        if sp.post_tempered: self.flags |= _lib.F_POST_TEMPERED
+        if sp.take_post_lik: self.flags |= _lib.F_TAKE_POST_LIK
+        if sp.denorm_half_min: self.flags |= _lib.F_DENORM_HALF_MIN
+        if sp.compare_surrogate: self.flags |= _lib.F_COMPARE_SURROGATE
+        if sp.lg_flow: self.flags |= _lib.F_REDRAW_ON_SURROGATE
+        if cfg.record_history and cfg.record_pos: self.flags |= _lib.F_RECORD_POS
+        self.evals = 0  # replica x row likelihood evaluations issued (host-side count of the worst case)
+
+    # ------------------------------------------------------------------------------------
+    def _chain_state(self) -> _lib.ChainState:
+        st = _lib.ChainState()
+        st.slot_of_row = self.slot_of_row.data_ptr(); st.temperature = self.T.data_ptr()
+        st.lik_cur = self.lik_cur.data_ptr(); st.lik_post = self.lik_post.data_ptr(); st.prior_cur = self.prior_cur.data_ptr()
+        st.mov = self.mov.data_ptr(); st.likl_wo_temp = self.likl_wo_temp.data_ptr()
+        st.last_rmse_train = self.last[0].data_ptr(); st.last_rmse_test = self.last[1].data_ptr()
+        st.last_acc_train = self.last[2].data_ptr(); st.last_acc_test = self.last[3].data_ptr()
+        st.naccept = self.naccept.data_ptr()
+        return st
+
+    def _history(self) -> _lib.History:
+        h = _lib.History()
+        h.n_slots = self.Rg
+        if self.hist is not None:
+            for k in ("lhood_list", "rmse_train", "rmse_test", "acc_train", "acc_test", "surg", "likeh", "accept_list", "accepted", "is_sur"):
+                setattr(h, k, self.hist[k].data_ptr())
+            if "pos_w" in self.hist:
+                h.pos_w = self.hist["pos_w"].data_ptr()
+        return h
+
+    def _inj(self, key, step):
+        if self.inj is None or key not in self.inj:
+            return None
+        return self.inj[key][step]
+
+    # ------------------------------------------------------------------------------------
+    def initialize(self, w0):
+        """All chains start from the same w (_revamp.py:940-943); initial likelihood/prior as in
+        ptReplica.run before the loop (_revamp.py:452-468)."""
+        w0 = torch.as_tensor(np.asarray(w0, dtype=np.float32)).to(self.dev)
+        self.theta.zero_()
+        self.theta[:, : self.P] = w0[None, :]
+        self.prop.copy_(self.theta)
+        Ltr, _, _ = self.p.loglik(self.theta, 0, path=self.cfg.path)
+        Lte = None
+        if self.p.n[1] > 0:
+            Lte, _, _ = self.p.loglik(self.theta, 1, path=self.cfg.path)
+        pr = torch.empty(self.R, dtype=torch.float64, device=self.dev)
+        _lib.check(self.L.sapt_prior(_ptr(self.theta), self.ld, self.R, self.P, self.cfg.sigma_squared, _ptr(pr), current_stream_ptr()))
+        slots = self.slot_of_row.long()
+        lik = Ltr / self.T[slots]
+        self.lik_cur[slots] = lik
+        self.lik_post[slots] = lik
+        self.prior_cur[slots] = pr
+        # `likl_without_temp` is overwritten by the TEST-set call during initialisation (RW:466-467)
+        self.likl_wo_temp[slots] = Lte if Lte is not None else Ltr
+        if self.hist is not None:
+            self.hist["likeh"][0].fill_(-100.0)  # RW:473
+            if "pos_w" in self.hist:
+                self.hist["pos_w"][0].fill_(1.0)  # pos_w = np.ones (RW:431)
+
+    # ------------------------------------------------------------------------------------
+    def step(self, i: int):
+        cfg, sp, L = self.cfg, self.spec, self.L
+        st = current_stream_ptr()
+        use_sur = bool(cfg.use_surrogate)
+        self.counters[:3].zero_()
+        gate = cfg.swap_interval if sp.gate_on_swap_interval else cfg.surrogate_interval
+        a = _lib.ProposeArgs()
+        a.base = self.theta.data_ptr(); a.proposal = self.prop.data_ptr(); a.ld = self.ld; a.R = self.R; a.P = self.P
+        a.slot_of_row = self.slot_of_row.data_ptr(); a.slot_offset = 0
+        a.step_w = cfg.step_w; a.sigma_squared = cfg.sigma_squared; a.prior_prop = self.prior_prop.data_ptr()
+        a.seed = cfg.seed & 0xFFFFFFFF; a.kind = _lib.STREAM_Z1; a.step = i
+        z1 = self._inj("z1", i); a.z_inject = z1.data_ptr() if z1 is not None else None
+        a.decide = 1 if use_sur else 0
+        a.redraw = 1 if sp.lg_flow else 0
+        a.surrogate_ready = 1 if self.surrogate.ready else 0
+        a.surrogate_prob = cfg.surrogate_prob; a.gate = gate
+        z2 = self._inj("z2", i); a.z2_inject = z2.data_ptr() if z2 is not None else None
+        ku = self._inj("ku", i); a.ku_inject = ku.data_ptr() if ku is not None else None
+        a.is_sur = self.is_sur.data_ptr(); a.true_rows = self.true_rows.data_ptr(); a.n_true = self.counters[0:1].data_ptr()
+        a.sur_rows = self.sur_rows.data_ptr(); a.n_sur = self.counters[1:2].data_ptr()
+        _lib.check(L.sapt_propose(C.byref(a), st), "sapt_propose")
+
+        sur_possible = use_sur and self.surrogate.ready and i >= gate + 1 and cfg.surrogate_prob > 0
+        true_rows = self.true_rows if use_sur else None
+        n_true = self.counters[0:1] if use_sur else None
+        if sur_possible:
+            w = self.surrogate.weights
+            _lib.check(L.sapt_surrogate_predict(_ptr(self.prop), self.ld, self.R, self.P, _ptr(self.sur_rows), _ptr(self.counters[1:2]),
+                                                _ptr(w["W1"]), _ptr(w["b1"]), self.surrogate.h1, _ptr(w["W2"]), _ptr(w["b2"]),
+                                                self.surrogate.h2, _ptr(w["W3"]), _ptr(w["b3"]), _ptr(self.sur_s), st), "sapt_surrogate_predict")
+        out_tr = (self.L_train, self.nc_train, self.sq_train)
+        out_te = (self.L_test, self.nc_test, self.sq_test)
+        ntr, nte = self.p.n
+        if sp.lg_flow:
+            self.p.loglik(self.prop, 0, rows=true_rows, n_rows=n_true, out=out_tr, path=cfg.path)
+            f = _lib.LgFirstArgs()
+            f.proposal = self.prop.data_ptr(); f.ld = self.ld; f.R = self.R; f.P = self.P
+            f.st = self._chain_state(); f.step = i; f.seed = cfg.seed & 0xFFFFFFFF
+            f.true_rows = _ptr(true_rows); f.n_true = _ptr(n_true)
+            f.L_train = self.L_train.data_ptr(); f.surg_first = self.surg_first.data_ptr()
+            f.use_langevin = 1 if cfg.use_langevin else 0; f.l_prob = cfg.l_prob
+            lx2 = self._inj("lx2", i); f.lx2_inject = lx2.data_ptr() if lx2 is not None else None
+            f.lang_rows = self.lang_rows.data_ptr(); f.n_lang = self.counters[2:3].data_ptr()
+            if self.train_theta is not None:
+                f.train_theta = self.train_theta.data_ptr(); f.train_L = self.train_L.data_ptr()
+                f.train_count = self.train_count.data_ptr(); f.train_cap = self.train_cap
+            _lib.check(L.sapt_lg_first_eval(C.byref(f), st), "sapt_lg_first_eval")
+            self.evals += self.R * ntr
+            if cfg.use_langevin:
+                mode = 0 if cfg.langevin_mode == "sgd_exact" else 1
+                # Eq. 8: w_gd = langevin_gradient(w) (LG:650); the second call on w_proposal (LG:652) only
+                # feeds diff_prop, which never reaches the MH ratio (LG:665-668 vs 687-691) and is skipped.
+                self.p.langevin(self.theta, cfg.learn_rate, mode, cfg.langevin_batch_scale, rows=self.lang_rows,
+                                n_rows=self.counters[2:3], out=self.theta_gd)
+                b = _lib.ProposeArgs()
+                b.base = self.theta_gd.data_ptr(); b.proposal = self.prop.data_ptr(); b.ld = self.ld; b.R = self.R; b.P = self.P
+                b.slot_of_row = self.slot_of_row.data_ptr(); b.rows = self.lang_rows.data_ptr(); b.n_rows = self.counters[2:3].data_ptr()
+                b.step_w = cfg.step_w; b.sigma_squared = cfg.sigma_squared; b.prior_prop = self.prior_prop.data_ptr()
+                b.seed = cfg.seed & 0xFFFFFFFF; b.kind = _lib.STREAM_Z2; b.step = i
+                b.z_inject = z2.data_ptr() if z2 is not None else None
+                b.decide = 0
+                _lib.check(L.sapt_propose(C.byref(b), st), "sapt_propose(langevin)")
+                # LG:676 re-evaluates every true row; only the Langevin rows have a new proposal, the
+                # others would reproduce the first evaluation bit for bit.
+                self.p.loglik(self.prop, 0, rows=self.lang_rows, n_rows=self.counters[2:3], out=out_tr, path=cfg.path)
+                self.evals += self.R * ntr // 2
+            if nte > 0:
+                self.p.loglik(self.prop, 1, rows=true_rows, n_rows=n_true, out=out_te, path=cfg.path)
+                self.evals += self.R * nte
+        else:
+            if sp.compare_surrogate or not use_sur:
+                self.p.loglik(self.prop, 0, out=out_tr, path=cfg.path)   # RV:543-544: train set on every step
+            else:
+                self.p.loglik(self.prop, 0, rows=true_rows, n_rows=n_true, out=out_tr, path=cfg.path)
+            self.evals += self.R * ntr
+            if nte > 0:
+                self.p.loglik(self.prop, 1, rows=true_rows, n_rows=n_true, out=out_te, path=cfg.path)
+                self.evals += self.R * nte
+
+        m = _lib.AcceptArgs()
+        m.theta = self.theta.data_ptr(); m.proposal = self.prop.data_ptr(); m.ld = self.ld; m.R = self.R; m.P = self.P
+        m.st = self._chain_state(); m.hist = self._history(); m.step = i; m.flags = self.flags
+        m.is_sur = self.is_sur.data_ptr() if use_sur else None
+        m.L_train = self.L_train.data_ptr(); m.nc_train = self.nc_train.data_ptr(); m.sq_train = self.sq_train.data_ptr()
+        m.L_test = self.L_test.data_ptr(); m.nc_test = self.nc_test.data_ptr(); m.sq_test = self.sq_test.data_ptr()
+        m.n_train = ntr; m.n_test = nte
+        m.prior_prop = self.prior_prop.data_ptr(); m.sur_s = self.sur_s.data_ptr()
+        m.min_y = self.surrogate.min_y; m.max_y = self.surrogate.max_y
+        m.seed = cfg.seed & 0xFFFFFFFF
+        u = self._inj("u", i); m.u_inject = u.data_ptr() if u is not None else None
+        if self.train_theta is not None:
+            m.train_theta = self.train_theta.data_ptr(); m.train_L = self.train_L.data_ptr()
+            m.train_count = self.train_count.data_ptr(); m.train_cap = self.train_cap
+        m.capture = 0 if sp.lg_flow else 1
+        m.surg_first = self.surg_first.data_ptr() if sp.lg_flow else None
+        _lib.check(L.sapt_mh_accept(C.byref(m), st), "sapt_mh_accept")
+
+    # ------------------------------------------------------------------------------------
+    def _hosted_mask(self):
+        mask = torch.zeros(self.Rg, dtype=torch.float64, device=self.dev)
+        mask[self.slot_of_row.long()] = 1.0
+        return mask
+
+    def sync_slots(self):
+        """Masked all-reduce of the per-chain scalars: every rank contributes the slots its rows host."""
+        if self.cfg.world == 1:
+            return
+        import torch.distributed as dist
+        mask = self._hosted_mask()
+        pack = torch.cat([self.lik_cur[None], self.lik_post[None], self.prior_cur[None], self.likl_wo_temp[None], self.last,
+                          self.mov.t(), self.naccept.double()[None]], dim=0)
+        pack = torch.where(mask[None, :] > 0, pack, torch.zeros_like(pack))
+        cnt = self.train_count.double() * mask if self.train_count is not None else None
+        dist.all_reduce(pack, group=self.pg)
+        self.lik_cur.copy_(pack[0]); self.lik_post.copy_(pack[1]); self.prior_cur.copy_(pack[2]); self.likl_wo_temp.copy_(pack[3])
+        self.last.copy_(pack[4:8]); self.mov.copy_(pack[8:11].t()); self.naccept.copy_(pack[11].round().to(torch.int32))
+
+    def swap(self, i: int):
+        """Replica exchange at a rendezvous (RW:1095-1099)."""
+        if self.Rg < 2:
+            return
+        self.sync_slots()
+        u = None
+        if self.inj is not None and "swap_u" in self.inj:
+            u = self.inj["swap_u"][self.sweep_count]
+        swapped = torch.zeros(self.Rg - 1, dtype=torch.uint8, device=self.dev)
+        _lib.check(self.L.sapt_swap_sweep(self.Rg, _ptr(self.lik_post), _ptr(self.T), _ptr(self.row_of_slot), self.flags,
+                                          self.cfg.seed & 0xFFFFFFFF, self.sweep_count, _ptr(u), _ptr(swapped),
+                                          _ptr(self.counters[3:4]), None, self.row0, self.R, _ptr(self.slot_of_row),
+                                          current_stream_ptr()), "sapt_swap_sweep")
+        self.swap_log.append(swapped)
+        self.sweep_count += 1
+        self.total_swap_proposals += self.Rg - 1
+
+    def gather_training_rows(self):
+        """(theta', L_untempered) rows of the interval's true steps, chain by chain (RW:1105-1116)."""
+        cnt = self.train_count
+        th, tl = self.train_theta, self.train_L
+        if self.cfg.world > 1:
+            import torch.distributed as dist
+            mask = self._hosted_mask()
+            cnt = (cnt.double() * mask)
+            th = th * mask[:, None, None].float(); tl = tl * mask[:, None]
+            dist.all_reduce(cnt, group=self.pg); dist.all_reduce(th, group=self.pg); dist.all_reduce(tl, group=self.pg)
+            cnt = cnt.round().to(torch.int32)
+        cnt_h = cnt.cpu().numpy()
+        th_h = th.cpu().numpy().astype(np.float64); tl_h = tl.cpu().numpy()
+        rows = []
+        for s in range(self.Rg):
+            n = int(cnt_h[s])
+            blk = np.concatenate([th_h[s, :n], tl_h[s, :n, None]], axis=1)
+            if self.spec.ship_zero_row:
+                blk = np.vstack([np.zeros((1, self.P + 1)), blk])
+            rows.append(blk)
+        self.train_count.zero_()
+        return np.concatenate(rows, axis=0) if rows else np.zeros((0, self.P + 1))
+
+    def surrogate_rendezvous(self, i: int):
+        batch = self.gather_training_rows()
+        self.surr_batches.append(batch)
+        if batch.shape[0] == 0:
+            return
+        sur = self.surrogate
+        sur.signature += 1
+        Y = batch[:, self.P]
+        if sur.signature == 1:  # minmax.txt is written once and read once (RV:996-997, RV:707-710)
+            sur.min_y = float(np.min(Y) * 2)
+            sur.max_y = -1.0
+        if self.inj is not None and self.inj_weights is not None:
+            sur.set_weights(self.inj_weights[sur.signature - 1])
+        elif self.trainer is not None:
+            w = self.trainer(batch, sur.signature)
+            if w is not None:
+                sur.set_weights(w)
+
+    def rendezvous(self, i: int):
+        cfg, sp = self.cfg, self.spec
+        do_swap = sp.swap and (i % cfg.swap_interval == 0) and (sp.swap_at_zero or i != 0)
+        if sp.common_interval:
+            do_train = do_swap and cfg.use_surrogate
+        else:
+            do_train = cfg.use_surrogate and (i % cfg.surrogate_interval == 0) and (i != 0)
+        if do_swap:
+            self.swap(i)
+        if do_train:
+            self.surrogate_rendezvous(i)
+
+    def run(self, steps: Optional[int] = None):
+        n = self.cfg.samples - 1 if steps is None else steps
+        for i in range(n):
+            self.step(i)
+            self.rendezvous(i)
+
+    # ------------------------------------------------------------------------------------
+    def results(self) -> dict:
+        """Histories as numpy arrays shaped like the reference's per-chain arrays ([chain, sample...])."""
+        self.sync_slots()
+        out = {}
+        if self.hist is not None:
+            hist = self.hist
+            if self.cfg.world > 1:
+                import torch.distributed as dist
+                hist = {}
+                for k, v in self.hist.items():
+                    t = v.clone() if v.dtype != torch.uint8 else v.to(torch.int32)
+                    dist.all_reduce(t, group=self.pg)
+                    hist[k] = t
+                hist["likeh"][0].fill_(-100.0)
+                if "pos_w" in hist:
+                    hist["pos_w"][0].fill_(1.0)
+            for k in ("lhood_list", "rmse_train", "rmse_test", "acc_train", "acc_test", "accept_list"):
+                out[k] = hist[k].t().cpu().numpy()
+            out["surg_likeh_list"] = hist["surg"].permute(1, 0, 2).cpu().numpy()
+            lk = np.zeros((self.Rg, self.cfg.samples, 2)); lk[:, 0, :] = -100
+            lk[:, :, 0] = hist["likeh"].t().cpu().numpy()
+            out["likeh_list"] = lk
+            out["accepted"] = hist["accepted"].t().cpu().numpy().astype(bool)
+            out["is_surrogate_step"] = hist["is_sur"].t().cpu().numpy().astype(bool)
+            if "pos_w" in hist:
+                out["pos_w"] = hist["pos_w"].permute(1, 0, 2).cpu().numpy().astype(np.float64)
+        out["naccept"] = self.naccept.cpu().numpy()
+        out["swap_decisions"] = [s.cpu().numpy().astype(bool) for s in self.swap_log]
+        out["num_swap"] = int(self.counters[3].item())
+        out["total_swap_proposals"] = self.total_swap_proposals
+        out["surr_batches"] = self.surr_batches
+        out["min_y"] = self.surrogate.min_y; out["max_y"] = self.surrogate.max_y; out["signature"] = self.surrogate.signature
+        out["row_of_slot"] = self.row_of_slot.cpu().numpy()
+        out["likelihood"] = self.lik_post.cpu().numpy(); out["likelihood_copy"] = self.lik_cur.cpu().numpy()
+        out["prior_current"] = self.prior_cur.cpu().numpy()
+        return out
+
+    def current_w(self) -> np.ndarray:
+        """[chain, P] parameter vector each chain currently holds (single rank)."""
+        th = self.theta[:, : self.P].cpu().numpy().astype(np.float64)
+        ros = self.row_of_slot.cpu().numpy()
+        return th[ros - self.row0] if self.cfg.world == 1 else th

@@ -1,0 +1,319 @@
+"""GPU parity tests: every C-ABI entry point against the oracle / the reference-generated golden
+fixtures on identical inputs, through libsapt.so. Run on the B200 box with `-m gpu`.
+
+Tolerances (BASELINE.json north_star): per-proposal log-likelihoods and gradients within 1e-4
+relative of the fp64 reference (we assert tighter where fp32 allows); accept/reject and swap
+decisions identical; class predictions / integer counts exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from oracle import sapt_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from sapt_b200 import _lib
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return _lib
+
+
+def _paths(lib, prob):
+    return [lib.PATH_F32] + ([lib.PATH_TC] if prob.tc_supported else [])
+
+
+@pytest.mark.parametrize("problem", ["cancer", "ions", "pendigit"])
+def test_loglik_matches_reference(lib, problem):
+    from sapt_b200.problem import Problem
+    g = gu.load(f"unit_{problem}")
+    topo = [int(v) for v in g["topology"]]
+    prob = Problem(topo, g["train"], g["test"])
+    theta = torch.as_tensor(g["W"].astype(np.float32)).cuda()
+    # the device sees fp32-rounded parameters: compare with the oracle on the SAME rounded inputs
+    W32 = g["W"].astype(np.float32).astype(np.float64)
+    for path in _paths(lib, prob):
+        for which, name in ((0, "train"), (1, "test")):
+            L, nc, sq = prob.loglik(theta, which, path=path)
+            torch.cuda.synchronize()
+            data = g[name]
+            ref = [so.loglik_stats(data, W32[k], topo) for k in range(W32.shape[0])]
+            refL = np.array([r[0] for r in ref])
+            np.testing.assert_allclose(L.cpu().numpy(), refL, rtol=2e-6, err_msg=f"path {path} {name}")
+            np.testing.assert_allclose(L.cpu().numpy(), g[f"L_{name}"], rtol=1e-4)          # vs the reference itself (fp64 inputs)
+            assert np.array_equal(nc.cpu().numpy(), np.array([r[1] for r in ref])), f"ncorrect path {path}"
+            assert np.array_equal(sq.cpu().numpy(), np.array([r[2] for r in ref])), f"sqerr path {path}"
+            rm = np.sqrt(sq.cpu().numpy() / data.shape[0])
+            np.testing.assert_allclose(rm, g[f"rmse_{name}"], rtol=1e-12)
+
+
+def test_loglik_row_subset_and_ragged_sizes(lib):
+    """active-row lists, non-multiple-of-tile row counts, a single row, a single chain."""
+    from sapt_b200.problem import Problem
+    g = gu.load("unit_cancer")
+    topo = [int(v) for v in g["topology"]]
+    W = g["W"].astype(np.float32)
+    for n in (1, 2, 127, 128, 129, 257, 489):
+        prob = Problem(topo, g["train"][:n], None)
+        theta = torch.as_tensor(W).cuda()
+        for path in _paths(lib, prob):
+            L, nc, sq = prob.loglik(theta, 0, path=path)
+            ref = np.array([so.loglik_stats(g["train"][:n], W[k].astype(np.float64), topo)[0] for k in range(W.shape[0])])
+            np.testing.assert_allclose(L.cpu().numpy(), ref, rtol=3e-6, atol=1e-6, err_msg=f"n={n} path={path}")
+    prob = Problem(topo, g["train"], g["test"])
+    theta = torch.as_tensor(W).cuda()
+    rows = torch.tensor([4, 1, 0, 0, 0, 0], dtype=torch.int32).cuda()
+    n_rows = torch.tensor([2], dtype=torch.int32).cuda()
+    for path in _paths(lib, prob):
+        out = (torch.full((6,), 7.0, dtype=torch.float64).cuda(), torch.full((6,), 7, dtype=torch.int32).cuda(),
+               torch.full((6,), 7.0, dtype=torch.float64).cuda())
+        prob.loglik(theta, 0, rows=rows, n_rows=n_rows, out=out, path=path)
+        L = out[0].cpu().numpy()
+        assert L[0] == 7.0 and L[2] == 7.0 and L[3] == 7.0 and L[5] == 7.0      # untouched
+        np.testing.assert_allclose(L[[4, 1]], g["L_train"][[4, 1]], rtol=1e-4)
+
+
+def test_evaluate_proposal_rows(lib):
+    from sapt_b200 import Network
+    g = gu.load("unit_pendigit")
+    topo = [int(v) for v in g["topology"]]
+    net = Network(topo, g["train"], g["test"], 0.5)
+    for k in (0, 3):
+        fx, prob = net.evaluate_proposal(g["train"], g["W"][k])
+        ref_fx, ref_prob = so.evaluate_proposal(g["train"], g["W"][k].astype(np.float32).astype(np.float64), topo)
+        assert np.mean(fx == ref_fx) == 1.0
+        np.testing.assert_allclose(prob, ref_prob, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(prob, g["prob_train"][k], rtol=0, atol=1e-5)
+
+
+def test_reference_surface_likelihood_func_and_prior(lib):
+    from sapt_b200 import Network, ptReplica
+    g = gu.load("unit_cancer")
+    topo = [int(v) for v in g["topology"]]
+    net = Network(topo, g["train"], g["test"], 0.5)
+    for k in range(3):
+        rep = ptReplica(topo, float(g["temps"][k]))
+        lt, fx, rm, l = rep.likelihood_func(net, g["train"], g["W"][k])
+        np.testing.assert_allclose(l, g["L_train"][k], rtol=1e-4)
+        np.testing.assert_allclose(lt, g["Ltemp_train"][k], rtol=1e-4)
+        assert np.array_equal(fx, g["fx_train"][k])
+        np.testing.assert_allclose(rm, g["rmse_train"][k], rtol=1e-12)
+        assert rep.accuracy(fx, g["train"][:, topo[0]]) == g["acc_train"][k]
+        np.testing.assert_allclose(rep.prior_likelihood(25, 0, 0, g["W"][k]), g["prior"][k], rtol=1e-6)
+
+
+@pytest.mark.parametrize("problem", ["cancer", "ions", "pendigit"])
+def test_langevin_sgd_exact(lib, problem):
+    from sapt_b200.problem import Problem
+    g = gu.load(f"unit_{problem}")
+    topo = [int(v) for v in g["topology"]]
+    n = int(g["langevin_rows"])
+    prob = Problem(topo, g["train"][:n], None)
+    theta = torch.as_tensor(g["W"].astype(np.float32)).cuda()
+    for li, lr in enumerate(g["langevin_lr"]):
+        out = prob.langevin(theta, float(lr), mode=0).cpu().numpy().astype(np.float64)
+        ref = g["langevin_out"][li]
+        # 1e-4 relative on the parameter vector (fp32 in/out, fp64 recurrence on the device)
+        assert np.max(np.abs(out - ref)) <= 1e-4 * np.max(np.abs(ref)) + 1e-6, (problem, lr, np.max(np.abs(out - ref)))
+        ref32 = np.array([so.langevin_gradient(g["train"][:n], g["W"][k].astype(np.float32).astype(np.float64), topo, float(lr), 1)
+                          for k in range(theta.shape[0])])
+        np.testing.assert_allclose(out, ref32, rtol=0, atol=2e-6 * max(1.0, np.max(np.abs(ref32))))
+
+
+def test_langevin_batch_gradient(lib):
+    from sapt_b200.problem import Problem
+    g = gu.load("unit_cancer")
+    topo = [int(v) for v in g["topology"]]
+    prob = Problem(topo, g["train"], None)
+    W = g["W"].astype(np.float32)
+    theta = torch.as_tensor(W).cuda()
+    lr = 0.01
+    out = prob.langevin(theta, lr, mode=1, batch_scale=1.0).cpu().numpy().astype(np.float64)
+    for k in range(W.shape[0]):
+        grad = so.langevin_batch_gradient(g["train"], W[k].astype(np.float64), topo)
+        got = (out[k] - W[k].astype(np.float64)) / lr
+        assert np.max(np.abs(got - grad)) <= 1e-4 * np.max(np.abs(grad)) + 1e-4, k
+
+
+def test_swap_sweep_matches_reference(lib):
+    g = gu.load("swap_ladder")
+    L = lib.lib()
+    for n in range(int(g["n_swap_cases"])):
+        lik = g[f"swap{n}_lik"]; u = g[f"swap{n}_u"]; R = len(lik)
+        lik_d = torch.as_tensor(lik.copy()).cuda(); T = torch.ones(R, dtype=torch.float64).cuda()
+        ros = torch.arange(R, dtype=torch.int32).cuda(); u_d = torch.as_tensor(u.copy()).cuda()
+        sw = torch.zeros(R - 1, dtype=torch.uint8).cuda(); ns = torch.zeros(1, dtype=torch.int32).cuda()
+        src = torch.zeros(R, dtype=torch.int32).cuda(); sor = torch.zeros(R, dtype=torch.int32).cuda()
+        lib.check(L.sapt_swap_sweep(R, lik_d.data_ptr(), T.data_ptr(), ros.data_ptr(), 0, 1, 0, u_d.data_ptr(), sw.data_ptr(),
+                                    ns.data_ptr(), src.data_ptr(), 0, R, sor.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(src.cpu().numpy(), g[f"swap{n}_src"])
+        assert np.array_equal(sw.cpu().numpy().astype(bool), g[f"swap{n}_swapped"])
+        assert int(ns.item()) == int(g[f"swap{n}_num_swap"])
+        assert np.array_equal(ros.cpu().numpy(), g[f"swap{n}_src"])          # identity binding before -> rows follow src
+        inv = np.empty(R, dtype=np.int64); inv[g[f"swap{n}_src"]] = np.arange(R)
+        assert np.array_equal(sor.cpu().numpy(), inv)
+
+
+def test_philox_device_matches_oracle(lib):
+    L = lib.lib()
+    n = 1003
+    for kind, step, chain in ((0, 0, 0), (5, 17, 3), (1, 123456, 1023)):
+        out = torch.zeros(n, dtype=torch.float32).cuda()
+        lib.check(L.sapt_philox_fill(99, kind, step, chain, n, 0, out.data_ptr(), None))
+        ref = so.philox_uniform(99, kind, step, np.full(n, chain), np.arange(n))
+        assert np.array_equal(out.cpu().numpy(), ref)                         # integer stage + conversion: bit exact
+        lib.check(L.sapt_philox_fill(99, kind, step, chain, n, 1, out.data_ptr(), None))
+        refz = so.philox_normal(99, kind, step, chain, n)
+        np.testing.assert_allclose(out.cpu().numpy(), refz, rtol=0, atol=2e-5)
+    z = torch.zeros(1 << 20, dtype=torch.float32).cuda()
+    lib.check(L.sapt_philox_fill(5, 0, 0, 0, 1 << 20, 1, z.data_ptr(), None))
+    zz = z.cpu().numpy().astype(np.float64)
+    assert abs(zz.mean()) < 5e-3 and abs(zz.std() - 1) < 5e-3 and abs((zz ** 4).mean() - 3) < 0.05
+
+
+@pytest.mark.parametrize("topology_id,P", [(1, 146), (3, 820)])
+def test_surrogate_predict(lib, topology_id, P):
+    L = lib.lib()
+    w = so.make_surrogate_weights(P, topology_id, 5, scale=0.2)
+    rs = np.random.RandomState(3)
+    R = 37
+    theta = rs.randn(R, P).astype(np.float32)
+    th = torch.as_tensor(theta).cuda()
+    wd = {k: torch.as_tensor(v.reshape(-1).copy()).cuda() for k, v in w.items()}
+    h1, h2 = so.SURROGATE_HIDDEN[topology_id]
+    s = torch.full((R,), -1.0, dtype=torch.float32).cuda()
+    rows = torch.tensor(sorted(rs.choice(R, 20, replace=False)), dtype=torch.int32).cuda()
+    n_rows = torch.tensor([20], dtype=torch.int32).cuda()
+    lib.check(L.sapt_surrogate_predict(th.data_ptr(), P, R, P, rows.data_ptr(), n_rows.data_ptr(), wd["W1"].data_ptr(), wd["b1"].data_ptr(), h1,
+                                       wd["W2"].data_ptr(), wd["b2"].data_ptr(), h2, wd["W3"].data_ptr(), wd["b3"].data_ptr(), s.data_ptr(), None))
+    ref = so.surrogate_forward(theta, w)
+    got = s.cpu().numpy()
+    idx = rows.cpu().numpy()
+    np.testing.assert_allclose(got[idx], ref[idx], rtol=2e-5, atol=1e-6)
+    assert np.all(got[np.setdiff1d(np.arange(R), idx)] == -1.0)
+
+
+@pytest.mark.parametrize("name", list(gu.RUNS))
+@pytest.mark.parametrize("path_name", ["f32", "auto"])
+def test_full_run_matches_reference_traces(lib, name, path_name):
+    """R chains x S steps with the reference's recorded random streams injected: every
+    accept/reject, swap decision, surrogate/true branch and Langevin coin must match the trace of
+    the unmodified reference; recorded scalars within fp32 tolerance."""
+    from sapt_b200.engine import EngineConfig, PTEngine
+    from sapt_b200.problem import Problem
+    g = gu.load(name)
+    kw = gu.run_inputs(g)
+    variant = gu.RUNS[name]
+    path = lib.PATH_F32 if path_name == "f32" else lib.PATH_AUTO
+    prob = Problem(kw["topology"], kw["traindata"], kw["testdata"], path=path)
+    if path_name == "auto" and not prob.tc_supported:
+        pytest.skip("tcgen05 path does not cover this topology")
+    cfg = EngineConfig(variant=variant, samples=kw["samples"], swap_interval=kw["swap_interval"],
+                       surrogate_interval=kw["surrogate_interval"], surrogate_prob=kw["surrogate_prob"], use_surrogate=True,
+                       use_langevin=kw["use_langevin"], learn_rate=kw["learn_rate"], surrogate_topology=int(g["surrogate_topology"]),
+                       seed=1, record_history=True, record_pos=True, path=path)
+    st = kw["streams"]
+    inject = dict(z1=st.z1, z2=st.z2, lx2=st.lx2, ku=st.ku, u=st.u, swap_u=st.swap_u,
+                  surrogate_weights_per_signature=kw["surrogate_weights_per_signature"])
+    eng = PTEngine(prob, kw["temperatures"], cfg, inject=inject)
+    eng.initialize(kw["w0"])
+    eng.run()
+    torch.cuda.synchronize()
+    res = eng.results()
+    ora = so.run_pt(variant, **kw)
+    assert np.array_equal(res["accepted"], ora["accepted"]), "accept/reject decisions differ"
+    assert np.array_equal(res["is_surrogate_step"], ora["is_surrogate_step"])
+    assert np.array_equal(res["accept_list"], g["trace_accept_list"])
+    assert len(res["swap_decisions"]) == len(ora["swap_decisions"])
+    for a, b in zip(res["swap_decisions"], ora["swap_decisions"]):
+        assert np.array_equal(a, b), "swap decisions differ"
+    assert res["num_swap"] == ora["num_swap"]
+    np.testing.assert_allclose(res["pos_w"], g["trace_pos_w"], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(eng.current_w(), ora["w_final"], rtol=0, atol=5e-6)
+    # integer-derived metrics: exact
+    for k in ("acc_train", "acc_test", "rmse_train", "rmse_test"):
+        a, b = res[k], g["trace_" + k]
+        assert np.array_equal(np.isinf(a), np.isinf(b)), k
+        m = np.isfinite(b)
+        np.testing.assert_allclose(a[m], b[m], rtol=1e-12, atol=0, err_msg=k)
+    gu.compare_traces(g, res, rtol=2e-5, atol=2e-4, keys=("surg_likeh_list", "likeh_list"))
+    for s, b in enumerate(res["surr_batches"]):
+        np.testing.assert_allclose(b, g[f"trainer_batch_{s}"], rtol=2e-5, atol=2e-4)
+    np.testing.assert_allclose(res["min_y"], float(g["min_y"]), rtol=1e-5)
+
+
+def test_large_shape_properties(lib):
+    """C3-shape (16-30-10) at a size the oracle cannot finish: size-independent properties.
+    (1) identical chains give identical L; (2) L is additive over a split of the rows;
+    (3) row order does not matter beyond fp64 summation noise; (4) both kernel paths agree."""
+    from sapt_b200.problem import Problem
+    rs = np.random.RandomState(0)
+    n, D, H, O, R = 200_000, 16, 30, 10, 64
+    x = rs.standard_normal((n, D)).astype(np.float32); y = rs.randint(0, O, n).astype(np.int32)
+    P = D * H + H * O + H + O
+    W = (rs.standard_normal((R, P)) * 0.5).astype(np.float32)
+    W[1] = W[0]
+    th = torch.as_tensor(W).cuda()
+    full = Problem.from_f32([D, H, O], x, y)
+    a = Problem.from_f32([D, H, O], x[:70_001], y[:70_001]); b = Problem.from_f32([D, H, O], x[70_001:], y[70_001:])
+    perm = rs.permutation(n)
+    shuf = Problem.from_f32([D, H, O], x[perm], y[perm])
+    results = {}
+    for path in _paths(lib, full):
+        L, nc, sq = (t.cpu().numpy() for t in full.loglik(th, 0, path=path))
+        assert L[0] == L[1] and nc[0] == nc[1]
+        La, nca, sqa = (t.cpu().numpy() for t in a.loglik(th, 0, path=path))
+        Lb, ncb, sqb = (t.cpu().numpy() for t in b.loglik(th, 0, path=path))
+        np.testing.assert_allclose(La + Lb, L, rtol=1e-12)
+        assert np.array_equal(nca + ncb, nc) and np.array_equal(sqa + sqb, sq)
+        Ls, ncs, sqs = (t.cpu().numpy() for t in shuf.loglik(th, 0, path=path))
+        np.testing.assert_allclose(Ls, L, rtol=1e-11)
+        assert np.array_equal(ncs, nc)
+        results[path] = (L, nc)
+        # spot-check a few chains against the oracle on a 20k-row slice
+    if len(results) == 2:
+        (L1, n1), (L2, n2) = results.values()
+        np.testing.assert_allclose(L1, L2, rtol=2e-6)
+        assert np.mean(n1 == n2) > 0.9
+    sub = Problem.from_f32([D, H, O], x[:20_000], y[:20_000])
+    data = np.concatenate([x[:20_000].astype(np.float64), y[:20_000, None].astype(np.float64)], axis=1)
+    for path in _paths(lib, sub):
+        L, nc, sq = (t.cpu().numpy() for t in sub.loglik(th[:4], 0, path=path))
+        for k in range(4):
+            rl, rn, rq = so.loglik_stats(data, W[k].astype(np.float64), [D, H, O])
+            np.testing.assert_allclose(L[k], rl, rtol=2e-6)
+            assert abs(int(nc[k]) - rn) <= 2          # fp32 argmax can differ from fp64 on exact near-ties
+
+
+def test_engine_philox_run_is_deterministic_and_sane(lib):
+    """In-kernel RNG: same seed -> bit-identical chains; different seed -> different; chains move."""
+    from sapt_b200.engine import EngineConfig, PTEngine
+    from sapt_b200.ladder import assign_temperatures
+    from sapt_b200.problem import Problem
+    g = gu.load("unit_cancer")
+    topo = [int(v) for v in g["topology"]]
+    prob = Problem(topo, g["train"], g["test"])
+
+    def run(seed):
+        cfg = EngineConfig(variant="rw", samples=40, swap_interval=5, surrogate_interval=5, surrogate_prob=0.0,
+                           use_surrogate=False, seed=seed)
+        eng = PTEngine(prob, assign_temperatures(8, 4.0), cfg)
+        eng.initialize(g["W"][0])
+        eng.run(); torch.cuda.synchronize()
+        return eng.results()
+
+    r1, r2, r3 = run(11), run(11), run(12)
+    assert np.array_equal(r1["pos_w"], r2["pos_w"]) and np.array_equal(r1["accepted"], r2["accepted"])
+    assert not np.array_equal(r1["pos_w"], r3["pos_w"])
+    assert r1["naccept"].sum() > 0 and r1["total_swap_proposals"] == 7 * 7
+    assert np.all(np.isfinite(r1["lhood_list"][:, 1:]))
+    # proposal noise has the reference's scale: accepted moves are ~0.025 per coordinate
+    d = np.diff(r1["pos_w"][0, 1:], axis=0)
+    moved = d[np.any(d != 0, axis=1)]
+    assert 0.015 < moved.std() < 0.04
