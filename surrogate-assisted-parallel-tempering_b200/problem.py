@@ -99,7 +99,7 @@ class Problem:
             out = (torch.zeros(R, dtype=torch.float64, device=theta.device),
                    torch.zeros(R, dtype=torch.int32, device=theta.device),
                    torch.zeros(R, dtype=torch.float64, device=theta.device))
-        _lib.check(_lib.lib().sapt_loglik(self._h, which, _ptr(theta), theta.stride(0), R, _ptr(rows), _ptr(n_rows),
+        _lib.check(_lib.lib().sapt_loglik(self._h, which, _ptr(theta), _ld(theta), R, _ptr(rows), _ptr(n_rows),
                                           _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
                                           self.path if path is None else path, current_stream_ptr()), "sapt_loglik")
         return out
@@ -124,13 +124,19 @@ class Problem:
     def langevin(self, theta: torch.Tensor, lrate: float, mode: int = 0, batch_scale: float = 1.0, rows=None, n_rows=None, out=None):
         if out is None:
             out = theta.clone()
-        _lib.check(_lib.lib().sapt_langevin(self._h, _ptr(theta), _ptr(out), theta.stride(0), theta.shape[0], _ptr(rows), _ptr(n_rows),
+        _lib.check(_lib.lib().sapt_langevin(self._h, _ptr(theta), _ptr(out), _ld(theta), theta.shape[0], _ptr(rows), _ptr(n_rows),
                                             float(lrate), int(mode), float(batch_scale), current_stream_ptr()), "sapt_langevin")
         return out
 
 
+def _ld(t: torch.Tensor) -> int:
+    """Row stride in elements; a single-row tensor may report any stride for dim 0."""
+    return max(int(t.stride(0)), int(t.shape[1])) if t.shape[0] == 1 else int(t.stride(0))
+
+
 def prior(theta: torch.Tensor, P: int, sigma_squared: float = 25.0):
+    theta = theta.contiguous()
     out = torch.empty(theta.shape[0], dtype=torch.float64, device=theta.device)
-    _lib.check(_lib.lib().sapt_prior(_ptr(theta), theta.stride(0), theta.shape[0], P, float(sigma_squared), _ptr(out),
+    _lib.check(_lib.lib().sapt_prior(_ptr(theta), _ld(theta), theta.shape[0], P, float(sigma_squared), _ptr(out),
                                      current_stream_ptr()), "sapt_prior")
     return out

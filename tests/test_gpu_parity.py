@@ -300,8 +300,8 @@ def test_engine_philox_run_is_deterministic_and_sane(lib):
     topo = [int(v) for v in g["topology"]]
     prob = Problem(topo, g["train"], g["test"])
 
-    def run(seed):
-        cfg = EngineConfig(variant="rw", samples=40, swap_interval=5, surrogate_interval=5, surrogate_prob=0.0,
+    def run(seed, swap_interval=5):
+        cfg = EngineConfig(variant="rw", samples=40, swap_interval=swap_interval, surrogate_interval=5, surrogate_prob=0.0,
                            use_surrogate=False, seed=seed)
         eng = PTEngine(prob, assign_temperatures(8, 4.0), cfg)
         eng.initialize(g["W"][0])
@@ -313,7 +313,8 @@ def test_engine_philox_run_is_deterministic_and_sane(lib):
     assert not np.array_equal(r1["pos_w"], r3["pos_w"])
     assert r1["naccept"].sum() > 0 and r1["total_swap_proposals"] == 7 * 7
     assert np.all(np.isfinite(r1["lhood_list"][:, 1:]))
-    # proposal noise has the reference's scale: accepted moves are ~0.025 per coordinate
-    d = np.diff(r1["pos_w"][0, 1:], axis=0)
+    # proposal noise has the reference's scale: accepted moves are ~0.025 per coordinate (no exchanges in this run)
+    r4 = run(11, swap_interval=1000)
+    d = np.diff(r4["pos_w"][0, 1:], axis=0)
     moved = d[np.any(d != 0, axis=1)]
     assert 0.015 < moved.std() < 0.04
