@@ -80,6 +80,8 @@ int ensure_workspace(sapt_problem* p, size_t bytes);
 int launch_loglik_f32(sapt_problem* p, int which, const float* theta, int64_t ld, int R,
                       const int32_t* rows, const int32_t* n_rows, double* L, int32_t* nc, double* sq,
                       cudaStream_t st);
+int launch_loglik_finalize(const double* partL, const int32_t* partNc, const int32_t* partSq, int n_chunks, int R, const int32_t* rows,
+                           const int32_t* n_rows, double* L, int32_t* nc, double* sq, cudaStream_t st);
 int launch_forward_rows_f32(sapt_problem* p, int which, const float* theta, int32_t* fx, float* prob, cudaStream_t st);
 // implemented in sapt_loglik_tc.cu
 int tc_prepare_dataset(sapt_problem* p, int which, const float* x_host, int64_t n);

@@ -346,8 +346,13 @@ int launch_loglik_f32(sapt_problem* p, int which, const float* theta, int64_t ld
     default: set_error("fp32 path: D padded to %d unsupported (D <= 64)", p->DP); return SAPT_ERR_UNSUPPORTED;
   }
   if (rc) return rc;
+  return launch_loglik_finalize(a.partL, a.partNc, a.partSq, (int)n_chunks, R, rows, n_rows, L, nc, sq, st);
+}
+
+int launch_loglik_finalize(const double* partL, const int32_t* partNc, const int32_t* partSq, int n_chunks, int R, const int32_t* rows,
+                           const int32_t* n_rows, double* L, int32_t* nc, double* sq, cudaStream_t st) {
   const int wpb = 8;
-  loglik_finalize_kernel<<<(R + wpb - 1) / wpb, wpb * 32, 0, st>>>(a.partL, a.partNc, a.partSq, (int)n_chunks, R, rows, n_rows, L, nc, sq);
+  loglik_finalize_kernel<<<(R + wpb - 1) / wpb, wpb * 32, 0, st>>>(partL, partNc, partSq, n_chunks, R, rows, n_rows, L, nc, sq);
   SAPT_CHECK_LAUNCH();
   return SAPT_OK;
 }
