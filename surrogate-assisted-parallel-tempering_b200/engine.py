@@ -20,7 +20,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, parallel
 from .problem import Problem, _ptr, current_stream_ptr
 
 SURROGATE_HIDDEN = {1: (64, 16), 2: (120, 40), 3: (200, 50)}  # _revamp.py:221-229
@@ -104,9 +104,7 @@ class PTEngine:
         self.dev = problem.device
         self.L = _lib.lib()
         self.Rg = int(len(temperatures))
-        assert self.Rg % cfg.world == 0, "num_chains must divide evenly over ranks"
-        self.R = self.Rg // cfg.world
-        self.row0 = cfg.rank * self.R
+        self.row0, self.R = parallel.shard_bounds(self.Rg, cfg.rank, cfg.world)
         self.P = problem.P
         self.ld = (self.P + 3) & ~3
         self.pg = process_group
@@ -334,23 +332,15 @@ class PTEngine:
 
     # ------------------------------------------------------------------------------------
     def _hosted_mask(self):
-        mask = torch.zeros(self.Rg, dtype=torch.float64, device=self.dev)
-        mask[self.slot_of_row.long()] = 1.0
-        return mask
+        return parallel.hosted_mask(self.slot_of_row, self.Rg)
 
     def sync_slots(self):
         """Masked all-reduce of the per-chain scalars: every rank contributes the slots its rows host."""
         if self.cfg.world == 1:
             return
-        import torch.distributed as dist
-        mask = self._hosted_mask()
-        pack = torch.cat([self.lik_cur[None], self.lik_post[None], self.prior_cur[None], self.likl_wo_temp[None], self.last,
-                          self.mov.t(), self.naccept.double()[None]], dim=0)
-        pack = torch.where(mask[None, :] > 0, pack, torch.zeros_like(pack))
-        cnt = self.train_count.double() * mask if self.train_count is not None else None
-        dist.all_reduce(pack, group=self.pg)
-        self.lik_cur.copy_(pack[0]); self.lik_post.copy_(pack[1]); self.prior_cur.copy_(pack[2]); self.likl_wo_temp.copy_(pack[3])
-        self.last.copy_(pack[4:8]); self.mov.copy_(pack[8:11].t()); self.naccept.copy_(pack[11].round().to(torch.int32))
+        args = (self.lik_cur, self.lik_post, self.prior_cur, self.likl_wo_temp, self.last, self.mov, self.naccept)
+        pack = parallel.sync_hosted(parallel.pack_state(*args), self._hosted_mask(), self.pg)
+        parallel.unpack_state(pack, *args)
 
     def swap(self, i: int):
         """Replica exchange at a rendezvous (RW:1095-1099)."""
@@ -436,12 +426,7 @@ class PTEngine:
         if self.hist is not None:
             hist = self.hist
             if self.cfg.world > 1:
-                import torch.distributed as dist
-                hist = {}
-                for k, v in self.hist.items():
-                    t = v.clone() if v.dtype != torch.uint8 else v.to(torch.int32)
-                    dist.all_reduce(t, group=self.pg)
-                    hist[k] = t
+                hist = {k: parallel.merge_history(v, self.pg) for k, v in self.hist.items()}
                 hist["likeh"][0].fill_(-100.0)
                 if "pos_w" in hist:
                     hist["pos_w"][0].fill_(1.0)
