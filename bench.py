@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(name="C3 PenDigit-shape 16-30-10 synthetic", D=16, H=30, O=10, n_train=1_000_000, n_test=65_536,
-                chains_per_gpu=1024, maxtemp=4.0, swap_interval=50, seed=1234)
+                chains_per_gpu=1024, maxtemp=4.0, swap_interval=5, seed=1234)
 METRIC = "replica_x_row_likelihood_evals_per_sec"
 UNIT = "evals/s"
 

@@ -179,6 +179,7 @@ class PTEngine:
         if sp.lg_flow: self.flags |= _lib.F_REDRAW_ON_SURROGATE
         if cfg.record_history and cfg.record_pos: self.flags |= _lib.F_RECORD_POS
         self.evals = 0  # replica x row likelihood evaluations issued (host-side count of the worst case)
+        self._segments = [(0, self._hosted_mask())]  # (first history row, hosted mask) per binding epoch
 
     # ------------------------------------------------------------------------------------
     def _chain_state(self) -> _lib.ChainState:
@@ -347,6 +348,13 @@ class PTEngine:
         if self.Rg < 2:
             return
         self.sync_slots()
+        if self.cfg.world > 1 and self.hist is not None and "pos_w" in self.hist:
+            # a rejected step copies pos_w history row i (RV:608): the row must follow the slot across ranks
+            import torch.distributed as dist
+            row = self.hist["pos_w"][i + 1]
+            mask = self._hosted_mask().to(row.dtype)
+            row.mul_(mask[:, None])
+            dist.all_reduce(row, group=self.pg)
         u = None
         if self.inj is not None and "swap_u" in self.inj:
             u = self.inj["swap_u"][self.sweep_count]
@@ -356,6 +364,7 @@ class PTEngine:
                                           _ptr(self.counters[3:4]), None, self.row0, self.R, _ptr(self.slot_of_row),
                                           current_stream_ptr()), "sapt_swap_sweep")
         self.swap_log.append(swapped)
+        self._segments.append((i + 2, self._hosted_mask()))  # history rows >= i+2 are written under the new binding
         self.sweep_count += 1
         self.total_swap_proposals += self.Rg - 1
 
@@ -426,7 +435,11 @@ class PTEngine:
         if self.hist is not None:
             hist = self.hist
             if self.cfg.world > 1:
-                hist = {k: parallel.merge_history(v, self.pg) for k, v in self.hist.items()}
+                hist = {k: v for k, v in self.hist.items()}
+                if "pos_w" in hist:
+                    # rows synchronised at exchanges are present on every rank: keep only hosted-at-write entries
+                    hist["pos_w"] = self._pos_w_owned()
+                hist = {k: parallel.merge_history(v, self.pg) for k, v in hist.items()}
                 hist["likeh"][0].fill_(-100.0)
                 if "pos_w" in hist:
                     hist["pos_w"][0].fill_(1.0)
@@ -450,6 +463,18 @@ class PTEngine:
         out["likelihood"] = self.lik_post.cpu().numpy(); out["likelihood_copy"] = self.lik_cur.cpu().numpy()
         out["prior_current"] = self.prior_cur.cpu().numpy()
         return out
+
+    def _pos_w_owned(self):
+        """pos_w history with every entry that this rank did not write itself zeroed (rows that were
+        all-reduced at an exchange exist on all ranks and must be counted once in the merge)."""
+        owned = self.hist["pos_w"].clone()
+        S = owned.shape[0]
+        owner = torch.zeros((S, self.Rg), dtype=owned.dtype, device=owned.device)
+        segs = self._segments + [(S, None)]
+        for (r0, mask), (r1, _) in zip(segs[:-1], segs[1:]):
+            owner[r0:r1] = mask[None, :].to(owned.dtype)
+        owned.mul_(owner[:, :, None])
+        return owned
 
     def current_w(self) -> np.ndarray:
         """[chain, P] parameter vector each chain currently holds (single rank)."""
