@@ -18,11 +18,14 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
 #include "sapt_device.cuh"
 #include "sapt_internal.h"
+#include "sapt_tc_ptx.cuh"
 
 namespace sapt {
 
@@ -42,98 +45,7 @@ constexpr uint32_t kBBytes = 2 * kBBytesPerKb;       // 64 KB
 
 bool tc_topology_supported(int D, int H, int O) { return D <= 16 && H <= 32 && O <= 20; }
 
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Bounded wait: a lost TMA/MMA completion must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; ; ++spin) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (spin > (1u << 24)) {  // each failed try_wait already sleeps up to the HW time limit
-      printf("sapt: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                   smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, SWIZZLE_128B canonical layout ((8,n),2):((8,SBO),1) in 16-byte units (cute/atom/mma_traits_sm100.hpp)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address
-  d |= (uint64_t)1 << 16;                      // leading byte offset (ignored for swizzled K-major; CUTLASS writes 1)
-  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset: 8 rows x 128 B
-  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
-      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 // ---- per-step operand packing -----------------------------------------------------------------
-__device__ __forceinline__ void split3(float v, __nv_bfloat16& p1, __nv_bfloat16& p2, __nv_bfloat16& p3) {
-  p1 = __float2bfloat16_rn(v);
-  const float r1 = v - __bfloat162float(p1);
-  p2 = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(p2);
-  p3 = __float2bfloat16_rn(r2);
-}
-
 // B image rows: [group][NG*HP][128] bf16; W2 image: [pos][HP*OP + OP] fp32 (pre-scaled by -/+ log2 e)
 __global__ void tc_pack_kernel(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O,
                                int HP, int OP, int NG, __nv_bfloat16* bimg, float* w2img) {
@@ -401,11 +313,12 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, void* base, uint64_t rows, uint32_t box_rows) {
+// bf16 [rows][inner_elems] row-major, box = 64 elements (one 128-byte swizzle row) x box_rows
+int tc_make_map_2d(CUtensorMap* map, void* base, uint64_t inner_elems, uint64_t rows, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return SAPT_ERR_CUDA; }
-  const cuuint64_t dims[2] = {(cuuint64_t)kKA, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)kKA * 2};
+  const cuuint64_t dims[2] = {(cuuint64_t)inner_elems, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)inner_elems * 2};
   const cuuint32_t box[2] = {64, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -413,6 +326,7 @@ static int make_map(CUtensorMap* map, void* base, uint64_t rows, uint32_t box_ro
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SAPT_ERR_CUDA; }
   return SAPT_OK;
 }
+static int make_map(CUtensorMap* map, void* base, uint64_t rows, uint32_t box_rows) { return tc_make_map_2d(map, base, kKA, rows, box_rows); }
 
 static inline uint16_t f2bf(float v) {  // round-to-nearest-even, host side
   uint32_t u; memcpy(&u, &v, 4);
@@ -467,10 +381,21 @@ static int launch_tc(int OP, const CUtensorMap& ma, const CUtensorMap& mb, const
 
 static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
+int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld, int R, const int32_t* rows, const int32_t* n_rows,
+                      double* L, int32_t* nc, double* sq, cudaStream_t st);  // sapt_loglik_tc2.cu
+
+static int tc_version() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SAPT_TC_VERSION"); v = (e && e[0] == '1') ? 1 : 2; }
+  return v;
+}
+
 int launch_loglik_tc(sapt_problem* p, int which, const float* theta, int64_t ld, int R, const int32_t* rows, const int32_t* n_rows,
                      double* L, int32_t* nc, double* sq, cudaStream_t st) {
   const DataSet& ds = p->set[which];
   if (R <= 0 || ds.n <= 0) return SAPT_OK;
+  // v2 (both layers on the tensor cores) is the product path; v1 (layer 2 on the FMA pipe) is kept for A/B runs
+  if (tc_version() == 2 && !(p->O > 16 && p->H <= 16)) return launch_loglik_tc2(p, which, theta, ld, R, rows, n_rows, L, nc, sq, st);
   const int HP = p->H <= 16 ? 16 : 32;
   const int OP = p->OP;
   const int NG = kUmmaN / HP;
