@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsapt.so")
+LIB_PATH = os.environ.get("SAPT_LIB", os.path.join(_HERE, "libsapt.so"))  # SAPT_LIB: developer override for A/B builds
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 PATH_AUTO, PATH_F32, PATH_TC = 0, 1, 2

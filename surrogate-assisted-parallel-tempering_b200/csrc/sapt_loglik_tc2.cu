@@ -1,23 +1,31 @@
-// tcgen05 likelihood, version 2: BOTH layers on the tensor cores (sm_100a only).
+// tcgen05 / TMEM / TMA likelihood kernel: BOTH layers of every chain on the tensor cores (sm_100a only).
 //
-// v1 (sapt_loglik_tc.cu) ran layer 2 (H x O per chain) as FFMA with weights fetched by warp-uniform
-// LDS.128; ncu showed the shared-memory pipe at 93 % (a uniform LDS.128 still costs 4 wavefronts), i.e.
-// the kernel was bound by weight fetch, not math. v2 follows the flash-attention-on-Blackwell pattern:
+// Replaces, for all chains a GPU hosts: ptReplica.likelihood_func (_revamp.py:391-402) ->
+// Network.evaluate_proposal (:155-174) -> ForwardPass (:70-76) + softmax (:129-131).
 //
-//   MMA-1  D1[128 rows, 4 chains x HP]  = A[128, 112] . B1            (smem x smem -> TMEM, as v1)
-//   epilogue phase 1 (thread = row): tcgen05.ld D1 -> h = sigmoid -> split h = h1 + h2 (bf16) ->
-//            tcgen05.st  HV[chain] = [h1 | h1 | h2 | h1]  (bf16 pairs, the A operand of MMA-2, in TMEM)
-//   MMA-2  D2[128 rows, ON] = HV[chain] . [w1 ; w2 ; w1 ; w3]          (TMEM x smem -> TMEM, per chain),
-//            w = -log2(e) W2 split into three bf16 pieces (exact); D2 overwrites the chain's dead D1 columns
-//   epilogue phase 2: tcgen05.ld D2 (+ bias) -> sigmoid -> softmax / argmax -> fp64 log-likelihood sums
+//   MMA-1  D1[128 rows, 4 chains x HP] = X . W1'      smem x smem -> TMEM     (kind::f16, bf16 in, fp32 acc)
+//   phase 1 (thread = data row):  tcgen05.ld D1 -> h = sigmoid -> h = h1 + h2 (bf16 pieces) ->
+//           tcgen05.st HV[chain] = [h1 | h2]          (the A operand of MMA-2, never leaves TMEM)
+//   MMA-2  D2[128 rows, ON] = H . W2'                 TMEM x smem -> TMEM, one per chain; D2 overwrites the
+//                                                      chain's dead D1 columns
+//   phase 2: tcgen05.ld D2 (+ bias) -> sigmoid -> softmax / argmax -> fp64 log-likelihood sums
 //
-// Shared memory now only feeds the tensor cores (TMA-written, UMMA-read); the SIMT side touches it for
-// 16 bias floats per evaluation. Dropped cross terms: h2.w2, h3.* (|.| <= 2^-17 per activation, row
-// dependent rounding residue, i.e. unbiased noise ~1e-5 in z2) — parity tests hold the 1e-4 bound with
-// 3 orders of magnitude to spare; the weights themselves are represented exactly.
+// fp32-grade accuracy from bf16 tensor cores: every fp32 operand is split into bf16 pieces that sum to it
+// (x = x1+x2+x3, w = w1+w2+w3 exactly; h = h1+h2 to 2^-16, unbiased) and the significant cross terms are
+// accumulated by pointing successive MMA K-steps at different (A chunk, B chunk) pairs — each piece is
+// stored once. MMA-1 (K = 7 x 16): (x1,w1) (x1,w2) (x2,w1) (x1,w3) (x2,w2) (x3,w1) (1,b): dropped terms
+// O(2^-24). MMA-2: (h1,w1) (h1,w2) (h2,w1) (h1,w3). Weights are pre-scaled by -log2(e) (biases +log2(e)),
+// so an accumulator is t = -log2(e) z and sigmoid(z) = 1 / (1 + 2^t).
 //
-// TMEM map (512 columns): [0,256) two D1/D2 stages of 128 | [256,512) four HV buffers of 64
-// (HP=16: stages of 64 at 0/64, HV buffers of 32 from 256).
+// The SIMT side is bound by the SFU (MUFU) pipe, so reciprocals are batched four at a time
+// (1/a = (1/(abcd)) * bcd: one MUFU.RCP + 9 FMUL per four sigmoids) and the bf16 split uses integer
+// ops (truncate / add-half + PRMT) instead of F2FP conversions, which also issue on the SFU pipe.
+//
+// CTA = (row chunk, CH = 256/HP chains). Warp 16 lane 0: TMA producer (A ring; B1, W2 panels once).
+// Warp 17: TMEM alloc + single-thread MMA issue. Warps 0-15: epilogue; warp (quarter q, index e) owns TMEM
+// lanes 32q.. and one chain of every unit (16 epilogue warps). TMEM (512 columns): D1 (4 HP columns), two HV
+// buffers of 4 HP columns, two D2 buffers of 4 ON columns. The epilogue is software pipelined (phase 1 of unit
+// u+1 before phase 2 of unit u) so that every MMA has a full unit of slack before its result is awaited.
 #include <algorithm>
 #include <vector>
 
@@ -29,15 +37,18 @@ namespace sapt {
 
 namespace v2 {
 constexpr int kTileM = 128;
-constexpr int kKA = 128;        // bf16 per A/B1 row
-constexpr int kK1 = 112;        // used K of MMA-1
+constexpr int kKA = 64;         // bf16 per A / B1 row: [p1 | p2 | p3 | bias chunk]
 constexpr int kUC = 4;          // chains per unit (one MMA-1)
-constexpr int kEpiWarps = 8;
+constexpr int kEPQ = 4;                 // epilogue warps per TMEM lane quarter
+constexpr int kEpiWarps = 4 * kEPQ;
+constexpr int kCPW = kUC / kEPQ;        // chains per epilogue warp and unit
 constexpr int kThreads = 32 * (2 + kEpiWarps);
-constexpr uint32_t kABytesPerKb = kTileM * 128;
-constexpr uint32_t kAStageBytes = 2 * kABytesPerKb;
-constexpr uint32_t kB1BytesPerKb = 256 * 128;
-constexpr uint32_t kB1Bytes = 2 * kB1BytesPerKb;
+// The SMSP arbiter favours the highest warp id: the two single-thread roles that feed everyone else
+// (TMA producer, MMA issuer) sit above the epilogue warps so they are never starved by them.
+constexpr int kTmaWarp = kEpiWarps;
+constexpr int kMmaWarp = kEpiWarps + 1;
+constexpr uint32_t kAStageBytes = kTileM * 128;  // 16 KB
+constexpr uint32_t kB1Bytes = 256 * 128;         // 32 KB
 }  // namespace v2
 
 struct Tc2Params {
@@ -48,57 +59,64 @@ struct Tc2Params {
   double* partL; int32_t* partNc; int32_t* partSq;
 };
 
-// ---- per-step operand packing: B1 rows, W2 rows (bf16 pieces), bias2 (fp32) ---------------------
-// B1: [group][CH*HP][128]; W2: [group][CH*ON][K2] with K2 = 4*HP = [w1 | w2 | w1 | w3] per output row
+// ---- per-step operand packing ------------------------------------------------------------------------
+// B1: [group][CH*HP][64] = [w1 | w2 | w3 | b1 b2 b3 0..] per hidden unit (rows), 16 inputs per chunk
+// W2: [group][CH][3 pieces][ON][64]: row (p, o) = piece p of -log2(e) W2[:, o] over the HP hidden units (rest 0).
+//     MMA-2 reads rows [0, 3 ON) as one N = 3 ON operand against h1 and rows [0, ON) again against h2.
 __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O,
                                 int HP, int ON, int CH, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2) {
+  constexpr int KW = 64;
   const int nact = n_rows ? *n_rows : R;
   const int pos = blockIdx.x;
   const int n_pos_pad = ((nact + CH - 1) / CH) * CH;
   if (pos >= n_pos_pad) return;
   const int grp = pos / CH, within = pos - grp * CH;
-  const int K2 = 4 * HP;
   __nv_bfloat16* brow0 = b1img + ((int64_t)grp * 256 + (int64_t)within * HP) * v2::kKA;
-  __nv_bfloat16* wrow0 = w2img + ((int64_t)grp * CH * ON + (int64_t)within * ON) * K2;
+  __nv_bfloat16* wrow0 = w2img + ((int64_t)grp * CH + within) * (3 * ON) * KW;
   float* bb = bias2 + (int64_t)pos * ON;
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
   if (pos >= nact) {
     for (int i = threadIdx.x; i < HP * v2::kKA; i += blockDim.x) brow0[i] = zero;
-    for (int i = threadIdx.x; i < ON * K2; i += blockDim.x) wrow0[i] = zero;
+    for (int i = threadIdx.x; i < 3 * ON * KW; i += blockDim.x) wrow0[i] = zero;
     for (int i = threadIdx.x; i < ON; i += blockDim.x) bb[i] = 0.f;
     return;
   }
   const int row = rows ? rows[pos] : pos;
   const float* src = theta + (int64_t)row * ld;
-  for (int i = threadIdx.x; i < HP * 8; i += blockDim.x) {
-    const int h = i >> 3, c = i & 7;
-    __nv_bfloat16* dst = brow0 + (int64_t)h * v2::kKA + c * 16;
-    if (h >= H || c == 7) {
-#pragma unroll
-      for (int d = 0; d < 16; ++d) dst[d] = zero;
-    } else if (c == 6) {
-      __nv_bfloat16 p1, p2, p3;
-      split3(kLog2e * src[D * H + H * O + h], p1, p2, p3);
-      dst[0] = p1; dst[1] = p2; dst[2] = p3;
-#pragma unroll
-      for (int d = 3; d < 16; ++d) dst[d] = zero;
-    } else {
-      const int piece = (c == 0 || c == 2 || c == 5) ? 0 : ((c == 1 || c == 4) ? 1 : 2);
-      for (int d = 0; d < 16; ++d) {
-        __nv_bfloat16 p[3] = {zero, zero, zero};
-        if (d < D) split3(-kLog2e * src[d * H + h], p[0], p[1], p[2]);
-        dst[d] = p[piece];
-      }
+  for (int i = threadIdx.x; i < HP * 16; i += blockDim.x) {
+    const int h = i >> 4, d = i & 15;
+    __nv_bfloat16 p[3] = {zero, zero, zero}, b[3] = {zero, zero, zero};
+    if (h < H) {
+      if (d < D) split3(-kLog2e * src[d * H + h], p[0], p[1], p[2]);
+      if (d == 0) split3(kLog2e * src[D * H + H * O + h], b[0], b[1], b[2]);
     }
+    __nv_bfloat16* dst = brow0 + (int64_t)h * v2::kKA;
+    dst[d] = p[0]; dst[16 + d] = p[1]; dst[32 + d] = p[2];
+    if (d == 0) { dst[48] = b[0]; dst[49] = b[1]; dst[50] = b[2]; }
+    else if (d >= 3) dst[48 + d] = zero;
   }
-  for (int i = threadIdx.x; i < ON * HP; i += blockDim.x) {
-    const int o = i / HP, h = i - o * HP;
+  for (int i = threadIdx.x; i < ON * KW; i += blockDim.x) {
+    const int o = i / KW, h = i - o * KW;
     __nv_bfloat16 p[3] = {zero, zero, zero};
     if (o < O && h < H) split3(-kLog2e * src[D * H + h * O + o], p[0], p[1], p[2]);
-    __nv_bfloat16* dst = wrow0 + (int64_t)o * K2;
-    dst[h] = p[0]; dst[HP + h] = p[1]; dst[2 * HP + h] = p[0]; dst[3 * HP + h] = p[2];
+    wrow0[(int64_t)o * KW + h] = p[0];
+    wrow0[(int64_t)(ON + o) * KW + h] = p[1];
+    wrow0[(int64_t)(2 * ON + o) * KW + h] = p[2];
   }
   for (int i = threadIdx.x; i < ON; i += blockDim.x) bb[i] = (i < O) ? kLog2e * src[D * H + H * O + H + i] : 0.f;
+}
+
+// four sigmoids with one reciprocal:  s_i = 1 / a_i,  a_i = 1 + 2^min(t_i, 30)  (clamp: |error| < 1e-9,
+// keeps the product of four below 2^120)
+__device__ __forceinline__ void sigmoid4(float t0, float t1, float t2, float t3, float& s0, float& s1, float& s2, float& s3) {
+  const float a0 = 1.0f + ex2_approx(fminf(t0, 30.0f));
+  const float a1 = 1.0f + ex2_approx(fminf(t1, 30.0f));
+  const float a2 = 1.0f + ex2_approx(fminf(t2, 30.0f));
+  const float a3 = 1.0f + ex2_approx(fminf(t3, 30.0f));
+  const float ab = a0 * a1, cd = a2 * a3;
+  const float r = rcp_approx(ab * cd);
+  const float rab = r * cd, rcd = r * ab;
+  s0 = rab * a1; s1 = rab * a0; s2 = rcd * a3; s3 = rcd * a2;
 }
 
 template <int HP, int ON, int STAGES>
@@ -109,12 +127,17 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   constexpr int CH = 256 / HP;              // chains per CTA
   constexpr int UPT = CH / kUC;             // units (MMA-1 issues) per row tile
   constexpr int N1 = kUC * HP;              // MMA-1 N
-  constexpr int K2 = 4 * HP;                // MMA-2 K
-  constexpr int KB2 = K2 / 64;              // K blocks of the W2 operand
-  constexpr int HVC = K2 / 2;               // TMEM columns of one HV buffer
-  constexpr uint32_t kW2BytesPerKb = CH * ON * 128;
-  constexpr uint32_t kW2Bytes = KB2 * kW2BytesPerKb;
-  static_assert(ON <= HP, "D2 must fit in the chain's D1 columns");
+  constexpr int N2 = 3 * ON;                // MMA-2 N against h1: [w1 | w2 | w3] side by side
+  constexpr uint32_t kW2ChainBytes = N2 * 128;           // per chain: 3 ON rows of 128 bytes
+  constexpr uint32_t kW2Bytes = CH * kW2ChainBytes;
+  // TMEM columns: [D1 | HV (A operand of MMA-2) | D2 buffers]. D2 of a chain is 3 ON wide: the three partial
+  // sums h.w1, h.w2, h.w3 land side by side (each A piece is read from TMEM once — an MMA with A in TMEM costs
+  // ~64 cycles whatever N is) and are added by the epilogue.
+  constexpr int kHvBufs = 1;
+  constexpr int kD2Bufs = (N1 + kUC * HP + 2 * kUC * N2 <= 512) ? 2 : 1;
+  constexpr int kHvBase = N1;
+  constexpr int kD2Base = kHvBase + kHvBufs * kUC * HP;
+  static_assert(kD2Base + kD2Bufs * kUC * N2 <= 512, "TMEM budget");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB1 = smem;
@@ -125,11 +148,13 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   uint64_t* full_a = bars;                  // [STAGES]
   uint64_t* empty_a = full_a + STAGES;      // [STAGES]
   uint64_t* b_full = empty_a + STAGES;      // [1]
-  uint64_t* d1_full = b_full + 1;           // [2]
-  uint64_t* d1_empty = d1_full + 2;         // [2]
-  uint64_t* hv_full = d1_empty + 2;         // [kUC]
-  uint64_t* d2_full = hv_full + kUC;        // [kUC]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d2_full + kUC);
+  uint64_t* d1_full = b_full + 1;           // [2] (one used)
+  uint64_t* d1_empty = d1_full + 2;         // [2] (one used)
+  // hv_full / d2_full are per (unit parity, chain): with one barrier per chain a fast warp could complete
+  // phase u+1 before the waiter has looked at phase u, and a parity wait cannot see a barrier two phases ahead
+  uint64_t* hv_full = d1_empty + 2;         // [2][kUC]
+  uint64_t* d2_full = hv_full + 2 * kUC;    // [2][kUC]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d2_full + 2 * kUC);
   double* red = reinterpret_cast<double*>(tmem_ptr + 2);  // [CH][4 quarters][3]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,12 +169,13 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
     mbar_init(b_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&d1_full[s], 1); mbar_init(&d1_empty[s], kEpiWarps); }
-    for (int c = 0; c < kUC; ++c) { mbar_init(&hv_full[c], 4); mbar_init(&d2_full[c], 1); }
+    mbar_init(&d1_full[0], 1);
+    mbar_init(&d1_empty[0], kEpiWarps);
+    for (int c = 0; c < 2 * kUC; ++c) { mbar_init(&hv_full[c], 4); mbar_init(&d2_full[c], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -162,170 +188,212 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_hv = tmem_base + 256;
+  const uint32_t tmem_hv = tmem_base + kHvBase;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ================= TMA producer =================
     if (lane == 0) {
       mbar_expect_tx(b_full, kB1Bytes + kW2Bytes);
       tma_load_2d(&map_b1, b_full, sB1, 0, blockIdx.y * 256);
-      tma_load_2d(&map_b1, b_full, sB1 + kB1BytesPerKb, 64, blockIdx.y * 256);
 #pragma unroll
-      for (int kb = 0; kb < KB2; ++kb) tma_load_2d(&map_w2, b_full, sW2 + kb * kW2BytesPerKb, kb * 64, blockIdx.y * CH * ON);
+      for (int q = 0; q < CH / 4; ++q)  // boxes of 4 chains x 3 ON rows
+        tma_load_2d(&map_w2, b_full, sW2 + q * 4 * kW2ChainBytes, 0, (blockIdx.y * CH + q * 4) * N2);
       for (int it = 0; it < n_my_tiles; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty_a[s], ph ^ 1);
         mbar_expect_tx(&full_a[s], kAStageBytes);
-        const int row0 = (int)((t_begin + it) * kTileM);
-        tma_load_2d(&map_a, &full_a[s], sA + s * kAStageBytes, 0, row0);
-        tma_load_2d(&map_a, &full_a[s], sA + s * kAStageBytes + kABytesPerKb, 64, row0);
+        tma_load_2d(&map_a, &full_a[s], sA + s * kAStageBytes, 0, (int)((t_begin + it) * kTileM));
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ON >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t idesc2a = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t idesc2b = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ON >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t b1_addr = smem_u32(sB1);
       const uint32_t w2_addr = smem_u32(sW2);
       mbar_wait(b_full, 0);
       auto issue_mma1 = [&](int u) {
         const int it = u / UPT, uu = u - it * UPT;
         const int s = it % STAGES;
-        const int ds = u & 1;
-        mbar_wait(&d1_empty[ds], ((u >> 1) & 1) ^ 1);
+        if (u > 0) mbar_wait(&d1_empty[0], (u - 1) & 1);  // every warp holds D1(u-1) in registers
         if (uu == 0) mbar_wait(&full_a[s], (it / STAGES) & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA + s * kAStageBytes);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ds * N1);
+        const uint32_t b_addr = b1_addr + (uint32_t)(uu * N1) * 128;
+        // (A chunk, B chunk) pairs: x1w1 x1w2 x2w1 x1w3 x2w2 x3w1 + bias; a chunk = 16 elements = 32 bytes
+        constexpr int ia[7] = {0, 0, 1, 0, 1, 2, 3};
+        constexpr int ib[7] = {0, 1, 0, 2, 1, 0, 3};
 #pragma unroll
-        for (int k = 0; k < kK1 / 16; ++k) {
-          const uint32_t kb = k >> 2, kin = k & 3;
-          const uint64_t ad = umma_desc_sw128(a_addr + kb * kABytesPerKb + kin * 32);
-          const uint64_t bd = umma_desc_sw128(b1_addr + kb * kB1BytesPerKb + (uint32_t)(uu * N1) * 128 + kin * 32);
-          tc_mma_bf16(d_tmem, ad, bd, idesc1, k > 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < 7; ++k)
+#if defined(SAPT_EXP_NO_MMA1)
+          if (k == 0)
+#endif
+          tc_mma_bf16(tmem_base, umma_desc_sw128(a_addr + ia[k] * 32), umma_desc_sw128(b_addr + ib[k] * 32), idesc1, k > 0 ? 1u : 0u);
         if (uu == UPT - 1) tc_commit(&empty_a[s]);
-        tc_commit(&d1_full[ds]);
+        tc_commit(&d1_full[0]);
       };
       if (n_units > 0) issue_mma1(0);
       for (int u = 0; u < n_units; ++u) {
         const int uu = u % UPT;
-        const int ds = u & 1;
-        const uint32_t uph = u & 1;
+        // D1(u+1) first: its trigger (all warps loaded D1(u)) precedes the HV(u) hand-over in every warp
+        if (u + 1 < n_units) issue_mma1(u + 1);
 #pragma unroll
-        for (int ci = 0; ci < kUC; ++ci) {
-          // chains are finished by the epilogue warps in the order 0,2 (first chain of each warp) then 1,3
-          const int c = (ci < 2) ? (2 * ci) : (2 * (ci - 2) + 1);
-          if (ci == 2 && u + 1 < n_units) issue_mma1(u + 1);
-          mbar_wait(&hv_full[c], uph);
+        for (int c = 0; c < kUC; ++c) {
+          mbar_wait(&hv_full[(u & 1) * kUC + c], (u >> 1) & 1);
           tc_fence_after();
-          const uint32_t d2 = tmem_base + (uint32_t)(ds * N1 + c * HP);
-          const uint32_t hv = tmem_hv + (uint32_t)(c * HVC);
-          const int chain = uu * kUC + c;
+          const uint32_t d2 = tmem_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (kUC * N2) + c * N2);
+          const uint32_t hv = tmem_hv + (uint32_t)(c * HP);
+          const uint32_t wb = w2_addr + (uint32_t)(uu * kUC + c) * kW2ChainBytes;
+          // D2[:, 0:3ON] = h1 . [w1|w2|w3]  then  D2[:, 0:ON] += h2 . w1   (h piece = HP/2 TMEM columns)
 #pragma unroll
-          for (int j = 0; j < K2 / 16; ++j) {
-            const uint32_t kb = j >> 2, kin = j & 3;
-            const uint64_t bd = umma_desc_sw128(w2_addr + kb * kW2BytesPerKb + (uint32_t)(chain * ON) * 128 + kin * 32);
-            tc_mma_bf16_ts(d2, hv + (uint32_t)(j * 8), bd, idesc2, j > 0 ? 1u : 0u);
-          }
-          tc_commit(&d2_full[c]);
+          for (int half = 0; half < HP / 16; ++half)
+            tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), umma_desc_sw128(wb + half * 32), idesc2a, half ? 1u : 0u);
+#pragma unroll
+          for (int half = 0; half < HP / 16; ++half)
+            tc_mma_bf16_ts(d2, hv + (uint32_t)(HP / 2 + half * 8), umma_desc_sw128(wb + half * 32), idesc2b, 1u);
+          tc_commit(&d2_full[(u & 1) * kUC + c]);
         }
       }
     }
   } else {
     // ================= epilogue warps =================
-    const int ew = warp - 2;
+    const int ew = warp;
     const int quarter = warp & 3;
-    const int e = ew >> 2;                    // this warp owns chains 2e, 2e+1 of every unit
+    const int e = ew >> 2;                    // this warp owns chains e*kCPW .. e*kCPW+kCPW-1 of every unit
     const int O = p.O;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    double accL[UPT][2];
-    int accNc[UPT][2], accSq[UPT][2];
+    double accL[UPT][kCPW];
+    int accNc[UPT][kCPW], accSq[UPT][kCPW];
 #pragma unroll
     for (int a = 0; a < UPT; ++a)
 #pragma unroll
-      for (int b = 0; b < 2; ++b) { accL[a][b] = 0.0; accNc[a][b] = 0; accSq[a][b] = 0; }
+      for (int b = 0; b < kCPW; ++b) { accL[a][b] = 0.0; accNc[a][b] = 0; accSq[a][b] = 0; }
+    // Software pipeline over units: phase 1 of unit u+1 (sigmoid + split, SIMT) runs while the tensor pipe
+    // computes MMA-2 of unit u, so the warp never waits for D2 right after handing over its activations.
+    uint32_t hv[kCPW][HP];  // [h1 pairs (HP/2) | h2 pairs (HP/2)] of the unit whose phase 1 ran last
+    auto phase1 = [&](int u) {
+      mbar_wait(&d1_full[0], u & 1);
+      tc_fence_after();
+      uint32_t zr[kCPW][HP];
+#pragma unroll
+      for (int cc = 0; cc < kCPW; ++cc) {
+        const uint32_t taddr = tmem_base + lane_base + (uint32_t)((kCPW * e + cc) * HP);
+        if constexpr (HP == 32) tmem_ld32(taddr, zr[cc]); else tmem_ld16(taddr, zr[cc]);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d1_empty[0]);  // D1 is in registers: the next MMA-1 may overwrite it
+#if defined(SAPT_EXP_SKIP_P1)
+#pragma unroll
+      for (int cc = 0; cc < kCPW; ++cc)
+#pragma unroll
+        for (int j = 0; j < HP; ++j) hv[cc][j] = zr[cc][j] & 0x3f803f80u;
+      return;
+#endif
+#pragma unroll
+      for (int cc = 0; cc < kCPW; ++cc) {
+#pragma unroll
+        for (int j = 0; j < HP / 4; ++j) {
+          float h0, h1, h2, h3;
+          sigmoid4(__uint_as_float(zr[cc][4 * j]), __uint_as_float(zr[cc][4 * j + 1]), __uint_as_float(zr[cc][4 * j + 2]),
+                   __uint_as_float(zr[cc][4 * j + 3]), h0, h1, h2, h3);
+          // h1 piece = h rounded (half-up) to bf16, h2 piece = the exact residual rounded the same way:
+          // both zero-mean, so the dropped h2.w2 term does not bias z2
+          const uint32_t u0 = __float_as_uint(h0) + 0x8000u, u1 = __float_as_uint(h1) + 0x8000u;
+          const uint32_t u2 = __float_as_uint(h2) + 0x8000u, u3 = __float_as_uint(h3) + 0x8000u;
+          hv[cc][2 * j] = __byte_perm(u0, u1, 0x7632);
+          hv[cc][2 * j + 1] = __byte_perm(u2, u3, 0x7632);
+          const uint32_t r0 = __float_as_uint(h0 - __uint_as_float(u0 & 0xffff0000u)) + 0x8000u;
+          const uint32_t r1 = __float_as_uint(h1 - __uint_as_float(u1 & 0xffff0000u)) + 0x8000u;
+          const uint32_t r2 = __float_as_uint(h2 - __uint_as_float(u2 & 0xffff0000u)) + 0x8000u;
+          const uint32_t r3 = __float_as_uint(h3 - __uint_as_float(u3 & 0xffff0000u)) + 0x8000u;
+          hv[cc][HP / 2 + 2 * j] = __byte_perm(r0, r1, 0x7632);
+          hv[cc][HP / 2 + 2 * j + 1] = __byte_perm(r2, r3, 0x7632);
+        }
+      }
+    };
+    auto publish_hv = [&](int u) {  // activations of unit u -> TMEM (A operand of MMA-2), then tell the MMA warp
+#pragma unroll
+      for (int cc = 0; cc < kCPW; ++cc) {
+        const uint32_t hva = tmem_hv + lane_base + (uint32_t)((kCPW * e + cc) * HP);
+        if constexpr (HP == 32) tmem_st32(hva, hv[cc]); else tmem_st16(hva, hv[cc]);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int cc = 0; cc < kCPW; ++cc) mbar_arrive(&hv_full[(u & 1) * kUC + kCPW * e + cc]);
+      }
+    };
+    if (n_units > 0) { phase1(0); publish_hv(0); }
     for (int it = 0; it < n_my_tiles; ++it) {
       const int64_t row = (t_begin + it) * kTileM + quarter * 32 + lane;
       const int y = __ldg(p.y + row);
 #pragma unroll
       for (int uu = 0; uu < UPT; ++uu) {
         const int u = it * UPT + uu;
-        const int ds = u & 1;
-        mbar_wait(&d1_full[ds], (u >> 1) & 1);
-        tc_fence_after();
-        // ---- phase 1: hidden activations -> bf16 pieces -> TMEM (A operand of MMA-2) ----
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = 2 * e + cc;
-          uint32_t zr[HP];
-          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(ds * N1 + c * HP);
-          if constexpr (HP == 32) tmem_ld32(taddr, zr); else tmem_ld16(taddr, zr);
-          tmem_ld_wait();
-          uint32_t h1p[HP / 2], h2p[HP / 2];
-#pragma unroll
-          for (int j = 0; j < HP / 2; ++j) {
-            const float ha = sigmoid_from_neg_log2e(__uint_as_float(zr[2 * j]));
-            const float hb = sigmoid_from_neg_log2e(__uint_as_float(zr[2 * j + 1]));
-            const uint32_t hi = pack_bf16x2(ha, hb);
-            const float ra = ha - __uint_as_float(hi << 16);
-            const float rb = hb - __uint_as_float(hi & 0xffff0000u);
-            h1p[j] = hi;
-            h2p[j] = pack_bf16x2(ra, rb);
-          }
-          // HV[c] = [h1 | h1 | h2 | h1], HP/2 packed columns per chunk
-          const uint32_t hv = tmem_hv + lane_base + (uint32_t)(c * HVC);
-          if constexpr (HP == 32) {
-            uint32_t w[32];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { w[j] = h1p[j]; w[16 + j] = h1p[j]; }
-            tmem_st32(hv, w);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { w[j] = h2p[j]; w[16 + j] = h1p[j]; }
-            tmem_st32(hv + 32, w);
-          } else {
-            uint32_t w[16];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { w[j] = h1p[j]; w[8 + j] = h1p[j]; }
-            tmem_st16(hv, w);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { w[j] = h2p[j]; w[8 + j] = h1p[j]; }
-            tmem_st16(hv + 16, w);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&hv_full[c]);
+        const bool has_next = (u + 1 < n_units);
+        if (has_next) {
+          phase1(u + 1);
+          // two HV buffers: HV[(u+1)%2] was last read by MMA-2(u-1), whose completion this warp already observed
+          if constexpr (kHvBufs == 2) publish_hv(u + 1);
         }
-        // ---- phase 2: output layer from D2 ----
+        // ---- D2 of unit u: wait for MMA-2 (with one HV buffer this also frees it), pull it into registers ----
+        uint32_t dr[kCPW][N2];
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = 2 * e + cc;
-          mbar_wait(&d2_full[c], u & 1);
-          tc_fence_after();
-          uint32_t dr[ON];
-          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(ds * N1 + c * HP);
-          if constexpr (ON == 32) tmem_ld32(taddr, dr); else tmem_ld16(taddr, dr);
-          tmem_ld_wait();
-          if (cc == 1) {  // both of this warp's D2 blocks are in registers: the stage may be overwritten
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d1_empty[ds]);
+        for (int cc = 0; cc < kCPW; ++cc) {
+          const int c = kCPW * e + cc;
+          mbar_wait(&d2_full[(u & 1) * kUC + c], (u >> 1) & 1);
+        }
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < kCPW; ++cc) {
+          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (kUC * N2) + (kCPW * e + cc) * N2);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            uint32_t (&blk)[ON] = *reinterpret_cast<uint32_t(*)[ON]>(&dr[cc][q * ON]);
+            if constexpr (ON == 32) tmem_ld32(taddr + q * ON, blk); else tmem_ld16(taddr + q * ON, blk);
           }
+        }
+        tmem_ld_wait();
+        if constexpr (kHvBufs == 1) { if (has_next) publish_hv(u + 1); }
+        // ---- phase 2: output layer ----
+#pragma unroll
+        for (int cc = 0; cc < kCPW; ++cc) {
+          const int c = kCPW * e + cc;
           const float* bias = sBias + (uu * kUC + c) * ON;
           float tmin = 0.f; int pm = 0; float sum = 0.f, oy = 0.f;
+#if defined(SAPT_EXP_SKIP_P2)
+          sum = 2.0f; oy = __uint_as_float(dr[cc][0]) + __uint_as_float(dr[cc][N2 - 1]) + bias[y & 3];
+#else
 #pragma unroll
-          for (int o = 0; o < ON; ++o) {
-            if (o < O) {
-              const float t = __uint_as_float(dr[o]) + bias[o];
-              if (o == 0 || t < tmin) { tmin = t; pm = o; }
-              const float s = sigmoid_from_neg_log2e(t);
-              sum += ex2_approx(s * kLog2e);
-              if (o == y) oy = s;
+          for (int g = 0; g < ON / 4; ++g) {
+            if (4 * g < O) {
+              const float4 b = *reinterpret_cast<const float4*>(bias + 4 * g);
+              float t[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                t[k] = (__uint_as_float(dr[cc][4 * g + k]) + __uint_as_float(dr[cc][ON + 4 * g + k])) +
+                       (__uint_as_float(dr[cc][2 * ON + 4 * g + k]) + (k == 0 ? b.x : k == 1 ? b.y : k == 2 ? b.z : b.w));
+              float s[4];
+              sigmoid4(t[0], t[1], t[2], t[3], s[0], s[1], s[2], s[3]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int o = 4 * g + k;
+                if (o < O) {
+                  if (o == 0 || t[k] < tmin) { tmin = t[k]; pm = o; }
+                  sum += ex2_approx(s[k] * kLog2e);
+                  if (o == y) oy = s[k];
+                }
+              }
             }
           }
+#endif
           if (y >= 0) {
             accL[uu][cc] += (double)(oy - kLn2 * lg2_approx(sum));
             accNc[uu][cc] += (pm == y);
@@ -338,8 +406,8 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
 #pragma unroll
     for (int uu = 0; uu < UPT; ++uu)
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int chain = uu * kUC + 2 * e + cc;
+      for (int cc = 0; cc < kCPW; ++cc) {
+        const int chain = uu * kUC + kCPW * e + cc;
         const double l = warp_sum(accL[uu][cc]);
         const int a = warp_sum(accNc[uu][cc]);
         const int b = warp_sum(accSq[uu][cc]);
@@ -351,7 +419,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
@@ -370,9 +438,8 @@ int tc_make_map_2d(CUtensorMap* map, void* base, uint64_t inner_elems, uint64_t 
 template <int HP, int ON, int STAGES>
 static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb1, const CUtensorMap& mw2, const Tc2Params& a, dim3 grid, cudaStream_t st) {
   constexpr int CH = 256 / HP;
-  constexpr int K2 = 4 * HP;
-  const size_t smem = 1024 + v2::kB1Bytes + (size_t)STAGES * v2::kAStageBytes + (size_t)(K2 / 64) * CH * ON * 128 + (size_t)CH * ON * 4 +
-                      (2 * STAGES + 1 + 4 + 2 * v2::kUC) * 8 + 16 + (size_t)CH * 12 * 8 + 64;
+  const size_t smem = 1024 + v2::kB1Bytes + (size_t)STAGES * v2::kAStageBytes + (size_t)CH * 3 * ON * 128 + (size_t)CH * ON * 4 +
+                      (2 * STAGES + 1 + 2 * 2 + 4 * v2::kUC) * 8 + 16 + (size_t)CH * 12 * 8 + 64;
   auto k = loglik_tc2_kernel<HP, ON, STAGES>;
   SAPT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<grid, v2::kThreads, smem, st>>>(ma, mb1, mw2, a);
@@ -387,10 +454,9 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   const DataSet& ds = p->set[which];
   if (R <= 0 || ds.n <= 0) return SAPT_OK;
   const int HP = p->H <= 16 ? 16 : 32;
-  const int ON = (p->O <= 16) ? 16 : 32;
-  if (ON > HP) { set_error("tcgen05 v2: O=%d needs H > 16", p->O); return SAPT_ERR_UNSUPPORTED; }
+  const int ON = 16;
+  if (p->O > ON) { set_error("tcgen05 path: O=%d > 16", p->O); return SAPT_ERR_UNSUPPORTED; }
   const int CH = 256 / HP;
-  const int K2 = 4 * HP;
   const int n_groups = (R + CH - 1) / CH;
   const int64_t n_tiles = ds.n_pad / v2::kTileM;
   const int base = p->num_sms / gcd_int2(n_groups, p->num_sms);
@@ -402,7 +468,7 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
 
   auto up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
   const size_t b1_bytes = (size_t)n_groups * 256 * v2::kKA * 2;
-  const size_t w2_bytes = (size_t)n_groups * CH * ON * K2 * 2;
+  const size_t w2_bytes = (size_t)n_groups * CH * 3 * ON * 64 * 2;
   const size_t bias_bytes = (size_t)n_groups * CH * ON * sizeof(float);
   const size_t part_bytes = (size_t)n_chunks * R * (sizeof(double) + 2 * sizeof(int32_t));
   int rc = ensure_workspace(p, up(b1_bytes) + up(w2_bytes) + up(bias_bytes) + up(part_bytes));
@@ -415,21 +481,20 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   int32_t* partNc = reinterpret_cast<int32_t*>(partL + (size_t)n_chunks * R);
   int32_t* partSq = partNc + (size_t)n_chunks * R;
 
-  tc2_pack_kernel<<<n_groups * CH, 128, 0, st>>>(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, ON, CH, b1img, w2img, bias2);
+  tc2_pack_kernel<<<n_groups * CH, 256, 0, st>>>(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, ON, CH, b1img, w2img, bias2);
   SAPT_CHECK_LAUNCH();
   CUtensorMap mb1, mw2;
   rc = tc_make_map_2d(&mb1, b1img, v2::kKA, (uint64_t)n_groups * 256, 256);
   if (rc) return rc;
-  rc = tc_make_map_2d(&mw2, w2img, (uint64_t)K2, (uint64_t)n_groups * CH * ON, (uint32_t)(CH * ON));
+  rc = tc_make_map_2d(&mw2, w2img, 64, (uint64_t)n_groups * CH * 3 * ON, (uint32_t)(4 * 3 * ON));
   if (rc) return rc;
   Tc2Params a{};
   a.y = ds.y; a.n_pad = ds.n_pad; a.bias2 = bias2; a.n_rows = n_rows; a.R = R; a.O = p->O;
   a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.partL = partL; a.partNc = partNc; a.partSq = partSq;
   dim3 grid((unsigned)n_chunks, (unsigned)n_groups);
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(ds.tmap);
-  if (HP == 16) rc = launch_tc2<16, 16, 3>(ma, mb1, mw2, a, grid, st);
-  else if (ON == 16) rc = launch_tc2<32, 16, 3>(ma, mb1, mw2, a, grid, st);
-  else rc = launch_tc2<32, 32, 2>(ma, mb1, mw2, a, grid, st);
+  if (HP == 16) rc = launch_tc2<16, 16, 4>(ma, mb1, mw2, a, grid, st);
+  else rc = launch_tc2<32, 16, 4>(ma, mb1, mw2, a, grid, st);
   if (rc) return rc;
   return launch_loglik_finalize(partL, partNc, partSq, (int)n_chunks, R, rows, n_rows, L, nc, sq, st);
 }
