@@ -14,7 +14,8 @@
 // (x = x1+x2+x3, w = w1+w2+w3 exactly; h = h1+h2 to 2^-16, unbiased) and the significant cross terms are
 // accumulated by pointing successive MMA K-steps at different (A chunk, B chunk) pairs — each piece is
 // stored once. MMA-1 (K = 7 x 16): (x1,w1) (x1,w2) (x2,w1) (x1,w3) (x2,w2) (x3,w1) (1,b): dropped terms
-// O(2^-24). MMA-2: (h1,w1) (h1,w2) (h2,w1) (h1,w3). Weights are pre-scaled by -log2(e) (biases +log2(e)),
+// O(2^-24). MMA-2: h1.[w1|w2|w3] and h2.[w1|w2] with the weight pieces side by side along N (three partial
+// sums per output, added by the epilogue), so each activation piece is read from TMEM once. Weights are pre-scaled by -log2(e) (biases +log2(e)),
 // so an accumulator is t = -log2(e) z and sigmoid(z) = 1 / (1 + 2^t).
 //
 // The SIMT side is bound by the SFU (MUFU) pipe, so reciprocals are batched four at a time
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
     if (lane == 0) {
       const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t idesc2a = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint32_t idesc2b = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ON >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t idesc2b = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * ON) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t b1_addr = smem_u32(sB1);
       const uint32_t w2_addr = smem_u32(sW2);
       mbar_wait(b_full, 0);
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
           const uint32_t d2 = tmem_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (kUC * N2) + c * N2);
           const uint32_t hv = tmem_hv + (uint32_t)(c * HP);
           const uint32_t wb = w2_addr + (uint32_t)(uu * kUC + c) * kW2ChainBytes;
-          // D2[:, 0:3ON] = h1 . [w1|w2|w3]  then  D2[:, 0:ON] += h2 . w1   (h piece = HP/2 TMEM columns)
+          // D2[:, 0:3ON] = h1 . [w1|w2|w3]  then  D2[:, 0:2ON] += h2 . [w1|w2]   (h piece = HP/2 TMEM columns)
 #pragma unroll
           for (int half = 0; half < HP / 16; ++half)
             tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), umma_desc_sw128(wb + half * 32), idesc2a, half ? 1u : 0u);
@@ -301,10 +302,9 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
           float h0, h1, h2, h3;
           sigmoid4(__uint_as_float(zr[cc][4 * j]), __uint_as_float(zr[cc][4 * j + 1]), __uint_as_float(zr[cc][4 * j + 2]),
                    __uint_as_float(zr[cc][4 * j + 3]), h0, h1, h2, h3);
-          // h1 piece = h rounded (half-up) to bf16, h2 piece = the exact residual rounded the same way:
-          // both zero-mean, so the dropped h2.w2 term does not bias z2
-          const uint32_t u0 = __float_as_uint(h0) + 0x8000u, u1 = __float_as_uint(h1) + 0x8000u;
-          const uint32_t u2 = __float_as_uint(h2) + 0x8000u, u3 = __float_as_uint(h3) + 0x8000u;
+          // h1 piece = h truncated to bf16 (one PRMT packs two), h2 piece = the exact, non-negative residual
+          // rounded half-up to bf16. The residual is not zero-mean, so MMA-2 also accumulates h2.w2.
+          const uint32_t u0 = __float_as_uint(h0), u1 = __float_as_uint(h1), u2 = __float_as_uint(h2), u3 = __float_as_uint(h3);
           hv[cc][2 * j] = __byte_perm(u0, u1, 0x7632);
           hv[cc][2 * j + 1] = __byte_perm(u2, u3, 0x7632);
           const uint32_t r0 = __float_as_uint(h0 - __uint_as_float(u0 & 0xffff0000u)) + 0x8000u;

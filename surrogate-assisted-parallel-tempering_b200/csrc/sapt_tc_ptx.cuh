@@ -21,6 +21,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a lost TMA/MMA completion must surface as a launch failure, never as a hung GPU.
+// try_wait carries a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
+// expires) instead of burning issue slots that the epilogue warps need.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
@@ -28,14 +30,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(100000u)
         : "memory");
     if (done) return;
-    if (spin > (1u << 24)) {  // each failed try_wait already sleeps up to the HW time limit
+    if (spin > (1u << 16)) {  // > 6 s of suspended waiting
       printf("sapt: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
       __trap();
     }
