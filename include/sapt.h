@@ -149,6 +149,9 @@ typedef struct {
   const double* ku_inject;  /* [R_slots] or NULL */
   int32_t* is_sur;          /* [R] */
   int32_t* true_rows; int32_t* n_true; int32_t* sur_rows; int32_t* n_sur;
+  /* CUDA-graph replay: if non-NULL the effective step is step + *step_dev (read on the device), so a captured
+   * sequence of launches can be replayed for later steps without re-recording (see sapt_advance) */
+  const int32_t* step_dev;
 } sapt_propose_args;
 int sapt_propose(const sapt_propose_args* a, void* stream);
 
@@ -224,6 +227,7 @@ typedef struct {
   int capture;              /* 1: capture here (RW/RV). 0: already captured by sapt_lg_first_eval */
   /* LG: the first evaluation's tempered likelihood feeds surg[:,0/2] and the window */
   const double* surg_first; /* [R] or NULL */
+  const int32_t* step_dev;  /* see sapt_propose_args.step_dev */
 } sapt_accept_args;
 int sapt_mh_accept(const sapt_accept_args* a, void* stream);
 
@@ -239,6 +243,7 @@ typedef struct {
   int use_langevin; double l_prob; const double* lx2_inject;
   int32_t* lang_rows; int32_t* n_lang;
   float* train_theta; double* train_L; int32_t* train_count; int train_cap;
+  const int32_t* step_dev;  /* see sapt_propose_args.step_dev */
 } sapt_lg_first_args;
 int sapt_lg_first_eval(const sapt_lg_first_args* a, void* stream);
 
@@ -257,6 +262,13 @@ int sapt_swap_sweep(int R_global, double* lik_post, const double* temperature, i
                     uint32_t flags, uint32_t seed, int sweep, const double* u_inject,
                     uint8_t* swapped, int32_t* num_swap, int32_t* src_slot,
                     int row0, int R_local, int32_t* slot_of_row_local, void* stream);
+/* same, with the sweep index taken as sweep + *sweep_dev (graph replay) */
+int sapt_swap_sweep_dev(int R_global, double* lik_post, const double* temperature, int32_t* row_of_slot,
+                        uint32_t flags, uint32_t seed, int sweep, const int32_t* sweep_dev, const double* u_inject,
+                        uint8_t* swapped, int32_t* num_swap, int32_t* src_slot,
+                        int row0, int R_local, int32_t* slot_of_row_local, void* stream);
+/* *counter += delta on the device, in stream order (advances the step / sweep counters between captured steps) */
+int sapt_advance(int32_t* counter, int delta, void* stream);
 
 /* ---- Philox4x32-10 exposed for the known-answer test */
 int sapt_philox_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -28,7 +28,7 @@ class ProposeArgs(C.Structure):
                 ("seed", u32), ("kind", C.c_int), ("step", C.c_int), ("z_inject", vp),
                 ("decide", C.c_int), ("redraw", C.c_int), ("surrogate_ready", C.c_int),
                 ("surrogate_prob", f64), ("gate", C.c_int), ("z2_inject", vp), ("ku_inject", vp),
-                ("is_sur", vp), ("true_rows", vp), ("n_true", vp), ("sur_rows", vp), ("n_sur", vp)]
+                ("is_sur", vp), ("true_rows", vp), ("n_true", vp), ("sur_rows", vp), ("n_sur", vp), ("step_dev", vp)]
 
 
 class ChainState(C.Structure):
@@ -49,7 +49,7 @@ class AcceptArgs(C.Structure):
                 ("L_train", vp), ("nc_train", vp), ("sq_train", vp), ("L_test", vp), ("nc_test", vp), ("sq_test", vp),
                 ("n_train", i64), ("n_test", i64), ("prior_prop", vp), ("sur_s", vp), ("min_y", f64), ("max_y", f64),
                 ("seed", u32), ("u_inject", vp), ("train_theta", vp), ("train_L", vp), ("train_count", vp),
-                ("train_cap", C.c_int), ("capture", C.c_int), ("surg_first", vp)]
+                ("train_cap", C.c_int), ("capture", C.c_int), ("surg_first", vp), ("step_dev", vp)]
 
 
 class LgFirstArgs(C.Structure):
@@ -57,7 +57,7 @@ class LgFirstArgs(C.Structure):
                 ("step", C.c_int), ("seed", u32), ("true_rows", vp), ("n_true", vp), ("L_train", vp),
                 ("surg_first", vp), ("use_langevin", C.c_int), ("l_prob", f64), ("lx2_inject", vp),
                 ("lang_rows", vp), ("n_lang", vp), ("train_theta", vp), ("train_L", vp), ("train_count", vp),
-                ("train_cap", C.c_int)]
+                ("train_cap", C.c_int), ("step_dev", vp)]
 
 
 class SaptError(RuntimeError):
@@ -96,6 +96,8 @@ def lib():
     L.sapt_mh_accept.argtypes = [C.POINTER(AcceptArgs), vp]
     L.sapt_lg_first_eval.argtypes = [C.POINTER(LgFirstArgs), vp]
     L.sapt_swap_sweep.argtypes = [C.c_int, vp, vp, vp, u32, u32, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
+    L.sapt_swap_sweep_dev.argtypes = [C.c_int, vp, vp, vp, u32, u32, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
+    L.sapt_advance.argtypes = [vp, C.c_int, vp]
     L.sapt_philox_host.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     L.sapt_philox_fill.argtypes = [u32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.sapt_struct_sizes.argtypes = [C.POINTER(i32)]
@@ -122,5 +124,5 @@ EXPORTS = [
     "sapt_problem_create", "sapt_problem_create_f32", "sapt_problem_destroy", "sapt_problem_num_param",
     "sapt_problem_rows", "sapt_problem_tc_supported", "sapt_loglik", "sapt_loglik_host", "sapt_evaluate_proposal",
     "sapt_prior", "sapt_propose", "sapt_langevin", "sapt_surrogate_predict", "sapt_mh_accept", "sapt_lg_first_eval",
-    "sapt_swap_sweep", "sapt_philox_host", "sapt_philox_fill",
+    "sapt_swap_sweep", "sapt_swap_sweep_dev", "sapt_advance", "sapt_philox_host", "sapt_philox_fill",
 ]

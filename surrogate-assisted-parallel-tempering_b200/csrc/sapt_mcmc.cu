@@ -34,11 +34,12 @@ __global__ void __launch_bounds__(256) propose_kernel(sapt_propose_args a) {
   if ((int)blockIdx.x >= nrows) return;
   const int row = a.rows ? a.rows[blockIdx.x] : (int)blockIdx.x;
   const int slot = a.slot_of_row ? a.slot_of_row[row] : (row + a.slot_offset);
+  const int step_i = a.step + (a.step_dev ? *a.step_dev : 0);
   if (threadIdx.x == 0) {
     int sur = 0;
     if (a.decide) {
-      const double ku = a.ku_inject ? a.ku_inject[slot] : (double)philox_uniform(a.seed, SAPT_STREAM_KU, a.step, (uint32_t)slot, 0);
-      sur = (a.surrogate_ready && ku < a.surrogate_prob && a.step >= a.gate + 1) ? 1 : 0;
+      const double ku = a.ku_inject ? a.ku_inject[slot] : (double)philox_uniform(a.seed, SAPT_STREAM_KU, step_i, (uint32_t)slot, 0);
+      sur = (a.surrogate_ready && ku < a.surrogate_prob && step_i >= a.gate + 1) ? 1 : 0;
       a.is_sur[row] = sur;
       if (sur) { const int k = atomicAdd(a.n_sur, 1); a.sur_rows[k] = row; }
       else     { const int k = atomicAdd(a.n_true, 1); a.true_rows[k] = row; }
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(256) propose_kernel(sapt_propose_args a) {
     const int nblk = (a.P + 3) >> 2;
     for (int q = threadIdx.x; q < nblk; q += blockDim.x) {
       float z[4];
-      philox_normal4(a.seed, kind, a.step, (uint32_t)slot, (uint32_t)q, z);
+      philox_normal4(a.seed, kind, step_i, (uint32_t)slot, (uint32_t)q, z);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int i = 4 * q + j;
@@ -88,6 +89,7 @@ __global__ void lg_first_kernel(sapt_lg_first_args a) {
   if ((int)blockIdx.x >= n) return;
   const int row = a.true_rows ? a.true_rows[blockIdx.x] : (int)blockIdx.x;
   const int slot = a.st.slot_of_row[row];
+  const int step_i = a.step + (a.step_dev ? *a.step_dev : 0);
   __shared__ int s_cnt;
   if (threadIdx.x == 0) {
     const double L = a.L_train[row];
@@ -100,7 +102,7 @@ __global__ void lg_first_kernel(sapt_lg_first_args a) {
     }
     s_cnt = cnt;
     if (a.use_langevin) {
-      const double lx = a.lx2_inject ? a.lx2_inject[slot] : (double)philox_uniform(a.seed, SAPT_STREAM_LX2, a.step, (uint32_t)slot, 0);
+      const double lx = a.lx2_inject ? a.lx2_inject[slot] : (double)philox_uniform(a.seed, SAPT_STREAM_LX2, step_i, (uint32_t)slot, 0);
       if (lx < a.l_prob) { const int k = atomicAdd(a.n_lang, 1); a.lang_rows[k] = row; }
     }
   }
@@ -119,11 +121,12 @@ __global__ void __launch_bounds__(128) mh_accept_kernel(sapt_accept_args a) {
   const int row = blockIdx.x;
   const int slot = a.st.slot_of_row[row];
   const int S = a.hist.n_slots;
+  const int step_i = a.step + (a.step_dev ? *a.step_dev : 0);
   __shared__ int s_accept, s_cnt;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const double NANV = __longlong_as_double(0x7ff8000000000000LL);
-  const int64_t hi = (int64_t)a.step * S + slot;        // history row i
-  const int64_t ho = (int64_t)(a.step + 1) * S + slot;  // history row i+1
+  const int64_t hi = (int64_t)step_i * S + slot;        // history row i
+  const int64_t ho = (int64_t)(step_i + 1) * S + slot;  // history row i+1
   if (threadIdx.x == 0) {
     const double T = a.st.temperature[slot];
     const bool sur = a.is_sur && a.is_sur[row];
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(128) mh_accept_kernel(sapt_accept_args a) {
     if (diff != diff) mh = 1.0;
     else if (diff >= 0.0) mh = 1.0;
     else mh = exp(diff);
-    const double u = a.u_inject ? a.u_inject[slot] : (double)philox_uniform(a.seed, SAPT_STREAM_U, a.step, (uint32_t)slot, 0);
+    const double u = a.u_inject ? a.u_inject[slot] : (double)philox_uniform(a.seed, SAPT_STREAM_U, step_i, (uint32_t)slot, 0);
     const int nacc = a.st.naccept[slot];
     const bool acc = u < mh;
     double h_lhood, h_rtr, h_rte, h_atr, h_ate;
@@ -220,14 +223,17 @@ __global__ void __launch_bounds__(128) mh_accept_kernel(sapt_accept_args a) {
 // -------------------------------------------------------------------------------------------
 // replica exchange: sequential sweep over all chains                 RW:869-898, RW:1095-1099
 // -------------------------------------------------------------------------------------------
+__global__ void advance_kernel(int32_t* counter, int delta) { *counter += delta; }
+
 __global__ void swap_sweep_kernel(int R, double* lik_post, const double* temperature, int32_t* row_of_slot, uint32_t flags,
-                                  uint32_t seed, int sweep, const double* u_inject, uint8_t* swapped, int32_t* num_swap,
+                                  uint32_t seed, int sweep_base, const int32_t* sweep_dev, const double* u_inject, uint8_t* swapped, int32_t* num_swap,
                                   int32_t* src_slot, int row0, int R_local, int32_t* slot_of_row_local) {
   extern __shared__ double sh[];
   double* post = sh;                                   // [R] message likelihoods
   double* uu = sh + R;                                 // [R-1]
   int32_t* src = reinterpret_cast<int32_t*>(uu + R);   // [R]
   int32_t* rows = src + R;                             // [R]
+  const int sweep = sweep_base + (sweep_dev ? *sweep_dev : 0);
   for (int k = threadIdx.x; k < R; k += blockDim.x) {
     // RW:623 posts likelihood*adapttemp ; LG:805 posts the tempered value
     post[k] = (flags & SAPT_F_POST_TEMPERED) ? lik_post[k] : lik_post[k] * temperature[k];
@@ -318,15 +324,30 @@ extern "C" int sapt_mh_accept(const sapt_accept_args* a, void* stream) {
   return SAPT_OK;
 }
 
+extern "C" int sapt_advance(int32_t* counter, int delta, void* stream) {
+  SAPT_REQUIRE(counter, "sapt_advance");
+  advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}
+
 extern "C" int sapt_swap_sweep(int R_global, double* lik_post, const double* temperature, int32_t* row_of_slot, uint32_t flags,
                                uint32_t seed, int sweep, const double* u_inject, uint8_t* swapped, int32_t* num_swap,
                                int32_t* src_slot, int row0, int R_local, int32_t* slot_of_row_local, void* stream) {
+  return sapt_swap_sweep_dev(R_global, lik_post, temperature, row_of_slot, flags, seed, sweep, nullptr, u_inject, swapped, num_swap,
+                             src_slot, row0, R_local, slot_of_row_local, stream);
+}
+
+extern "C" int sapt_swap_sweep_dev(int R_global, double* lik_post, const double* temperature, int32_t* row_of_slot, uint32_t flags,
+                                   uint32_t seed, int sweep, const int32_t* sweep_dev, const double* u_inject, uint8_t* swapped,
+                                   int32_t* num_swap, int32_t* src_slot, int row0, int R_local, int32_t* slot_of_row_local,
+                                   void* stream) {
   SAPT_REQUIRE(R_global >= 1 && lik_post && temperature && row_of_slot, "sapt_swap_sweep");
   const size_t smem = (size_t)R_global * (2 * sizeof(double) + 2 * sizeof(int32_t));
   if (smem > 200 * 1024) { set_error("sapt_swap_sweep: %d chains exceed the single-CTA sweep capacity", R_global); return SAPT_ERR_UNSUPPORTED; }
   if (smem > 48 * 1024) SAPT_CUDA(cudaFuncSetAttribute(swap_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  swap_sweep_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(R_global, lik_post, temperature, row_of_slot, flags, seed, sweep, u_inject,
-                                                            swapped, num_swap, src_slot, row0, R_local, slot_of_row_local);
+  swap_sweep_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(R_global, lik_post, temperature, row_of_slot, flags, seed, sweep, sweep_dev,
+                                                            u_inject, swapped, num_swap, src_slot, row0, R_local, slot_of_row_local);
   SAPT_CHECK_LAUNCH();
   return SAPT_OK;
 }

@@ -179,6 +179,11 @@ class PTEngine:
         if sp.lg_flow: self.flags |= _lib.F_REDRAW_ON_SURROGATE
         if cfg.record_history and cfg.record_pos: self.flags |= _lib.F_RECORD_POS
         self.evals = 0  # replica x row likelihood evaluations issued (host-side count of the worst case)
+        # device-side step / sweep counters: kernels read step = base + *counter, so a captured CUDA graph of
+        # one exchange interval can be replayed for every later interval
+        self.step_dev = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._graph_mode = False
+        self._graphs = {}
         self._segments = [(0, self._hosted_mask())]  # (first history row, hosted mask) per binding epoch
 
     # ------------------------------------------------------------------------------------
@@ -235,8 +240,13 @@ class PTEngine:
 
     # ------------------------------------------------------------------------------------
     def step(self, i: int):
+        """Enqueue one MCMC step of every local chain (no host synchronisation). In graph mode `i` is the
+        offset inside the captured segment and the absolute step lives in self.step_dev[0]."""
         cfg, sp, L = self.cfg, self.spec, self.L
         st = current_stream_ptr()
+        sdev = self.step_dev[0:1].data_ptr() if self._graph_mode else None
+        if self._graph_mode:
+            i = 0  # the device counter is advanced after every captured step: the absolute step is *step_dev
         use_sur = bool(cfg.use_surrogate)
         self.counters[:3].zero_()
         gate = cfg.swap_interval if sp.gate_on_swap_interval else cfg.surrogate_interval
@@ -244,7 +254,7 @@ class PTEngine:
         a.base = self.theta.data_ptr(); a.proposal = self.prop.data_ptr(); a.ld = self.ld; a.R = self.R; a.P = self.P
         a.slot_of_row = self.slot_of_row.data_ptr(); a.slot_offset = 0
         a.step_w = cfg.step_w; a.sigma_squared = cfg.sigma_squared; a.prior_prop = self.prior_prop.data_ptr()
-        a.seed = cfg.seed & 0xFFFFFFFF; a.kind = _lib.STREAM_Z1; a.step = i
+        a.seed = cfg.seed & 0xFFFFFFFF; a.kind = _lib.STREAM_Z1; a.step = i; a.step_dev = sdev
         z1 = self._inj("z1", i); a.z_inject = z1.data_ptr() if z1 is not None else None
         a.decide = 1 if use_sur else 0
         a.redraw = 1 if sp.lg_flow else 0
@@ -256,7 +266,7 @@ class PTEngine:
         a.sur_rows = self.sur_rows.data_ptr(); a.n_sur = self.counters[1:2].data_ptr()
         _lib.check(L.sapt_propose(C.byref(a), st), "sapt_propose")
 
-        sur_possible = use_sur and self.surrogate.ready and i >= gate + 1 and cfg.surrogate_prob > 0
+        sur_possible = use_sur and self.surrogate.ready and cfg.surrogate_prob > 0 and (self._graph_mode or i >= gate + 1)
         true_rows = self.true_rows if use_sur else None
         n_true = self.counters[0:1] if use_sur else None
         if sur_possible:
@@ -271,7 +281,7 @@ class PTEngine:
             self.p.loglik(self.prop, 0, rows=true_rows, n_rows=n_true, out=out_tr, path=cfg.path)
             f = _lib.LgFirstArgs()
             f.proposal = self.prop.data_ptr(); f.ld = self.ld; f.R = self.R; f.P = self.P
-            f.st = self._chain_state(); f.step = i; f.seed = cfg.seed & 0xFFFFFFFF
+            f.st = self._chain_state(); f.step = i; f.step_dev = sdev; f.seed = cfg.seed & 0xFFFFFFFF
             f.true_rows = _ptr(true_rows); f.n_true = _ptr(n_true)
             f.L_train = self.L_train.data_ptr(); f.surg_first = self.surg_first.data_ptr()
             f.use_langevin = 1 if cfg.use_langevin else 0; f.l_prob = cfg.l_prob
@@ -292,7 +302,7 @@ class PTEngine:
                 b.base = self.theta_gd.data_ptr(); b.proposal = self.prop.data_ptr(); b.ld = self.ld; b.R = self.R; b.P = self.P
                 b.slot_of_row = self.slot_of_row.data_ptr(); b.rows = self.lang_rows.data_ptr(); b.n_rows = self.counters[2:3].data_ptr()
                 b.step_w = cfg.step_w; b.sigma_squared = cfg.sigma_squared; b.prior_prop = self.prior_prop.data_ptr()
-                b.seed = cfg.seed & 0xFFFFFFFF; b.kind = _lib.STREAM_Z2; b.step = i
+                b.seed = cfg.seed & 0xFFFFFFFF; b.kind = _lib.STREAM_Z2; b.step = i; b.step_dev = sdev
                 b.z_inject = z2.data_ptr() if z2 is not None else None
                 b.decide = 0
                 _lib.check(L.sapt_propose(C.byref(b), st), "sapt_propose(langevin)")
@@ -315,7 +325,7 @@ class PTEngine:
 
         m = _lib.AcceptArgs()
         m.theta = self.theta.data_ptr(); m.proposal = self.prop.data_ptr(); m.ld = self.ld; m.R = self.R; m.P = self.P
-        m.st = self._chain_state(); m.hist = self._history(); m.step = i; m.flags = self.flags
+        m.st = self._chain_state(); m.hist = self._history(); m.step = i; m.step_dev = sdev; m.flags = self.flags
         m.is_sur = self.is_sur.data_ptr() if use_sur else None
         m.L_train = self.L_train.data_ptr(); m.nc_train = self.nc_train.data_ptr(); m.sq_train = self.sq_train.data_ptr()
         m.L_test = self.L_test.data_ptr(); m.nc_test = self.nc_test.data_ptr(); m.sq_test = self.sq_test.data_ptr()
@@ -421,11 +431,66 @@ class PTEngine:
         if do_train:
             self.surrogate_rendezvous(i)
 
-    def run(self, steps: Optional[int] = None):
+    def run(self, steps: Optional[int] = None, graph: Optional[bool] = None):
+        """Run the chain loop. `graph=True` captures the launches of one interval between rendezvous points in a
+        CUDA graph and replays it (the step index is read from device memory), which removes the per-launch host
+        cost that dominates small problems (C1/C2: microseconds of GPU work per step). Default: on for
+        single-rank Philox runs whose per-step work is small."""
         n = self.cfg.samples - 1 if steps is None else steps
+        if graph is None:
+            graph = (self.inj is None and self.cfg.world == 1 and
+                     self.R * (self.p.n[0] + self.p.n[1]) <= (1 << 24))
+        if not graph or self.inj is not None or self.cfg.world != 1:
+            for i in range(n):
+                self.step(i)
+                self.rendezvous(i)
+            return
+        self._run_graphed(n)
+
+    def _rendezvous_steps(self, n):
+        cfg, sp = self.cfg, self.spec
+        pts = set()
         for i in range(n):
-            self.step(i)
-            self.rendezvous(i)
+            do_swap = sp.swap and (i % cfg.swap_interval == 0) and (sp.swap_at_zero or i != 0)
+            do_train = (do_swap and cfg.use_surrogate) if sp.common_interval else (
+                cfg.use_surrogate and (i % cfg.surrogate_interval == 0) and (i != 0))
+            if do_swap or do_train:
+                pts.add(i)
+        return pts
+
+    def _run_graphed(self, n):
+        pts = self._rendezvous_steps(n)
+        i = 0
+        self.step(0)                       # eager warm-up step: grows workspaces outside any capture
+        self.rendezvous(0)
+        i = 1
+        while i < n:
+            j = i                          # segment [i, j]: ends at the next rendezvous step or at n-1
+            while j not in pts and j < n - 1:
+                j += 1
+            length = j - i + 1
+            key = (length, self.surrogate.signature, self.surrogate.ready)
+            g = self._graphs.get(key)
+            self.step_dev[0] = i
+            if g is None and length >= 4:
+                self._graph_mode = True
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        for k in range(length):
+                            self.step(k)
+                            _lib.check(self.L.sapt_advance(self.step_dev[0:1].data_ptr(), 1, current_stream_ptr()), "sapt_advance")
+                finally:
+                    self._graph_mode = False
+                self._graphs = {key: g}    # one live graph: surrogate state changes invalidate older ones
+                self.step_dev[0] = i       # capture does not execute
+            if g is not None:
+                g.replay()
+            else:
+                for k in range(i, j + 1):
+                    self.step(k)
+            self.rendezvous(j)
+            i = j + 1
 
     # ------------------------------------------------------------------------------------
     def results(self) -> dict:

@@ -320,3 +320,136 @@ def test_engine_philox_run_is_deterministic_and_sane(lib):
     d = np.diff(r4["pos_w"][0, 1:], axis=0)
     moved = d[np.any(d != 0, axis=1)]
     assert 0.015 < moved.std() < 0.04
+
+
+# ---- the remaining BASELINE.json configs at their topologies (synthetic rows, oracle as checker) ----
+def _synthetic(D, O, n, seed):
+    rs = np.random.RandomState(seed)
+    x = rs.standard_normal((n, D)); y = rs.randint(0, O, n)
+    return np.concatenate([x, y[:, None].astype(np.float64)], axis=1)
+
+
+@pytest.mark.parametrize("topo,name", [([54, 64, 7], "C4 covtype-shape"), ([6, 25, 18], "C5 chess-shape"), ([34, 50, 2], "C2 ionosphere"),
+                                       ([9, 12, 2], "C1 cancer"), ([16, 30, 10], "C3 pendigit-shape")])
+def test_config_topologies_loglik_and_prior(lib, topo, name):
+    from sapt_b200.problem import Problem, prior
+    data = _synthetic(topo[0], topo[2], 777, 5)
+    test = _synthetic(topo[0], topo[2], 130, 6)
+    P = so.num_param(topo)
+    rs = np.random.RandomState(9)
+    W = (rs.standard_normal((11, P)) * 0.7).astype(np.float32)
+    prob = Problem(topo, data, test)
+    th = torch.as_tensor(W).cuda()
+    for path in _paths(lib, prob):
+        for which, d in ((0, data), (1, test)):
+            L, nc, sq = (t.cpu().numpy() for t in prob.loglik(th, which, path=path))
+            ref = [so.loglik_stats(d, W[k].astype(np.float64), topo) for k in range(W.shape[0])]
+            np.testing.assert_allclose(L, [r[0] for r in ref], rtol=3e-6, err_msg=f"{name} path {path}")
+            assert np.max(np.abs(nc - np.array([r[1] for r in ref]))) <= 1, name     # exact up to an fp32 near-tie
+            assert np.max(np.abs(sq - np.array([r[2] for r in ref]))) <= (topo[2] - 1) ** 2, name
+    pr = prior(th, P, 25.0).cpu().numpy()
+    np.testing.assert_allclose(pr, [so.prior_likelihood(25, 0, 0, W[k].astype(np.float64), topo) for k in range(11)], rtol=1e-12)
+
+
+def test_c4_langevin_batch_and_exact_at_covtype_topology(lib):
+    from sapt_b200.problem import Problem
+    topo = [54, 64, 7]
+    data = _synthetic(*[topo[0], topo[2]], 300, 11)
+    P = so.num_param(topo)
+    W = (np.random.RandomState(3).standard_normal((5, P)) * 0.3).astype(np.float32)
+    prob = Problem(topo, data, None)
+    th = torch.as_tensor(W).cuda()
+    out = prob.langevin(th, 0.5, mode=0).cpu().numpy().astype(np.float64)
+    for k in range(5):
+        ref = so.langevin_gradient(data, W[k].astype(np.float64), topo, 0.5, 1)
+        assert np.max(np.abs(out[k] - ref)) <= 1e-4 * np.max(np.abs(ref)) + 1e-6
+    lr = 0.001
+    outb = prob.langevin(th, lr, mode=1, batch_scale=1.0 / data.shape[0]).cpu().numpy().astype(np.float64)
+    for k in range(5):
+        g = so.langevin_batch_gradient(data, W[k].astype(np.float64), topo) / data.shape[0]
+        got = (outb[k] - W[k].astype(np.float64)) / lr
+        assert np.max(np.abs(got - g)) <= 1e-4 * np.max(np.abs(g)) + 2e-4
+
+
+def test_c5_engine_with_surrogate_at_chess_topology(lib):
+    """C5-shape (6-25-18) chains with surrogate_prob 0.5 and a fixed surrogate MLP (topology 3), injected
+    streams generated here; the device engine must reproduce the oracle's decisions."""
+    from sapt_b200.engine import EngineConfig, PTEngine
+    from sapt_b200.problem import Problem
+    topo = [6, 25, 18]
+    train = _synthetic(6, 18, 200, 21); test = _synthetic(6, 18, 80, 22)
+    P = so.num_param(topo); R, S = 6, 30
+    rs = np.random.RandomState(5)
+    streams = so.Streams(z1=rs.standard_normal((S - 1, R, P)), z2=rs.standard_normal((S - 1, R, P)), lx2=rs.uniform(size=(S - 1, R)),
+                         ku=rs.uniform(size=(S - 1, R)), u=rs.uniform(size=(S - 1, R)), swap_u=rs.uniform(size=(S, R - 1)))
+    sw = [so.make_surrogate_weights(P, 3, 40 + s) for s in range(8)]
+    temps = so.assign_temperatures(R, 4.0)
+    w0 = rs.standard_normal(P) * 0.5
+    kw = dict(traindata=train, testdata=test, topology=topo, temperatures=temps, w0=w0, samples=S, swap_interval=4,
+              surrogate_interval=4, surrogate_prob=0.5, streams=streams, use_langevin=False, learn_rate=0.5,
+              surrogate_weights_per_signature=sw)
+    ora = so.run_pt("rw", **kw)
+    prob = Problem(topo, train, test)
+    cfg = EngineConfig(variant="rw", samples=S, swap_interval=4, surrogate_interval=4, surrogate_prob=0.5, use_surrogate=True,
+                       surrogate_topology=3, seed=1)
+    inject = dict(z1=streams.z1, z2=streams.z2, lx2=streams.lx2, ku=streams.ku, u=streams.u, swap_u=streams.swap_u,
+                  surrogate_weights_per_signature=sw)
+    eng = PTEngine(prob, temps, cfg, inject=inject)
+    eng.initialize(w0); eng.run(); torch.cuda.synchronize()
+    res = eng.results()
+    assert ora["is_surrogate_step"].sum() > 10
+    assert np.array_equal(res["is_surrogate_step"], ora["is_surrogate_step"])
+    assert np.array_equal(res["accepted"], ora["accepted"])
+    for a, b in zip(res["swap_decisions"], ora["swap_decisions"]):
+        assert np.array_equal(a, b)
+    np.testing.assert_allclose(res["pos_w"], ora["pos_w"], rtol=0, atol=5e-6)
+    m = np.isfinite(ora["surg_likeh_list"])
+    np.testing.assert_allclose(res["surg_likeh_list"][m], ora["surg_likeh_list"][m], rtol=3e-5, atol=3e-4)
+
+
+@pytest.mark.parametrize("variant,use_sur,use_lg", [("rw", False, False), ("rw", True, False), ("lg", True, True)])
+def test_cuda_graph_replay_equals_eager(lib, variant, use_sur, use_lg):
+    """The captured-and-replayed interval (device-side step counter) must reproduce the eager launches bit for bit."""
+    from sapt_b200.engine import EngineConfig, PTEngine
+    from sapt_b200.ladder import assign_temperatures
+    from sapt_b200.problem import Problem
+    g = gu.load("unit_cancer")
+    topo = [int(v) for v in g["topology"]]
+    prob = Problem(topo, g["train"][:200], g["test"][:80])
+    sw = [so.make_surrogate_weights(prob.P, 1, 70 + s) for s in range(12)]
+
+    def run(graph):
+        cfg = EngineConfig(variant=variant, samples=64, swap_interval=9, surrogate_interval=11, surrogate_prob=0.4,
+                           use_surrogate=use_sur, use_langevin=use_lg, learn_rate=0.05, seed=5)
+        eng = PTEngine(prob, assign_temperatures(6, 4.0), cfg, surrogate_trainer=lambda batch, sig: sw[sig - 1])
+        eng.initialize(g["W"][1])
+        eng.run(graph=graph); torch.cuda.synchronize()
+        return eng.results(), eng
+
+    (a, ea), (b, eb) = run(False), run(True)
+    assert len(eb._graphs) == 1, "graph mode did not capture"
+    for k in ("accepted", "is_surrogate_step", "pos_w", "accept_list", "naccept", "row_of_slot"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("lhood_list", "surg_likeh_list", "acc_train", "rmse_test"):
+        assert np.array_equal(np.nan_to_num(a[k], nan=-1.0, posinf=-2.0), np.nan_to_num(b[k], nan=-1.0, posinf=-2.0)), k
+    assert a["num_swap"] == b["num_swap"] and len(a["swap_decisions"]) == len(b["swap_decisions"])
+    if use_sur:
+        assert a["is_surrogate_step"].sum() > 0
+
+
+def test_c1_posterior_accuracy_envelope(lib):
+    """C1 end to end through the reference-facing class: Cancer 9-12-2, 8 chains, random-walk PT, no surrogate.
+    The reference's committed runs give train 95.6 +- 0.6 / test 98.8 +- 0.5 % for this problem
+    (master_result_file.txt:5); a correct sampler must land in that neighbourhood."""
+    from sapt_b200 import ParallelTempering
+    g = gu.load("unit_cancer")
+    topo = [int(v) for v in g["topology"]]
+    pt = ParallelTempering(False, False, 0.5, False, g["train"], g["test"], topo, 8, 4.0, 8 * 3000, 50, 50, 0.0, "/tmp/x", "/tmp/x", 1,
+                           variant="rw", seed=3)
+    pt.initialize_chains(0.5)
+    out = pt.run_chains()
+    pos_w, _, _, rmse_tr, rmse_te, acc_tr, acc_te, accept_list, swap_perc, lik, rmse_surr, surr_list, accept = out
+    assert pos_w.shape == (pt.num_param, 8 * 1500) and acc_tr.shape == (8 * 1500, 1) and accept_list.shape == (8, 3000)
+    assert lik.shape == (8 * 2999, 2)
+    assert acc_tr.mean() > 90.0 and acc_te.mean() > 94.0, (acc_tr.mean(), acc_te.mean())
+    assert 20.0 < accept < 99.0 and 0.0 < swap_perc < 100.0
