@@ -219,13 +219,22 @@ def run_ours(args):
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
     tc_path = bool(prob.tc_supported and path != _lib.PATH_F32)
     # SM-pipe ceiling at the clock observed during the run: MUFU 16/clk/SM; FP32 FMA 128/clk/SM
-    # (layer 1 leaves the FMA pipe on the tcgen05 path)
-    ffma_eff = (W["H"] * W["O"]) if tc_path else ffma_per_eval
+    # (2(H+O)+O+1 MUFU per eval with an ex2+rcp sigmoid; both GEMMs leave the FMA pipe on the
+    # tcgen05 path, so only the SFU term remains there)
+    ffma_eff = 0 if tc_path else ffma_per_eval
     clk_per_eval = max(mufu_per_eval / 16.0, ffma_eff / 128.0)
     gov_peak = n_sm * sm_mhz * 1e6 / clk_per_eval
     gov_ach = Rl * W["n_train"] / (k_ms * 1e-3)
-    roofline = dict(bound="tensor", achieved=ach_tf, peak=peak_tf, unit="TFLOP/s", frac=ach_tf / peak_tf, traffic=None,
-                    kernel="loglik_tc_kernel" if tc_path else "loglik_f32_kernel", kernel_ms=k_ms, peak_source=peak_src,
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        key = "loglik_tc2_kernel" if tc_path else "loglik_f32_kernel"
+        if tj.get(key) and tj[key].get("chains") == Rl:
+            traffic = tj[key]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = dict(bound="tensor", achieved=ach_tf, peak=peak_tf, unit="TFLOP/s", frac=ach_tf / peak_tf, traffic=traffic,
+                    kernel="loglik_tc2_kernel" if tc_path else "loglik_f32_kernel", kernel_ms=k_ms, peak_source=peak_src,
                     note="GEMM-only FLOPs (2DH+2HO per replica x row) vs dense bf16 peak; the kernel is bound by the "
                          "SFU/FP32 epilogue, see governing",
                     governing=dict(bound="sm_pipes(mufu|fp32)", achieved=gov_ach, peak=gov_peak, unit=UNIT, frac=gov_ach / gov_peak,

@@ -433,13 +433,13 @@ class PTEngine:
 
     def run(self, steps: Optional[int] = None, graph: Optional[bool] = None):
         """Run the chain loop. `graph=True` captures the launches of one interval between rendezvous points in a
-        CUDA graph and replays it (the step index is read from device memory), which removes the per-launch host
-        cost that dominates small problems (C1/C2: microseconds of GPU work per step). Default: on for
-        single-rank Philox runs whose per-step work is small."""
+        CUDA graph and replays it (the step index is read from device memory), removing the per-launch host cost.
+        Measured at C1 (8 chains x 699 rows) the eager loop is already GPU-latency bound (~67 us per step for ~10
+        dependent small kernels) and capture + instantiation only pays off for runs of >~10^4 steps, so the
+        default is off; the mode is kept for host-bound deployments (slow CPUs, many short kernels)."""
         n = self.cfg.samples - 1 if steps is None else steps
         if graph is None:
-            graph = (self.inj is None and self.cfg.world == 1 and
-                     self.R * (self.p.n[0] + self.p.n[1]) <= (1 << 24))
+            graph = False
         if not graph or self.inj is not None or self.cfg.world != 1:
             for i in range(n):
                 self.step(i)
