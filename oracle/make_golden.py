@@ -487,6 +487,9 @@ def main():
     make_run("lg", "cancer", "cancer", R=4, samples_per_chain=40, swap_interval=6, surrogate_interval=8,
              surrogate_prob=0.4, maxtemp=4.0, use_langevin=True, learn_rate=0.5, surrogate_topology=2,
              seed=33, n_train=64, n_test=32)
+    make_run("rv", "cancer", "cancer", R=4, samples_per_chain=44, swap_interval=5, surrogate_interval=7,
+             surrogate_prob=0.5, maxtemp=2.0, use_langevin=False, learn_rate=0.5, surrogate_topology=1,
+             seed=35, n_train=90, n_test=36)
     make_run("lg", "ions", "ions", R=3, samples_per_chain=24, swap_interval=100000, surrogate_interval=6,
              surrogate_prob=0.5, maxtemp=2.0, use_langevin=True, learn_rate=0.01, surrogate_topology=3,
              seed=34, n_train=48, n_test=24)

@@ -636,6 +636,10 @@ def run_pt(variant: str, traindata, testdata, topology, temperatures, w0, sample
             if spec.name in ("rw", "lg"):
                 # RW/LG ship surr_train_set INCLUDING its all-zero first row (RW:496,626; LG:543,822)
                 rows = [np.vstack([np.zeros((1, P + 1)), x]) for x in rows]
+            else:
+                # RV both vstacks and overwrites row count_real, then ships surr_train_set[1:count_real]
+                # (RV:560-567,683): the interval's FIRST true proposal of every chain is dropped
+                rows = [x[1:] for x in rows]
             batch = np.concatenate(rows, axis=0)
             surr_batches.append(batch)
             if batch.shape[0] > 0:

@@ -225,46 +225,74 @@ __global__ void __launch_bounds__(128) mh_accept_kernel(sapt_accept_args a) {
 // -------------------------------------------------------------------------------------------
 __global__ void advance_kernel(int32_t* counter, int delta) { *counter += delta; }
 
+// The sweep is a recurrence on ONE carried message: at pair k the carried message (what position k holds after
+// the earlier pairs) competes with the message chain k+1 posted; the loser of the comparison stays at k, the
+// other is carried on. Chains are staged through shared memory in chunks so any R fits; thread 0 walks a chunk,
+// the CTA loads / scatters around it.
+constexpr int kSweepChunk = 2048;
+
 __global__ void swap_sweep_kernel(int R, double* lik_post, const double* temperature, int32_t* row_of_slot, uint32_t flags,
-                                  uint32_t seed, int sweep_base, const int32_t* sweep_dev, const double* u_inject, uint8_t* swapped, int32_t* num_swap,
-                                  int32_t* src_slot, int row0, int R_local, int32_t* slot_of_row_local) {
-  extern __shared__ double sh[];
-  double* post = sh;                                   // [R] message likelihoods
-  double* uu = sh + R;                                 // [R-1]
-  int32_t* src = reinterpret_cast<int32_t*>(uu + R);   // [R]
-  int32_t* rows = src + R;                             // [R]
+                                  uint32_t seed, int sweep_base, const int32_t* sweep_dev, const double* u_inject,
+                                  uint8_t* swapped, int32_t* num_swap, int32_t* src_slot, int row0, int R_local,
+                                  int32_t* slot_of_row_local, int32_t* scratch_src /*[R]*/, double* scratch_post /*[R]*/) {
+  __shared__ double s_post[kSweepChunk];   // posted likelihood of chain k+1 (input) / of the message left at k (output)
+  __shared__ double s_u[kSweepChunk];
+  __shared__ int32_t s_src[kSweepChunk];   // output: which chain's message stays at position k
+  __shared__ uint8_t s_sw[kSweepChunk];
+  __shared__ double c_post;                // carried message
+  __shared__ int c_src, c_ns;
   const int sweep = sweep_base + (sweep_dev ? *sweep_dev : 0);
-  for (int k = threadIdx.x; k < R; k += blockDim.x) {
-    // RW:623 posts likelihood*adapttemp ; LG:805 posts the tempered value
-    post[k] = (flags & SAPT_F_POST_TEMPERED) ? lik_post[k] : lik_post[k] * temperature[k];
-    src[k] = k;
-    rows[k] = row_of_slot[k];
-    if (k < R - 1) uu[k] = u_inject ? u_inject[k] : (double)philox_uniform(seed, SAPT_STREAM_SWAP, sweep, 0u, (uint32_t)k);
+  auto posted = [&](int k) {  // RW:623 posts likelihood*adapttemp ; LG:805 posts the tempered value
+    return (flags & SAPT_F_POST_TEMPERED) ? lik_post[k] : lik_post[k] * temperature[k];
+  };
+  if (threadIdx.x == 0) { c_post = posted(0); c_src = 0; c_ns = 0; }
+  for (int k0 = 0; k0 < R - 1; k0 += kSweepChunk) {
+    const int n = min(kSweepChunk, R - 1 - k0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const int k = k0 + j;
+      s_post[j] = posted(k + 1);
+      s_u[j] = u_inject ? u_inject[k] : (double)philox_uniform(seed, SAPT_STREAM_SWAP, sweep, 0u, (uint32_t)k);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double cp = c_post; int cs = c_src; int ns = c_ns;
+      for (int j = 0; j < n; ++j) {
+        const double np_ = s_post[j];
+        const double d = fmin(709.0, np_ - cp);
+        double pr = 0.5 * exp(d);
+        if (d != d) pr = 1.0;  // min(1, nan) == 1 in Python
+        pr = fmin(1.0, pr);
+        const bool sw = s_u[j] < pr;
+        if (sw) { s_src[j] = k0 + j + 1; s_post[j] = np_; ++ns; }       // chain k+1's message drops to position k
+        else { s_src[j] = cs; s_post[j] = cp; cp = np_; cs = k0 + j + 1; } // carried message stays, k+1's is carried on
+        s_sw[j] = sw ? 1 : 0;
+      }
+      c_post = cp; c_src = cs; c_ns = ns;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const int k = k0 + j;
+      scratch_src[k] = s_src[j];
+      scratch_post[k] = s_post[j];
+      if (swapped) swapped[k] = s_sw[j];
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int ns = 0;
-    for (int k = 0; k < R - 1; ++k) {
-      const double d = fmin(709.0, post[k + 1] - post[k]);
-      double pr = 0.5 * exp(d);
-      if (d != d) pr = 1.0;  // min(1, nan) == 1 in Python
-      pr = fmin(1.0, pr);
-      const bool sw = uu[k] < pr;
-      if (sw) {
-        const double t = post[k]; post[k] = post[k + 1]; post[k + 1] = t;
-        const int s = src[k]; src[k] = src[k + 1]; src[k + 1] = s;
-        ++ns;
-      }
-      if (swapped) swapped[k] = sw ? 1 : 0;
-    }
-    if (num_swap) *num_swap += ns;
+    scratch_src[R - 1] = c_src; scratch_post[R - 1] = c_post;
+    if (num_swap) *num_swap += c_ns;
   }
   __syncthreads();
+  // new binding: chain k now holds the vector chain src[k] posted. row_of_slot is permuted through a copy.
+  int32_t* old_rows = scratch_src + R;  // [R]
+  for (int k = threadIdx.x; k < R; k += blockDim.x) old_rows[k] = row_of_slot[k];
+  __syncthreads();
   for (int k = threadIdx.x; k < R; k += blockDim.x) {
-    const int newrow = rows[src[k]];  // chain k now holds the vector chain src[k] posted
+    const int newrow = old_rows[scratch_src[k]];
     row_of_slot[k] = newrow;
-    if (src_slot) src_slot[k] = src[k];
-    if (flags & SAPT_F_TAKE_POST_LIK) lik_post[k] = post[k];  // LG:813-815
+    if (src_slot) src_slot[k] = scratch_src[k];
+    if (flags & SAPT_F_TAKE_POST_LIK) lik_post[k] = scratch_post[k];  // LG:813-815
     if (slot_of_row_local && newrow >= row0 && newrow < row0 + R_local) slot_of_row_local[newrow - row0] = k;
   }
 }
@@ -343,11 +371,20 @@ extern "C" int sapt_swap_sweep_dev(int R_global, double* lik_post, const double*
                                    int32_t* num_swap, int32_t* src_slot, int row0, int R_local, int32_t* slot_of_row_local,
                                    void* stream) {
   SAPT_REQUIRE(R_global >= 1 && lik_post && temperature && row_of_slot, "sapt_swap_sweep");
-  const size_t smem = (size_t)R_global * (2 * sizeof(double) + 2 * sizeof(int32_t));
-  if (smem > 200 * 1024) { set_error("sapt_swap_sweep: %d chains exceed the single-CTA sweep capacity", R_global); return SAPT_ERR_UNSUPPORTED; }
-  if (smem > 48 * 1024) SAPT_CUDA(cudaFuncSetAttribute(swap_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  swap_sweep_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(R_global, lik_post, temperature, row_of_slot, flags, seed, sweep, sweep_dev,
-                                                            u_inject, swapped, num_swap, src_slot, row0, R_local, slot_of_row_local);
+  // scratch: src[R] + old_rows[R] (int32) and post[R] (double), kept in a small per-process buffer
+  static int32_t* sc_i = nullptr; static double* sc_d = nullptr; static int sc_cap = 0;
+  if (R_global > sc_cap) {
+    SAPT_CUDA(cudaDeviceSynchronize());
+    if (sc_i) { SAPT_CUDA(cudaFree(sc_i)); SAPT_CUDA(cudaFree(sc_d)); }
+    const int cap = R_global + R_global / 4 + 64;
+    SAPT_CUDA(cudaMalloc(&sc_i, sizeof(int32_t) * 2 * cap));
+    SAPT_CUDA(cudaMalloc(&sc_d, sizeof(double) * cap));
+    sc_cap = cap;
+  }
+  // NOTE: old_rows lives at sc_i + R_global (the kernel derives it from scratch_src + R)
+  swap_sweep_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(R_global, lik_post, temperature, row_of_slot, flags, seed, sweep, sweep_dev,
+                                                         u_inject, swapped, num_swap, src_slot, row0, R_local, slot_of_row_local,
+                                                         sc_i, sc_d);
   SAPT_CHECK_LAUNCH();
   return SAPT_OK;
 }

@@ -397,6 +397,8 @@ class PTEngine:
             blk = np.concatenate([th_h[s, :n], tl_h[s, :n, None]], axis=1)
             if self.spec.ship_zero_row:
                 blk = np.vstack([np.zeros((1, self.P + 1)), blk])
+            elif self.spec.name == "rv":
+                blk = blk[1:]  # RV ships surr_train_set[1:count_real]: the interval's first true proposal is dropped (RV:683)
             rows.append(blk)
         self.train_count.zero_()
         return np.concatenate(rows, axis=0) if rows else np.zeros((0, self.P + 1))

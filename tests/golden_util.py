@@ -6,7 +6,7 @@ import numpy as np
 from oracle import sapt_oracle as so
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-RUNS = {"run_rw_cancer": "rw", "run_rw_nosurr": "rw", "run_lg_cancer": "lg", "run_lg_ions": "lg"}
+RUNS = {"run_rw_cancer": "rw", "run_rw_nosurr": "rw", "run_lg_cancer": "lg", "run_lg_ions": "lg", "run_rv_cancer": "rv"}
 
 
 def load(name):

@@ -91,8 +91,10 @@ def test_full_run_traces(name):
     gu.compare_traces(g, out, rtol=1e-12, atol=1e-11)
     n_sweeps = len(out["swap_decisions"])
     ref_log = g["swap_log"][: n_sweeps * (len(g["temperatures"]) - 1)]
-    assert np.array_equal(np.concatenate(out["swap_decisions"]).astype(int) if n_sweeps else np.zeros(0, int),
-                          ref_log if gu.RUNS[name] == "rw" else np.concatenate(out["swap_decisions"]).astype(int))
+    if n_sweeps and gu.RUNS[name] == "rw":   # LG's swap log is produced by the barrier harness, RV never swaps
+        assert np.array_equal(np.concatenate(out["swap_decisions"]).astype(int), ref_log)
+    if gu.RUNS[name] == "rv":
+        assert n_sweeps == 0 and int(g["num_swap"]) == 0
     for s, b in enumerate(out["surr_batches"]):
         np.testing.assert_allclose(b, g[f"trainer_batch_{s}"], rtol=1e-12, atol=1e-11)
     if float(g["surrogate_prob"]) > 0:
