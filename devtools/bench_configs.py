@@ -51,7 +51,7 @@ if "c5" in which:
         w = so.make_surrogate_weights(prob.P, 3, 7)
         cfg = EngineConfig(variant="rw", samples=40, swap_interval=4, surrogate_interval=4, surrogate_prob=0.5, use_surrogate=True,
                            surrogate_topology=3, seed=4, record_pos=False, train_cap=4)
-        eng = PTEngine(prob, assign_temperatures(R, 4.0), cfg, surrogate_trainer=lambda batch, sig: (w if sig == 1 else None))
+        eng = PTEngine(prob, assign_temperatures(R, 4.0), cfg, surrogate_trainer=lambda batch, sig: (w if sig == 1 else None)); eng.surr_batches = type("Drop", (list,), {"append": lambda self, x: None})()
         eng.initialize(np.random.RandomState(3).randn(prob.P) * 0.5)
         ms, eps = timed_steps(eng, 10, 8)
         out[f"C5 chess-shape 6-25-18, 16833+11223 rows, {R} chains, surrogate_prob 0.5 (fixed MLP P-200-50-1)"] = dict(

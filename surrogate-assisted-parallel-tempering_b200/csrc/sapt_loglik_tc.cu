@@ -22,7 +22,7 @@ namespace sapt {
 constexpr int kTileM = 128;
 constexpr int kKA = 64;  // bf16 per A / B1 row
 
-bool tc_topology_supported(int D, int H, int O) { return D <= 16 && H <= 32 && O <= 16; }
+bool tc_topology_supported(int D, int H, int O) { return D <= 16 && H <= 32 && O <= (H <= 16 ? 16 : 32) && O <= 20; }
 
 // ---- per-step operand packing -----------------------------------------------------------------
 // ---- host side ----------------------------------------------------------------------------------

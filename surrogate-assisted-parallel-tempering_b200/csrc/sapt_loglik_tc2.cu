@@ -128,8 +128,13 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   constexpr int CH = 256 / HP;              // chains per CTA
   constexpr int UPT = CH / kUC;             // units (MMA-1 issues) per row tile
   constexpr int N1 = kUC * HP;              // MMA-1 N
-  constexpr int N2 = 3 * ON;                // MMA-2 N against h1: [w1 | w2 | w3] side by side
-  constexpr uint32_t kW2ChainBytes = N2 * 128;           // per chain: 3 ON rows of 128 bytes
+  // MMA-2 output width per chain. ON = 16: three partial sums side by side (h.[w1|w2|w3]). ON = 32: two
+  // ([w1|w2]); the w3 term is a separate N = ON MMA accumulating onto the first block (TMEM budget).
+  constexpr int N2 = (ON == 16) ? 3 * ON : 2 * ON;
+  constexpr int kParts = N2 / ON;
+  constexpr int kW2Rows = 3 * ON;                        // W2 image rows per chain: pieces w1, w2, w3
+  constexpr int kW2Box = (ON == 16) ? 4 : 2;             // chains per TMA box (box rows <= 256)
+  constexpr uint32_t kW2ChainBytes = kW2Rows * 128;
   constexpr uint32_t kW2Bytes = CH * kW2ChainBytes;
   // TMEM columns: [D1 | HV (A operand of MMA-2) | D2 buffers]. D2 of a chain is 3 ON wide: the three partial
   // sums h.w1, h.w2, h.w3 land side by side (each A piece is read from TMEM once — an MMA with A in TMEM costs
@@ -197,8 +202,8 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
       mbar_expect_tx(b_full, kB1Bytes + kW2Bytes);
       tma_load_2d(&map_b1, b_full, sB1, 0, blockIdx.y * 256);
 #pragma unroll
-      for (int q = 0; q < CH / 4; ++q)  // boxes of 4 chains x 3 ON rows
-        tma_load_2d(&map_w2, b_full, sW2 + q * 4 * kW2ChainBytes, 0, (blockIdx.y * CH + q * 4) * N2);
+      for (int q = 0; q < CH / kW2Box; ++q)  // boxes of kW2Box chains x 3 ON rows
+        tma_load_2d(&map_w2, b_full, sW2 + q * kW2Box * kW2ChainBytes, 0, (blockIdx.y * CH + q * kW2Box) * kW2Rows);
       for (int it = 0; it < n_my_tiles; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -213,6 +218,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
       const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t idesc2a = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t idesc2b = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * ON) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t idesc2c = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ON >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t b1_addr = smem_u32(sB1);
       const uint32_t w2_addr = smem_u32(sW2);
       mbar_wait(b_full, 0);
@@ -248,10 +254,16 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
           const uint32_t d2 = tmem_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (kUC * N2) + c * N2);
           const uint32_t hv = tmem_hv + (uint32_t)(c * HP);
           const uint32_t wb = w2_addr + (uint32_t)(uu * kUC + c) * kW2ChainBytes;
-          // D2[:, 0:3ON] = h1 . [w1|w2|w3]  then  D2[:, 0:2ON] += h2 . [w1|w2]   (h piece = HP/2 TMEM columns)
+          // ON=16: D2[:, 0:3ON] = h1.[w1|w2|w3], D2[:, 0:2ON] += h2.[w1|w2]
+          // ON=32: D2[:, 0:2ON] = h1.[w1|w2],    D2[:, 0:ON] += h1.w3,  D2[:, 0:2ON] += h2.[w1|w2]   (h piece = HP/2 columns)
 #pragma unroll
           for (int half = 0; half < HP / 16; ++half)
             tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), umma_desc_sw128(wb + half * 32), idesc2a, half ? 1u : 0u);
+          if constexpr (ON == 32) {
+#pragma unroll
+            for (int half = 0; half < HP / 16; ++half)
+              tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), umma_desc_sw128(wb + 2 * ON * 128 + half * 32), idesc2c, 1u);
+          }
 #pragma unroll
           for (int half = 0; half < HP / 16; ++half)
             tc_mma_bf16_ts(d2, hv + (uint32_t)(HP / 2 + half * 8), umma_desc_sw128(wb + half * 32), idesc2b, 1u);
@@ -344,7 +356,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
           if constexpr (kHvBufs == 2) publish_hv(u + 1);
         }
         // ---- D2 of unit u: wait for MMA-2 (with one HV buffer this also frees it), pull it into registers ----
-        uint32_t dr[kCPW][N2];
+        uint32_t dr0[kCPW][ON], dr1[kCPW][ON], dr2[kCPW][ON];  // the partial sums of D2 (dr2 unused when kParts == 2)
 #pragma unroll
         for (int cc = 0; cc < kCPW; ++cc) {
           const int c = kCPW * e + cc;
@@ -354,11 +366,8 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
 #pragma unroll
         for (int cc = 0; cc < kCPW; ++cc) {
           const uint32_t taddr = tmem_base + lane_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (kUC * N2) + (kCPW * e + cc) * N2);
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            uint32_t (&blk)[ON] = *reinterpret_cast<uint32_t(*)[ON]>(&dr[cc][q * ON]);
-            if constexpr (ON == 32) tmem_ld32(taddr + q * ON, blk); else tmem_ld16(taddr + q * ON, blk);
-          }
+          if constexpr (ON == 32) { tmem_ld32(taddr, dr0[cc]); tmem_ld32(taddr + ON, dr1[cc]); }
+          else { tmem_ld16(taddr, dr0[cc]); tmem_ld16(taddr + ON, dr1[cc]); tmem_ld16(taddr + 2 * ON, dr2[cc]); }
         }
         tmem_ld_wait();
         if constexpr (kHvBufs == 1) { if (has_next) publish_hv(u + 1); }
@@ -369,7 +378,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
           const float* bias = sBias + (uu * kUC + c) * ON;
           float tmin = 0.f; int pm = 0; float sum = 0.f, oy = 0.f;
 #if defined(SAPT_EXP_SKIP_P2)
-          sum = 2.0f; oy = __uint_as_float(dr[cc][0]) + __uint_as_float(dr[cc][N2 - 1]) + bias[y & 3];
+          sum = 2.0f; oy = __uint_as_float(dr0[cc][0]) + __uint_as_float(dr1[cc][ON - 1]) + bias[y & 3];
 #else
 #pragma unroll
           for (int g = 0; g < ON / 4; ++g) {
@@ -377,9 +386,14 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
               const float4 b = *reinterpret_cast<const float4*>(bias + 4 * g);
               float t[4];
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                t[k] = (__uint_as_float(dr[cc][4 * g + k]) + __uint_as_float(dr[cc][ON + 4 * g + k])) +
-                       (__uint_as_float(dr[cc][2 * ON + 4 * g + k]) + (k == 0 ? b.x : k == 1 ? b.y : k == 2 ? b.z : b.w));
+              for (int k = 0; k < 4; ++k) {
+                const float bk = (k == 0 ? b.x : k == 1 ? b.y : k == 2 ? b.z : b.w);
+                if constexpr (kParts == 3)
+                  t[k] = (__uint_as_float(dr0[cc][4 * g + k]) + __uint_as_float(dr1[cc][4 * g + k])) +
+                         (__uint_as_float(dr2[cc][4 * g + k]) + bk);
+                else
+                  t[k] = (__uint_as_float(dr0[cc][4 * g + k]) + __uint_as_float(dr1[cc][4 * g + k])) + bk;
+              }
               float s[4];
               sigmoid4(t[0], t[1], t[2], t[3], s[0], s[1], s[2], s[3]);
 #pragma unroll
@@ -454,8 +468,8 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   const DataSet& ds = p->set[which];
   if (R <= 0 || ds.n <= 0) return SAPT_OK;
   const int HP = p->H <= 16 ? 16 : 32;
-  const int ON = 16;
-  if (p->O > ON) { set_error("tcgen05 path: O=%d > 16", p->O); return SAPT_ERR_UNSUPPORTED; }
+  const int ON = (p->O <= 16) ? 16 : 32;
+  if (ON > HP) { set_error("tcgen05 path: O=%d needs H > 16", p->O); return SAPT_ERR_UNSUPPORTED; }
   const int CH = 256 / HP;
   const int n_groups = (R + CH - 1) / CH;
   const int64_t n_tiles = ds.n_pad / v2::kTileM;
@@ -486,7 +500,7 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   CUtensorMap mb1, mw2;
   rc = tc_make_map_2d(&mb1, b1img, v2::kKA, (uint64_t)n_groups * 256, 256);
   if (rc) return rc;
-  rc = tc_make_map_2d(&mw2, w2img, 64, (uint64_t)n_groups * CH * 3 * ON, (uint32_t)(4 * 3 * ON));
+  rc = tc_make_map_2d(&mw2, w2img, 64, (uint64_t)n_groups * CH * 3 * ON, (uint32_t)((ON == 16 ? 4 : 2) * 3 * ON));
   if (rc) return rc;
   Tc2Params a{};
   a.y = ds.y; a.n_pad = ds.n_pad; a.bias2 = bias2; a.n_rows = n_rows; a.R = R; a.O = p->O;
@@ -494,7 +508,8 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   dim3 grid((unsigned)n_chunks, (unsigned)n_groups);
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(ds.tmap);
   if (HP == 16) rc = launch_tc2<16, 16, 4>(ma, mb1, mw2, a, grid, st);
-  else rc = launch_tc2<32, 16, 4>(ma, mb1, mw2, a, grid, st);
+  else if (ON == 16) rc = launch_tc2<32, 16, 4>(ma, mb1, mw2, a, grid, st);
+  else rc = launch_tc2<32, 32, 3>(ma, mb1, mw2, a, grid, st);
   if (rc) return rc;
   return launch_loglik_finalize(partL, partNc, partSq, (int)n_chunks, R, rows, n_rows, L, nc, sq, st);
 }

@@ -158,7 +158,7 @@ class PTEngine:
             self.train_theta = torch.zeros((self.Rg, self.train_cap, self.P), dtype=torch.float32, device=dev)
             self.train_L = torch.zeros((self.Rg, self.train_cap), **f64)
             self.train_count = torch.zeros(self.Rg, **i32)
-        self.surr_batches: List[np.ndarray] = []
+        self.surr_batches: List[torch.Tensor] = []   # device tensors; keep_batches=False drops them after training
         # injected streams (parity tests): numpy arrays indexed [step, chain(, P)]
         self.inj = None
         if inject is not None:
@@ -378,8 +378,9 @@ class PTEngine:
         self.sweep_count += 1
         self.total_swap_proposals += self.Rg - 1
 
-    def gather_training_rows(self):
-        """(theta', L_untempered) rows of the interval's true steps, chain by chain (RW:1105-1116)."""
+    def gather_training_rows(self) -> torch.Tensor:
+        """(theta', L_untempered) rows of the interval's true steps, chain by chain (RW:1105-1116), as ONE device
+        tensor [n, P+1] (fp64): the training set never visits the host (the reference pickles it through queues)."""
         cnt = self.train_count
         th, tl = self.train_theta, self.train_L
         if self.cfg.world > 1:
@@ -389,19 +390,18 @@ class PTEngine:
             th = th * mask[:, None, None].float(); tl = tl * mask[:, None]
             dist.all_reduce(cnt, group=self.pg); dist.all_reduce(th, group=self.pg); dist.all_reduce(tl, group=self.pg)
             cnt = cnt.round().to(torch.int32)
-        cnt_h = cnt.cpu().numpy()
-        th_h = th.cpu().numpy().astype(np.float64); tl_h = tl.cpu().numpy()
-        rows = []
-        for s in range(self.Rg):
-            n = int(cnt_h[s])
-            blk = np.concatenate([th_h[s, :n], tl_h[s, :n, None]], axis=1)
-            if self.spec.ship_zero_row:
-                blk = np.vstack([np.zeros((1, self.P + 1)), blk])
-            elif self.spec.name == "rv":
-                blk = blk[1:]  # RV ships surr_train_set[1:count_real]: the interval's first true proposal is dropped (RV:683)
-            rows.append(blk)
+        cap = self.train_cap
+        j = torch.arange(cap, device=self.dev)[None, :]
+        valid = j < cnt.long()[:, None]                       # [Rg, cap]
+        if self.spec.name == "rv":
+            valid = valid & (j >= 1)                           # RV ships surr_train_set[1:count_real] (RV:683)
+        rows = torch.cat([th.double(), tl[:, :, None]], dim=2)  # [Rg, cap, P+1]
+        if self.spec.ship_zero_row:                            # RW:496,626 / LG:543,822: all-zero first row per chain
+            rows = torch.cat([torch.zeros((self.Rg, 1, self.P + 1), dtype=torch.float64, device=self.dev), rows], dim=1)
+            valid = torch.cat([torch.ones((self.Rg, 1), dtype=torch.bool, device=self.dev), valid], dim=1)
+        batch = rows[valid]                                    # chain-major, step order within a chain
         self.train_count.zero_()
-        return np.concatenate(rows, axis=0) if rows else np.zeros((0, self.P + 1))
+        return batch
 
     def surrogate_rendezvous(self, i: int):
         batch = self.gather_training_rows()
@@ -410,9 +410,8 @@ class PTEngine:
             return
         sur = self.surrogate
         sur.signature += 1
-        Y = batch[:, self.P]
         if sur.signature == 1:  # minmax.txt is written once and read once (RV:996-997, RV:707-710)
-            sur.min_y = float(np.min(Y) * 2)
+            sur.min_y = float(torch.min(batch[:, self.P]).item() * 2)
             sur.max_y = -1.0
         if self.inj is not None and self.inj_weights is not None:
             sur.set_weights(self.inj_weights[sur.signature - 1])
@@ -524,7 +523,7 @@ class PTEngine:
         out["swap_decisions"] = [s.cpu().numpy().astype(bool) for s in self.swap_log]
         out["num_swap"] = int(self.counters[3].item())
         out["total_swap_proposals"] = self.total_swap_proposals
-        out["surr_batches"] = self.surr_batches
+        out["surr_batches"] = [b.cpu().numpy() for b in self.surr_batches]
         out["min_y"] = self.surrogate.min_y; out["max_y"] = self.surrogate.max_y; out["signature"] = self.surrogate.signature
         out["row_of_slot"] = self.row_of_slot.cpu().numpy()
         out["likelihood"] = self.lik_post.cpu().numpy(); out["likelihood_copy"] = self.lik_cur.cpu().numpy()

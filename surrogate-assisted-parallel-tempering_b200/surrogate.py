@@ -40,11 +40,12 @@ class SurrogateTrainer:
         return torch.sigmoid(a @ p["W3"] + p["b3"]).squeeze(-1)
 
     def __call__(self, batch: np.ndarray, signature: int):
-        """batch = [n, P+1] rows (theta', L_untempered) of one interval. Returns numpy weights."""
-        X = torch.as_tensor(batch[:, : self.P], dtype=torch.float32, device=self.device)
-        Y = batch[:, self.P].astype(np.float64)
-        min_y, max_y = 2.0 * float(np.min(Y)), -1.0                 # _revamp.py:989-993 (every call)
-        Yn = torch.as_tensor((Y - min_y) / (max_y - min_y), dtype=torch.float32, device=self.device)  # _revamp.py:1024
+        """batch = [n, P+1] rows (theta', L_untempered) of one interval (device tensor or numpy). Returns numpy weights."""
+        batch = torch.as_tensor(batch, device=self.device)
+        X = batch[:, : self.P].to(torch.float32)
+        Y = batch[:, self.P].to(torch.float64)
+        min_y, max_y = 2.0 * float(Y.min().item()), -1.0            # _revamp.py:989-993 (every call)
+        Yn = ((Y - min_y) / (max_y - min_y)).to(torch.float32)       # _revamp.py:1024
         if signature == 1 or self.params is None:                   # fresh model, else warm start (_revamp.py:247-255)
             self.params = self._init_params()
         params = self.params
