@@ -147,6 +147,188 @@ __global__ void __launch_bounds__(kBT) langevin_batch_kernel(const float* x, con
   for (int i = tid; i < P; i += kBT) dst[i] = g[i];
 }
 
+// ---- batch mode, register-tiled version (HP <= 64): the production path for large N ---------------------------
+// Phase A (thread = row, features in registers, weights via broadcast LDS.128): forward pass, output deltas,
+// hidden deltas; the tile (x, hid, hd, od) is parked in shared memory. Phase B: the outer products
+// X^T.hd (D x H), hid^T.od (H x O) and the bias sums are accumulated over the 128 rows by threads that own fixed
+// 4x4 blocks of the gradient in REGISTERS for the whole row chunk (2 FMA-instructions per shared-memory wavefront).
+template <int DP, int OP, int NB>
+__global__ void __launch_bounds__(kBT) langevin_batch_tiled_kernel(const float* x, const int32_t* y, int64_t n, int D, int H, int O, int HP,
+                                                                   const float* theta, int64_t ld, const int32_t* rows,
+                                                                   const int32_t* n_rows, int R, int tiles_per_chunk, float* part) {
+  const int nact = n_rows ? *n_rows : R;
+  if ((int)blockIdx.y >= nact) return;
+  const int row = rows ? rows[blockIdx.y] : (int)blockIdx.y;
+  extern __shared__ __align__(16) float smf[];
+  const int P = D * H + H * O + H + O;
+  const int HP4 = HP >> 2;
+  float* sW1 = smf;                    // [DP][HP]
+  float* sW2 = sW1 + DP * HP;          // [HP][OP]
+  float* sB1 = sW2 + HP * OP;          // [HP]
+  float* sB2 = sB1 + HP;               // [OP]
+  float* xt = sB2 + OP;                // [kBT][DP]
+  float* ht = xt + kBT * DP;           // [kBT][HP]
+  float* hd = ht + kBT * HP;           // [kBT][HP]
+  float* od = hd + kBT * HP;           // [kBT][OP]
+  const int tid = threadIdx.x;
+  const float* src = theta + (int64_t)row * ld;
+  for (int i = tid; i < DP * HP; i += kBT) { const int d = i / HP, h = i - d * HP; sW1[i] = (d < D && h < H) ? src[d * H + h] : 0.f; }
+  for (int i = tid; i < HP * OP; i += kBT) { const int h = i / OP, o = i - h * OP; sW2[i] = (h < H && o < O) ? src[D * H + h * O + o] : 0.f; }
+  for (int i = tid; i < HP; i += kBT) sB1[i] = (i < H) ? src[D * H + H * O + i] : 0.f;
+  for (int i = tid; i < OP; i += kBT) sB2[i] = (i < O) ? src[D * H + H * O + H + i] : 0.f;
+  float acc1[NB][16];
+  float acc2[16];
+#pragma unroll
+  for (int b = 0; b < NB; ++b)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc1[b][i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc2[i] = 0.f;
+  float accb = 0.f;
+  const int nblk1 = (DP / 4) * HP4, nblk2 = HP4 * (OP / 4);
+  __syncthreads();
+  const int64_t n_tiles = (n + kBT - 1) / kBT;
+  const int64_t t0 = (int64_t)blockIdx.x * tiles_per_chunk, t1 = min(t0 + tiles_per_chunk, n_tiles);
+  for (int64_t t = t0; t < t1; ++t) {
+    // ---------------- phase A ----------------
+    const int64_t r = t * kBT + tid;
+    const bool valid = r < n;
+    float xr[DP];
+    {
+      const float4* xp = reinterpret_cast<const float4*>(x + (valid ? r : 0) * DP);
+#pragma unroll
+      for (int d4 = 0; d4 < DP / 4; ++d4) {
+        float4 v = valid ? __ldg(xp + d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xr[4 * d4] = v.x; xr[4 * d4 + 1] = v.y; xr[4 * d4 + 2] = v.z; xr[4 * d4 + 3] = v.w;
+        *reinterpret_cast<float4*>(xt + tid * DP + 4 * d4) = v;
+      }
+    }
+    const int label = valid ? y[r] : -1;
+    float out[OP];
+#pragma unroll
+    for (int o = 0; o < OP; ++o) out[o] = -sB2[o];
+    for (int h4 = 0; h4 < HP; h4 += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(sB1 + h4);
+      float z0 = -b.x, z1 = -b.y, z2 = -b.z, z3 = -b.w;
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const float4 w = *reinterpret_cast<const float4*>(sW1 + d * HP + h4);
+        z0 = fmaf(xr[d], w.x, z0); z1 = fmaf(xr[d], w.y, z1); z2 = fmaf(xr[d], w.z, z2); z3 = fmaf(xr[d], w.w, z3);
+      }
+      float hv[4] = {1.f / (1.f + __expf(-z0)), 1.f / (1.f + __expf(-z1)), 1.f / (1.f + __expf(-z2)), 1.f / (1.f + __expf(-z3))};
+      *reinterpret_cast<float4*>(ht + tid * HP + h4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o4 = 0; o4 < OP; o4 += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(sW2 + (h4 + j) * OP + o4);
+          out[o4] = fmaf(hv[j], w.x, out[o4]); out[o4 + 1] = fmaf(hv[j], w.y, out[o4 + 1]);
+          out[o4 + 2] = fmaf(hv[j], w.z, out[o4 + 2]); out[o4 + 3] = fmaf(hv[j], w.w, out[o4 + 3]);
+        }
+    }
+    float odl[OP];
+#pragma unroll
+    for (int o = 0; o < OP; ++o) {
+      const float s = 1.f / (1.f + __expf(-out[o]));
+      const float desired = (o == label) ? 1.f : 0.f;
+      odl[o] = (valid && o < O) ? (desired - s) * (s * (1.f - s)) : 0.f;   // LG:100
+    }
+#pragma unroll
+    for (int o4 = 0; o4 < OP; o4 += 4) *reinterpret_cast<float4*>(od + tid * OP + o4) = make_float4(odl[o4], odl[o4 + 1], odl[o4 + 2], odl[o4 + 3]);
+    for (int h4 = 0; h4 < HP; h4 += 4) {
+      const float4 hvv = *reinterpret_cast<const float4*>(ht + tid * HP + h4);
+      const float hv[4] = {hvv.x, hvv.y, hvv.z, hvv.w};
+      float dl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int o4 = 0; o4 < OP; o4 += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(sW2 + (h4 + j) * OP + o4);
+          sacc = fmaf(odl[o4], w.x, sacc); sacc = fmaf(odl[o4 + 1], w.y, sacc); sacc = fmaf(odl[o4 + 2], w.z, sacc); sacc = fmaf(odl[o4 + 3], w.w, sacc);
+        }
+        dl[j] = sacc * (hv[j] * (1.f - hv[j]));                               // LG:101
+      }
+      *reinterpret_cast<float4*>(hd + tid * HP + h4) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+    }
+    __syncthreads();
+    // ---------------- phase B ----------------
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int blk = tid + b * kBT;
+      if (blk < nblk1) {
+        const int db = blk / HP4, hb = blk - db * HP4;
+        const float* xp = xt + db * 4;
+        const float* hp = hd + hb * 4;
+#pragma unroll 4
+        for (int rr = 0; rr < kBT; ++rr) {
+          const float4 xv = *reinterpret_cast<const float4*>(xp + rr * DP);
+          const float4 hv = *reinterpret_cast<const float4*>(hp + rr * HP);
+          const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+          const float ha[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc1[b][4 * i + j] = fmaf(xa[i], ha[j], acc1[b][4 * i + j]);
+        }
+      }
+    }
+    if (tid < nblk2) {
+      const int hb = tid / (OP / 4), ob = tid - hb * (OP / 4);
+      const float* hp = ht + hb * 4;
+      const float* op = od + ob * 4;
+#pragma unroll 4
+      for (int rr = 0; rr < kBT; ++rr) {
+        const float4 hv = *reinterpret_cast<const float4*>(hp + rr * HP);
+        const float4 ov = *reinterpret_cast<const float4*>(op + rr * OP);
+        const float ha[4] = {hv.x, hv.y, hv.z, hv.w};
+        const float oa[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc2[4 * i + j] = fmaf(ha[i], oa[j], acc2[4 * i + j]);
+      }
+    } else if (tid >= kBT - HP - OP) {   // the last HP + OP threads own the bias sums (requires nblk2 + HP + OP <= kBT)
+      const int q = tid - (kBT - HP - OP);
+      const float* colp = (q < HP) ? (hd + q) : (od + (q - HP));
+      const int stride = (q < HP) ? HP : OP;
+      float sacc = 0.f;
+      for (int rr = 0; rr < kBT; ++rr) sacc += colp[rr * stride];
+      accb -= sacc;                                                            // LG:103,106: biases move by -lr*delta
+    }
+    __syncthreads();
+  }
+  float* dst = part + ((int64_t)blockIdx.x * R + blockIdx.y) * P;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int blk = tid + b * kBT;
+    if (blk < nblk1) {
+      const int db = blk / HP4, hb = blk - db * HP4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int d = db * 4 + i, h = hb * 4 + j;
+          if (d < D && h < H) dst[d * H + h] = acc1[b][4 * i + j];
+        }
+    }
+  }
+  if (tid < nblk2) {
+    const int hb = tid / (OP / 4), ob = tid - hb * (OP / 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int h = hb * 4 + i, o = ob * 4 + j;
+        if (h < H && o < O) dst[D * H + h * O + o] = acc2[4 * i + j];
+      }
+  } else if (tid >= kBT - HP - OP) {
+    const int q = tid - (kBT - HP - OP);
+    if (q < HP) { if (q < H) dst[D * H + H * O + q] = accb; }
+    else if (q - HP < O) dst[D * H + H * O + H + (q - HP)] = accb;
+  }
+}
+
 __global__ void langevin_batch_finalize(const float* part, int n_chunks, int R, int P, const float* theta, float* theta_gd, int64_t ld,
                                         const int32_t* rows, const int32_t* n_rows, double lr_scale) {
   const int nact = n_rows ? *n_rows : R;
@@ -179,18 +361,50 @@ extern "C" int sapt_langevin(sapt_problem_t* p, const float* theta, float* theta
   }
   if (mode == 1) {
     const int P = p->P;
-    const size_t smem = (size_t)(2 * P + kBT * ((p->D | 1) + 2 * (p->H | 1) + (p->O | 1))) * sizeof(float);
-    if (smem > 220 * 1024) { set_error("sapt_langevin: topology too large for the batch kernel"); return SAPT_ERR_UNSUPPORTED; }
     const int64_t n_tiles = (ds.n + kBT - 1) / kBT;
     int64_t n_chunks = std::min<int64_t>(n_tiles, std::max<int64_t>(1, ((int64_t)p->num_sms * 4 + R - 1) / R));
     const int tiles_per_chunk = (int)((n_tiles + n_chunks - 1) / n_chunks);
     n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
     int rc = ensure_workspace(p, (size_t)n_chunks * R * P * sizeof(float));
     if (rc) return rc;
-    if (smem > 48 * 1024) SAPT_CUDA(cudaFuncSetAttribute(langevin_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    langevin_batch_kernel<<<dim3((unsigned)n_chunks, (unsigned)R), kBT, smem, st>>>(ds.x, ds.y, ds.n, p->DP, p->D, p->H, p->O, theta, ld, rows,
-                                                                                      n_rows, R, tiles_per_chunk, (float*)p->ws);
-    SAPT_CHECK_LAUNCH();
+    const dim3 grid((unsigned)n_chunks, (unsigned)R);
+    const int HP = p->HP, OP = p->OP, DP = p->DP;
+    const bool tiled = HP <= 64 && (HP / 4) * (OP / 4) + HP + OP <= kBT;
+    if (tiled) {
+      const size_t smem = (size_t)(DP * HP + HP * OP + HP + OP + kBT * (DP + 2 * HP + OP)) * sizeof(float);
+#define SAPT_LB(DPV, OPV, NBV)                                                                                            \
+  {                                                                                                                       \
+    auto k = langevin_batch_tiled_kernel<DPV, OPV, NBV>;                                                                  \
+    if (smem > 48 * 1024) SAPT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    k<<<grid, kBT, smem, st>>>(ds.x, ds.y, ds.n, p->D, p->H, p->O, HP, theta, ld, rows, n_rows, R, tiles_per_chunk, (float*)p->ws); \
+  }
+#define SAPT_LB_OP(DPV, NBV)                                                          \
+  switch (OP) {                                                                       \
+    case 4: SAPT_LB(DPV, 4, NBV) break;                                               \
+    case 8: SAPT_LB(DPV, 8, NBV) break;                                               \
+    case 12: SAPT_LB(DPV, 12, NBV) break;                                             \
+    case 16: SAPT_LB(DPV, 16, NBV) break;                                             \
+    case 20: SAPT_LB(DPV, 20, NBV) break;                                             \
+    default: set_error("sapt_langevin: O padded to %d unsupported", OP); return SAPT_ERR_UNSUPPORTED; \
+  }
+      switch (DP) {
+        case 8: SAPT_LB_OP(8, 1) break;
+        case 16: SAPT_LB_OP(16, 1) break;
+        case 32: SAPT_LB_OP(32, 1) break;
+        case 64: SAPT_LB_OP(64, 2) break;
+        default: set_error("sapt_langevin: D padded to %d unsupported", DP); return SAPT_ERR_UNSUPPORTED;
+      }
+#undef SAPT_LB_OP
+#undef SAPT_LB
+      SAPT_CHECK_LAUNCH();
+    } else {
+      const size_t smem = (size_t)(2 * P + kBT * ((p->D | 1) + 2 * (p->H | 1) + (p->O | 1))) * sizeof(float);
+      if (smem > 220 * 1024) { set_error("sapt_langevin: topology too large for the batch kernel"); return SAPT_ERR_UNSUPPORTED; }
+      if (smem > 48 * 1024) SAPT_CUDA(cudaFuncSetAttribute(langevin_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      langevin_batch_kernel<<<grid, kBT, smem, st>>>(ds.x, ds.y, ds.n, p->DP, p->D, p->H, p->O, theta, ld, rows, n_rows, R, tiles_per_chunk,
+                                                     (float*)p->ws);
+      SAPT_CHECK_LAUNCH();
+    }
     langevin_batch_finalize<<<dim3((P + 127) / 128, R), 128, 0, st>>>((const float*)p->ws, (int)n_chunks, R, P, theta, theta_gd, ld, rows, n_rows,
                                                                       lrate * batch_scale);
     SAPT_CHECK_LAUNCH();
