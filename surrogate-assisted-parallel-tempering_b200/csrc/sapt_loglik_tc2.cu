@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
       for (int it = 0; it < n_my_tiles; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_a[s], ph ^ 1);
+        mbar_wait<1000>(&empty_a[s], ph ^ 1);
         mbar_expect_tx(&full_a[s], kAStageBytes);
         tma_load_2d(&map_a, &full_a[s], sA + s * kAStageBytes, 0, (int)((t_begin + it) * kTileM));
       }

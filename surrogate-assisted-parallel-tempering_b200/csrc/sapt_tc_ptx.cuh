@@ -23,10 +23,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Bounded wait: a lost TMA/MMA completion must surface as a launch failure, never as a hung GPU.
 // try_wait carries a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
 // expires) instead of burning issue slots that the epilogue warps need.
+// kBackoffNs > 0: the role is not latency critical (TMA producer runs stages ahead); sleep between polls so the
+// failed polls do not take issue slots from the epilogue warps sharing the SM sub-partition.
+template <int kBackoffNs = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
   for (uint32_t spin = 0; ; ++spin) {
+    if (kBackoffNs > 0 && spin > 0) __nanosleep(kBackoffNs);
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
