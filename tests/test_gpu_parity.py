@@ -453,3 +453,29 @@ def test_c1_posterior_accuracy_envelope(lib):
     assert lik.shape == (8 * 2999, 2)
     assert acc_tr.mean() > 90.0 and acc_te.mean() > 94.0, (acc_tr.mean(), acc_te.mean())
     assert 20.0 < accept < 99.0 and 0.0 < swap_perc < 100.0
+
+
+def test_cli_reference_command_line(lib, tmp_path, monkeypatch):
+    """`problem samples surrogate_prob interval_ratio folder num_chains` end to end on Cancer files written in the
+    reference's format; checks the on-disk layout of _revamp.py:746-777 / 1383-1389 / 1705-1710."""
+    import os
+    from sapt_b200 import cli
+    g = gu.load("unit_cancer")
+    root = tmp_path / "DATA" / "Cancer"
+    root.mkdir(parents=True)
+    for fn, arr in (("ftrain.txt", g["train"]), ("ftest.txt", g["test"])):
+        np.savetxt(root / fn, np.hstack([arr, np.zeros((arr.shape[0], 1))]), delimiter=" ")   # trailing column dropped by [:, :-1]
+    monkeypatch.chdir(tmp_path)
+    out = str(tmp_path / "res_")
+    rc = cli.main(["5", "1600", "0.0", "0.1", out, "4", "--data-root", str(tmp_path / "DATA"), "--variant", "rw", "--seed", "2"])
+    assert rc == 0
+    path = out + "Cancer_0"
+    for f in ("result.txt", "pos_param.txt", "likelihood.txt", "acc_train.txt", "acc_test.txt"):
+        assert os.path.isfile(os.path.join(path, f)), f
+    row = np.loadtxt(os.path.join(path, "result.txt"))
+    assert row.shape == (19,) and row[0] == 5 and row[1] == 1600 and 50.0 < row[8] <= 100.0
+    chains = os.listdir(os.path.join(path, "posterior/pos_w"))
+    assert len(chains) == 4 and all(c.startswith("chain_") for c in chains)
+    pw = np.loadtxt(os.path.join(path, "posterior/pos_w", sorted(chains)[0]))
+    assert pw.shape == (400, 146) and np.all(pw[0] == 1.0)
+    assert os.path.isfile(tmp_path / "master_result_file.txt")

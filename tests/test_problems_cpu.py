@@ -1,0 +1,52 @@
+"""CPU tests of the host-side problem table / preprocessing / result-row helpers."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from oracle import ref_loader
+
+
+def test_problem_table_matches_reference_main():
+    from sapt_b200.problems import PROBLEMS
+    want = {1: (11, 50, 10, 2), 2: (11, 50, 10, 2), 3: (4, 8, 3, 1), 4: (34, 15, 2, 1), 5: (9, 8, 2, 1), 6: (20, 50, 2, 2),
+            7: (16, 30, 10, 2), 8: (6, 25, 18, 3)}   # _revamp.py:1425-1519
+    for k, (ip, h, o, st) in want.items():
+        s = PROBLEMS[k]
+        assert (s.ip, s.hidden, s.output, s.surrogate_topology) == (ip, h, o, st)
+
+
+def test_split_and_zscore():
+    from sapt_b200.problems import split_60_40, zscore_columns
+    rs = np.random.RandomState(0)
+    f = rs.randn(50, 3) * 5 + 2; c = rs.randint(0, 3, (50, 1)).astype(float)
+    tr, te = split_60_40(f, c, np.random.RandomState(1))
+    assert tr.shape == (30, 4) and te.shape == (20, 4)
+    allrows = np.vstack([tr, te])
+    np.testing.assert_allclose(allrows[:, :3].mean(0), 0, atol=1e-12)
+    np.testing.assert_allclose(allrows[:, :3].std(0), 1, atol=1e-12)
+    z = zscore_columns(f, 2)
+    np.testing.assert_allclose(z[:, 2], f[:, 2])
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="needs the reference DATA directory")
+def test_load_problem_reproduces_reference_arrays():
+    from sapt_b200.problems import load_problem
+    root = os.path.join(ref_loader.REFERENCE_ROOT, "DATA")
+    for prob, fixture, hidden in ((5, "unit_cancer", 12), (4, "unit_ions", 50)):
+        tr, te, topo, st, name = load_problem(prob, root, hidden=hidden)
+        g = gu.load(fixture)
+        assert topo == [int(v) for v in g["topology"]]
+        np.testing.assert_array_equal(tr, g["train"]); np.testing.assert_array_equal(te, g["test"])
+    tr, te, topo, st, name = load_problem(7, root)
+    g = gu.load("unit_pendigit")
+    np.testing.assert_array_equal(tr[:600], g["train"]); assert topo == [16, 30, 10] and st == 2
+
+
+def test_result_row_layout():
+    from sapt_b200.results import result_row
+    acc_tr = np.array([[90.0], [np.inf], [92.0]]); acc_te = np.array([[80.0], [82.0], [np.inf]])
+    row = result_row(5, 1000, 2, 5, 0.1, 0.5, False, 0.01, acc_tr, acc_te, 12.5, 70.0, 3.0, 1.5, 90)
+    assert row.shape == (19,)
+    assert row[0] == 5 and row[8] == 91.0 and row[10] == 92.0 and row[11] == 81.0 and row[14] == 12.5 and row[18] == 90
