@@ -467,7 +467,7 @@ def test_cli_reference_command_line(lib, tmp_path, monkeypatch):
         np.savetxt(root / fn, np.hstack([arr, np.zeros((arr.shape[0], 1))]), delimiter=" ")   # trailing column dropped by [:, :-1]
     monkeypatch.chdir(tmp_path)
     out = str(tmp_path / "res_")
-    rc = cli.main(["5", "1600", "0.0", "0.1", out, "4", "--data-root", str(tmp_path / "DATA"), "--variant", "rw", "--seed", "2"])
+    rc = cli.main(["5", "1600", "0.0", "0.1", out, "4", "--data-root", str(tmp_path / "DATA"), "--variant", "rw", "--seed", "2", "--hidden", "12"])
     assert rc == 0
     path = out + "Cancer_0"
     for f in ("result.txt", "pos_param.txt", "likelihood.txt", "acc_train.txt", "acc_test.txt"):
