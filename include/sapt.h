@@ -78,8 +78,8 @@ const char* sapt_last_error(void);
 long long sapt_launch_count(void);
 void sapt_launch_count_reset(void);
 /* sizeof() of sapt_propose_args, sapt_chain_state, sapt_history, sapt_accept_args,
- * sapt_lg_first_args — lets an FFI binding verify its struct mirrors at load time */
-int sapt_struct_sizes(int32_t out[5]);
+ * sapt_lg_first_args, sapt_fused_args — lets an FFI binding verify its struct mirrors at load time */
+int sapt_struct_sizes(int32_t out[6]);
 
 /* ---- data + topology: replaces Network.__init__(Topo, Train, Test, lr) RV:49-60 -------
  * train_host/test_host: row-major float64 [n][D+1], features then the class index as a
@@ -230,6 +230,22 @@ typedef struct {
   const int32_t* step_dev;  /* see sapt_propose_args.step_dev */
 } sapt_accept_args;
 int sapt_mh_accept(const sapt_accept_args* a, void* stream);
+
+/* ---- fused step for SMALL problems (random-walk forks): ONE launch runs n_steps complete MCMC steps of every chain
+ * — proposal (Philox) + prior, likelihood on train and test, optional surrogate MLP, MH accept and bookkeeping — i.e.
+ * n_steps iterations of the loop body RV:505-642 for R chains, with theta resident in shared memory. No exchange
+ * happens inside; call sapt_swap_sweep between calls. `acc` is the same struct sapt_mh_accept takes (its per-row
+ * input pointers, n_train/n_test and capture are ignored: the kernel computes them); acc.step (+ *acc.step_dev) is
+ * the first step index. */
+typedef struct {
+  float* theta; int64_t ld; int R, P;
+  double step_w, sigma_squared; uint32_t seed;
+  int use_surrogate, surrogate_ready; double surrogate_prob; int gate;
+  const float* W1; const float* b1; int h1; const float* W2; const float* b2; int h2; const float* W3; const float* b3;
+  sapt_accept_args acc;
+  int n_steps;
+} sapt_fused_args;
+int sapt_fused_steps(sapt_problem_t* p, const sapt_fused_args* a, void* stream);
 
 /* ---- LG only: after the FIRST true evaluation (LG:622-645): capture (proposal, L) into the
  * training set, remember L/T for surg[:,0/2], throw the Langevin coin lx2 < l_prob (LG:647-649)

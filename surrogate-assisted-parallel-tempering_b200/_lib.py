@@ -60,6 +60,13 @@ class LgFirstArgs(C.Structure):
                 ("train_cap", C.c_int), ("step_dev", vp)]
 
 
+class FusedArgs(C.Structure):
+    _fields_ = [("theta", vp), ("ld", i64), ("R", C.c_int), ("P", C.c_int), ("step_w", f64), ("sigma_squared", f64), ("seed", u32),
+                ("use_surrogate", C.c_int), ("surrogate_ready", C.c_int), ("surrogate_prob", f64), ("gate", C.c_int),
+                ("W1", vp), ("b1", vp), ("h1", C.c_int), ("W2", vp), ("b2", vp), ("h2", C.c_int), ("W3", vp), ("b3", vp),
+                ("acc", AcceptArgs), ("n_steps", C.c_int)]
+
+
 class SaptError(RuntimeError):
     pass
 
@@ -100,10 +107,11 @@ def lib():
     L.sapt_advance.argtypes = [vp, C.c_int, vp]
     L.sapt_philox_host.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     L.sapt_philox_fill.argtypes = [u32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.sapt_fused_steps.argtypes = [vp, C.POINTER(FusedArgs), vp]
     L.sapt_struct_sizes.argtypes = [C.POINTER(i32)]
-    sizes = (i32 * 5)()
+    sizes = (i32 * 6)()
     L.sapt_struct_sizes(sizes)
-    mine = [C.sizeof(t) for t in (ProposeArgs, ChainState, History, AcceptArgs, LgFirstArgs)]
+    mine = [C.sizeof(t) for t in (ProposeArgs, ChainState, History, AcceptArgs, LgFirstArgs, FusedArgs)]
     if list(sizes) != mine:
         raise ImportError(f"struct layout mismatch between include/sapt.h and _lib.py: C={list(sizes)} ctypes={mine}")
     if L.sapt_abi_version() != 1:
@@ -123,6 +131,6 @@ EXPORTS = [
     "sapt_abi_version", "sapt_last_error", "sapt_launch_count", "sapt_launch_count_reset", "sapt_struct_sizes",
     "sapt_problem_create", "sapt_problem_create_f32", "sapt_problem_destroy", "sapt_problem_num_param",
     "sapt_problem_rows", "sapt_problem_tc_supported", "sapt_loglik", "sapt_loglik_host", "sapt_evaluate_proposal",
-    "sapt_prior", "sapt_propose", "sapt_langevin", "sapt_surrogate_predict", "sapt_mh_accept", "sapt_lg_first_eval",
+    "sapt_prior", "sapt_propose", "sapt_fused_steps", "sapt_langevin", "sapt_surrogate_predict", "sapt_mh_accept", "sapt_lg_first_eval",
     "sapt_swap_sweep", "sapt_swap_sweep_dev", "sapt_advance", "sapt_philox_host", "sapt_philox_fill",
 ]

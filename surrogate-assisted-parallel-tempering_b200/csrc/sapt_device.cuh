@@ -97,6 +97,11 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // sigmoid of z given t = -z*log2(e):  1 / (1 + 2^t)   (2 MUFU + 1 FADD)
 __device__ __forceinline__ float sigmoid_from_neg_log2e(float t) { return rcp_approx(1.0f + ex2_approx(t)); }
 
+// prior: -(P/2) ln s2 - sum(w^2)/(2 s2)   (_revamp.py:404-410)
+__device__ __forceinline__ double prior_from_sumsq(double sumsq, int P, double s2) {
+  return -1.0 * ((double)P / 2.0) * log(s2) - (1.0 / (2.0 * s2)) * sumsq;
+}
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 

@@ -5,16 +5,13 @@
 
 #include "sapt_device.cuh"
 #include "sapt_internal.h"
+#include "sapt_mh.cuh"
 
 namespace sapt {
 
 // -------------------------------------------------------------------------------------------
 // prior: -(P/2) ln s2 - sum(w^2)/(2 s2)                                        RV:404-410
 // -------------------------------------------------------------------------------------------
-__device__ __forceinline__ double prior_from_sumsq(double sumsq, int P, double s2) {
-  return -1.0 * ((double)P / 2.0) * log(s2) - (1.0 / (2.0 * s2)) * sumsq;
-}
-
 __global__ void prior_kernel(const float* theta, int64_t ld, int P, double s2, double* prior) {
   __shared__ double scratch[32];
   const float* w = theta + (int64_t)blockIdx.x * ld;
@@ -123,87 +120,19 @@ __global__ void __launch_bounds__(128) mh_accept_kernel(sapt_accept_args a) {
   const int S = a.hist.n_slots;
   const int step_i = a.step + (a.step_dev ? *a.step_dev : 0);
   __shared__ int s_accept, s_cnt;
-  const double INF = __longlong_as_double(0x7ff0000000000000LL);
-  const double NANV = __longlong_as_double(0x7ff8000000000000LL);
   const int64_t hi = (int64_t)step_i * S + slot;        // history row i
   const int64_t ho = (int64_t)(step_i + 1) * S + slot;  // history row i+1
   if (threadIdx.x == 0) {
-    const double T = a.st.temperature[slot];
-    const bool sur = a.is_sur && a.is_sur[row];
-    double Lprop, s0, s1, s2;
-    double rmse_tr = a.st.last_rmse_train[slot], rmse_te = a.st.last_rmse_test[slot];
-    double acc_tr = a.st.last_acc_train[slot], acc_te = a.st.last_acc_test[slot];
-    double rm_tr_new = 0, rm_te_new = 0, ac_tr_new = 0, ac_te_new = 0;
-    int cnt = -1;
-    if (sur) {
-      // RV:319-320 / LG:325: float32 network output times float64 scalars
-      const double s = (double)a.sur_s[row];
-      double pred = (a.flags & SAPT_F_DENORM_HALF_MIN) ? (s * a.min_y / 2.0) : (s * (a.max_y - a.min_y) + a.min_y);
-      const double surl = pred * (1.0 / T);                                  // RV:540
-      const double* m = a.st.mov + (int64_t)slot * 3;
-      const double mov = (m[0] + m[1] + m[2]) / 3.0;                         // RV:541
-      Lprop = (surl * 0.5) + (mov * 0.5);                                    // RV:542
-      double ltrue = 0.0;
-      if (a.flags & SAPT_F_COMPARE_SURROGATE) {                              // RV:543-544
-        ltrue = a.L_train[row] / T;
-        a.st.likl_wo_temp[slot] = a.L_train[row];
-      }
-      s0 = ltrue; s1 = Lprop; s2 = mov;                                      // RV:549-551
-    } else {
-      const double L = a.L_train[row];
-      Lprop = L / T;
-      s0 = Lprop; s1 = NANV; s2 = Lprop;                                     // RV:555,564-565
-      if (a.surg_first) { s2 = a.surg_first[row]; }                          // LG:644-645 then LG:678-679
-      a.st.likl_wo_temp[slot] = L;
-      rm_tr_new = sqrt(a.sq_train[row] / (double)a.n_train);                 // RV:380-382
-      ac_tr_new = 100.0 * ((double)a.nc_train[row] / (double)a.n_train);     // RV:384-389
-      if (a.n_test > 0) {
-        rm_te_new = sqrt(a.sq_test[row] / (double)a.n_test);
-        ac_te_new = 100.0 * ((double)a.nc_test[row] / (double)a.n_test);
-      }
-      if (a.capture && a.train_count) {                                      // RW:540-545
-        cnt = a.train_count[slot];
-        if (cnt < a.train_cap) { a.train_L[(int64_t)slot * a.train_cap + cnt] = L; a.train_count[slot] = cnt + 1; }
-        else cnt = -1;
-      }
-    }
+    MhInputs in;
+    in.sur = a.is_sur && a.is_sur[row];
+    in.sur_s = a.sur_s ? a.sur_s[row] : 0.f;
+    in.L_train = a.L_train[row]; in.nc_train = a.nc_train[row]; in.sq_train = a.sq_train[row];
+    in.L_test = a.n_test > 0 ? a.L_test[row] : 0.0; in.nc_test = a.n_test > 0 ? a.nc_test[row] : 0; in.sq_test = a.n_test > 0 ? a.sq_test[row] : 0.0;
+    in.prior_prop = a.prior_prop[row];
+    in.has_surg_first = a.surg_first != nullptr; in.surg_first = a.surg_first ? a.surg_first[row] : 0.0;
+    int cnt;
+    s_accept = mh_decide(a, slot, step_i, in, &cnt) ? 1 : 0;
     s_cnt = cnt;
-    // moving-average window: newest first
-    double* m = a.st.mov + (int64_t)slot * 3;
-    m[2] = m[1]; m[1] = m[0]; m[0] = s2;
-    const double prior_prop = a.prior_prop[row];
-    const double diff = (Lprop - a.st.lik_cur[slot]) + (prior_prop - a.st.prior_cur[slot]);
-    // min(1, exp(diff)); OverflowError -> 1 (RV:571-577); Python's min(1, nan) is 1 as well
-    double mh;
-    if (diff != diff) mh = 1.0;
-    else if (diff >= 0.0) mh = 1.0;
-    else mh = exp(diff);
-    const double u = a.u_inject ? a.u_inject[slot] : (double)philox_uniform(a.seed, SAPT_STREAM_U, step_i, (uint32_t)slot, 0);
-    const int nacc = a.st.naccept[slot];
-    const bool acc = u < mh;
-    double h_lhood, h_rtr, h_rte, h_atr, h_ate;
-    if (acc) {
-      a.st.naccept[slot] = nacc + 1;
-      a.st.lik_cur[slot] = Lprop; a.st.lik_post[slot] = Lprop; a.st.prior_cur[slot] = prior_prop;
-      if (!sur) { h_lhood = Lprop * T; h_rtr = rm_tr_new; h_rte = rm_te_new; h_atr = ac_tr_new; h_ate = ac_te_new; }
-      else { h_lhood = h_rtr = h_rte = h_atr = h_ate = INF; }
-    } else {
-      if (!sur) { h_lhood = Lprop * T; h_rtr = rmse_tr; h_rte = rmse_te; h_atr = acc_tr; h_ate = acc_te; }
-      else { h_lhood = h_rtr = h_rte = h_atr = h_ate = INF; }
-    }
-    a.st.last_rmse_train[slot] = h_rtr; a.st.last_rmse_test[slot] = h_rte;
-    a.st.last_acc_train[slot] = h_atr; a.st.last_acc_test[slot] = h_ate;
-    if (a.hist.lhood_list) a.hist.lhood_list[ho] = h_lhood;
-    if (a.hist.rmse_train) a.hist.rmse_train[ho] = h_rtr;
-    if (a.hist.rmse_test) a.hist.rmse_test[ho] = h_rte;
-    if (a.hist.acc_train) a.hist.acc_train[ho] = h_atr;
-    if (a.hist.acc_test) a.hist.acc_test[ho] = h_ate;
-    if (a.hist.surg) { double* sg = a.hist.surg + ho * 3; sg[0] = s0; sg[1] = s1; sg[2] = s2; }
-    if (a.hist.likeh) a.hist.likeh[ho] = a.st.likl_wo_temp[slot];
-    if (a.hist.accept_list) a.hist.accept_list[ho] = (double)nacc;
-    if (a.hist.accepted) a.hist.accepted[ho] = acc ? 1 : 0;
-    if (a.hist.is_sur) a.hist.is_sur[ho] = sur ? 1 : 0;
-    s_accept = acc ? 1 : 0;
   }
   __syncthreads();
   const bool acc = s_accept != 0;

@@ -432,13 +432,63 @@ class PTEngine:
         if do_train:
             self.surrogate_rendezvous(i)
 
-    def run(self, steps: Optional[int] = None, graph: Optional[bool] = None):
+    # ------------------------------------------------------------------------------------
+    def fused_supported(self) -> bool:
+        """Small problems (the reference's own runnable cases) run n steps per launch in the fused kernel."""
+        return (not self.spec.lg_flow and self.inj is None and (self.p.n[0] + self.p.n[1]) <= 8192
+                and self.p.topology[0] <= 64 and self.p.topology[2] <= 20 and self.p.topology[1] <= 128)
+
+    def fused_steps(self, i0: int, n: int):
+        """Steps i0 .. i0+n-1 of every local chain in ONE launch (sapt_fused_steps)."""
+        cfg, sp = self.cfg, self.spec
+        f = _lib.FusedArgs()
+        f.theta = self.theta.data_ptr(); f.ld = self.ld; f.R = self.R; f.P = self.P
+        f.step_w = cfg.step_w; f.sigma_squared = cfg.sigma_squared; f.seed = cfg.seed & 0xFFFFFFFF
+        f.use_surrogate = 1 if cfg.use_surrogate else 0
+        f.surrogate_ready = 1 if self.surrogate.ready else 0
+        f.surrogate_prob = cfg.surrogate_prob
+        f.gate = cfg.swap_interval if sp.gate_on_swap_interval else cfg.surrogate_interval
+        f.h1 = self.surrogate.h1; f.h2 = self.surrogate.h2
+        if self.surrogate.ready:
+            w = self.surrogate.weights
+            f.W1 = w["W1"].data_ptr(); f.b1 = w["b1"].data_ptr(); f.W2 = w["W2"].data_ptr(); f.b2 = w["b2"].data_ptr()
+            f.W3 = w["W3"].data_ptr(); f.b3 = w["b3"].data_ptr()
+        m = f.acc
+        m.theta = self.theta.data_ptr(); m.proposal = self.prop.data_ptr(); m.ld = self.ld; m.R = self.R; m.P = self.P
+        m.st = self._chain_state(); m.hist = self._history(); m.step = i0; m.flags = self.flags
+        m.min_y = self.surrogate.min_y; m.max_y = self.surrogate.max_y; m.seed = cfg.seed & 0xFFFFFFFF
+        if self.train_theta is not None:
+            m.train_theta = self.train_theta.data_ptr(); m.train_L = self.train_L.data_ptr()
+            m.train_count = self.train_count.data_ptr(); m.train_cap = self.train_cap
+        f.n_steps = n
+        _lib.check(self.L.sapt_fused_steps(self.p.handle, C.byref(f), current_stream_ptr()), "sapt_fused_steps")
+        ntr, nte = self.p.n
+        self.evals += n * self.R * (ntr + nte)
+
+    def _run_fused(self, n):
+        pts = self._rendezvous_steps(n)
+        i = 0
+        while i < n:
+            j = i
+            while j not in pts and j < n - 1:
+                j += 1
+            self.fused_steps(i, j - i + 1)
+            self.rendezvous(j)
+            i = j + 1
+
+    def run(self, steps: Optional[int] = None, graph: Optional[bool] = None, fused: Optional[bool] = None):
         """Run the chain loop. `graph=True` captures the launches of one interval between rendezvous points in a
         CUDA graph and replays it (the step index is read from device memory), removing the per-launch host cost.
         Measured at C1 (8 chains x 699 rows) the eager loop is already GPU-latency bound (~67 us per step for ~10
         dependent small kernels) and capture + instantiation only pays off for runs of >~10^4 steps, so the
         default is off; the mode is kept for host-bound deployments (slow CPUs, many short kernels)."""
         n = self.cfg.samples - 1 if steps is None else steps
+        if fused is None:
+            fused = self.fused_supported()
+        if fused:
+            if not self.fused_supported():
+                raise NotImplementedError("fused step kernel: random-walk forks, Philox streams, <= 8192 rows only")
+            return self._run_fused(n)
         if graph is None:
             graph = False
         if not graph or self.inj is not None or self.cfg.world != 1:

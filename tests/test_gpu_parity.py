@@ -479,3 +479,40 @@ def test_cli_reference_command_line(lib, tmp_path, monkeypatch):
     pw = np.loadtxt(os.path.join(path, "posterior/pos_w", sorted(chains)[0]))
     assert pw.shape == (400, 146) and np.all(pw[0] == 1.0)
     assert os.path.isfile(tmp_path / "master_result_file.txt")
+
+
+@pytest.mark.parametrize("use_sur,variant", [(False, "rw"), (True, "rw"), (True, "rv")])
+def test_fused_small_problem_kernel_equals_multi_kernel_path(lib, use_sur, variant):
+    """sapt_fused_steps (n steps per launch, theta in shared memory) must give the same chains as the
+    launch-per-operation path: same Philox streams, same decisions, same posterior samples."""
+    from sapt_b200.engine import EngineConfig, PTEngine
+    from sapt_b200.ladder import assign_temperatures
+    from sapt_b200.problem import Problem
+    g = gu.load("unit_cancer")
+    topo = [int(v) for v in g["topology"]]
+    prob = Problem(topo, g["train"], g["test"], path=lib.PATH_F32)
+    sw = [so.make_surrogate_weights(prob.P, 1, 90 + s) for s in range(12)]
+
+    def run(fused):
+        cfg = EngineConfig(variant=variant, samples=70, swap_interval=9, surrogate_interval=11, surrogate_prob=0.5,
+                           use_surrogate=use_sur, seed=8, path=lib.PATH_F32)
+        eng = PTEngine(prob, assign_temperatures(6, 4.0), cfg, surrogate_trainer=lambda batch, sig: sw[sig - 1])
+        eng.initialize(g["W"][2])
+        eng.run(fused=fused); torch.cuda.synchronize()
+        return eng.results()
+
+    a, b = run(False), run(True)
+    for k in ("accepted", "is_surrogate_step", "accept_list", "naccept", "row_of_slot", "pos_w"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["num_swap"] == b["num_swap"]
+    for k in ("lhood_list", "surg_likeh_list", "likeh_list"):
+        x, y = a[k], b[k]
+        assert np.array_equal(np.isfinite(x), np.isfinite(y)), k
+        m = np.isfinite(x)
+        np.testing.assert_allclose(y[m], x[m], rtol=1e-9, atol=1e-9, err_msg=k)
+    for k in ("acc_train", "rmse_test"):
+        assert np.array_equal(np.nan_to_num(a[k], posinf=-2.0), np.nan_to_num(b[k], posinf=-2.0)), k
+    for x, y in zip(a["surr_batches"], b["surr_batches"]):
+        np.testing.assert_allclose(y, x, rtol=1e-9, atol=1e-9)
+    if use_sur:
+        assert a["is_surrogate_step"].sum() > 0
