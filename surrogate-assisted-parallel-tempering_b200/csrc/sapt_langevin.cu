@@ -74,6 +74,113 @@ __global__ void __launch_bounds__(256) langevin_sgd_kernel(const float* x, const
   for (int i = tid; i < P; i += nt) dst[i] = (float)sm[i];
 }
 
+// ---- sgd_exact, register-resident version (H <= 128): thread h owns column h of W1, row h of W2 and B1[h] in fp64
+// registers; every thread keeps its own (identical) copy of B2. One row costs D + O FMAs forward, one O-wide reduction
+// over the hidden units (warp shuffles + one shared-memory hop, ONE barrier per row) and D + O FMAs of update, instead
+// of four barriers and shared-memory weights. Same arithmetic as the reference epoch (LG:138-156, 96-106).
+template <int DP, int OP>
+__global__ void __launch_bounds__(128) langevin_sgd_reg_kernel(const float* x, int xstride, const int32_t* y, int64_t n, int D, int H, int O,
+                                                               const float* theta, float* theta_gd, int64_t ld, const int32_t* rows,
+                                                               const int32_t* n_rows, int R, double lr) {
+  const int nact = n_rows ? *n_rows : R;
+  if ((int)blockIdx.x >= nact) return;
+  const int row = rows ? rows[blockIdx.x] : (int)blockIdx.x;
+  __shared__ double xs[3][DP];
+  __shared__ int labs[3];
+  __shared__ double red[2][4][OP];
+  const int h = threadIdx.x, lane = h & 31, warp = h >> 5, nw = (blockDim.x + 31) >> 5;
+  const bool live = h < H;
+  const float* src = theta + (int64_t)row * ld;
+  double w1[DP], w2[OP], b2[OP], b1 = 0.0;
+#pragma unroll
+  for (int d = 0; d < DP; ++d) w1[d] = (live && d < D) ? (double)src[d * H + h] : 0.0;
+#pragma unroll
+  for (int o = 0; o < OP; ++o) {
+    w2[o] = (live && o < O) ? (double)src[D * H + h * O + o] : 0.0;
+    b2[o] = (o < O) ? (double)src[D * H + H * O + H + o] : 0.0;
+  }
+  if (live) b1 = (double)src[D * H + H * O + h];
+  for (int d = h; d < DP; d += blockDim.x) xs[0][d] = (d < D && n > 0) ? (double)x[d] : 0.0;
+  if (h == 0 && n > 0) labs[0] = y[0];
+  __syncthreads();
+  for (int64_t r = 0; r < n; ++r) {
+    const int cur = (int)(r % 3), nxt = (int)((r + 1) % 3), par = (int)(r & 1);
+    // issue the next row's loads now, park them in shared memory just before the barrier: the global-load
+    // latency overlaps the forward pass instead of stalling it
+    float xn[(DP + 31) / 32];
+    int labn = 0;
+    if (r + 1 < n) {
+#pragma unroll
+      for (int q = 0; q < (DP + 31) / 32; ++q) { const int d = h + 32 * q; xn[q] = (h < 32 && d < D) ? __ldg(x + (r + 1) * xstride + d) : 0.f; }
+      if (h == 0) labn = __ldg(y + r + 1);
+    }
+    double z4[4] = {0.0, 0.0, 0.0, 0.0};                                   // four partial sums: the FMA chain is latency bound
+#pragma unroll
+    for (int d = 0; d < DP; ++d) z4[d & 3] += xs[cur][d] * w1[d];          // LG:70 (padding columns are zero)
+    const double z = ((z4[0] + z4[1]) + (z4[2] + z4[3])) - b1;
+    const double hid = live ? 1.0 / (1.0 + exp(-z)) : 0.0;                 // LG:71
+#pragma unroll
+    for (int o = 0; o < OP; ++o) {
+      double pz = hid * w2[o];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) pz += __shfl_xor_sync(0xffffffffu, pz, s);
+      if (lane == 0) red[par][warp][o] = pz;
+    }
+    if (r + 1 < n && h < 32) {
+#pragma unroll
+      for (int q = 0; q < (DP + 31) / 32; ++q) { const int d = h + 32 * q; if (d < DP) xs[nxt][d] = (double)xn[q]; }
+      if (h == 0) labs[nxt] = labn;
+    }
+    __syncthreads();
+    const int label = labs[cur];
+    // each warp evaluates the O outputs once, lane o doing output o (the fp64 exp + divide chain is the latency of
+    // this loop; doing the O of them side by side instead of one after the other is what matters), then broadcasts
+    double my_od = 0.0;
+    double od[OP], back = 0.0;
+    {
+      // lane-parallel: lane o owns b2[o] through a select chain (b2 is replicated in registers)
+      double zsum = 0.0, bsel = 0.0;
+#pragma unroll
+      for (int o = 0; o < OP; ++o) {
+        double t = 0.0;
+        for (int w = 0; w < nw; ++w) t += red[par][w][o];
+        if (lane == o) { zsum = t; bsel = b2[o]; }
+      }
+      const double z2 = zsum - bsel;
+      const double out = 1.0 / (1.0 + exp(-z2));                           // LG:73
+      const double desired = (lane == label) ? 1.0 : 0.0;
+      my_od = (lane < O) ? (desired - out) * (out * (1.0 - out)) : 0.0;    // LG:100
+#pragma unroll
+      for (int o = 0; o < OP; ++o) {
+        od[o] = __shfl_sync(0xffffffffu, my_od, o);
+        back += od[o] * w2[o];                                             // LG:101 (W2 BEFORE its update)
+      }
+    }
+    const double hd = back * (hid * (1.0 - hid));
+#pragma unroll
+    for (int o = 0; o < OP; ++o) {
+      w2[o] += hid * (od[o] * lr);                                         // LG:102
+      b2[o] += (-1.0 * lr) * od[o];                                        // LG:103
+    }
+    const double hl = hd * lr;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) w1[d] += xs[cur][d] * hl;                 // LG:105
+    b1 += (-1.0 * lr) * hd;                                                // LG:106
+  }
+  float* dst = theta_gd + (int64_t)row * ld;
+  if (live) {
+#pragma unroll
+    for (int d = 0; d < DP; ++d) if (d < D) dst[d * H + h] = (float)w1[d];
+#pragma unroll
+    for (int o = 0; o < OP; ++o) if (o < O) dst[D * H + h * O + o] = (float)w2[o];
+    dst[D * H + H * O + h] = (float)b1;
+  }
+  if (h == 0) {
+#pragma unroll
+    for (int o = 0; o < OP; ++o) if (o < O) dst[D * H + H * O + H + o] = (float)b2[o];
+  }
+}
+
 constexpr int kBT = 128;  // rows per tile == threads
 
 __global__ void __launch_bounds__(kBT) langevin_batch_kernel(const float* x, const int32_t* y, int64_t n, int DP, int D, int H, int O,
@@ -352,6 +459,34 @@ extern "C" int sapt_langevin(sapt_problem_t* p, const float* theta, float* theta
   const DataSet& ds = p->set[0];
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 0) {
+    if (p->H <= 128) {
+      const int threads = ((p->H + 31) / 32) * 32;
+#define SAPT_SGD(DPV, OPV) langevin_sgd_reg_kernel<DPV, OPV><<<R, threads, 0, st>>>(ds.x, p->DP, ds.y, ds.n, p->D, p->H, p->O, theta, theta_gd, ld, rows, n_rows, R, lrate);
+#define SAPT_SGD_OP(DPV)                                                          \
+  switch (p->OP) {                                                                \
+    case 4: SAPT_SGD(DPV, 4) break;                                               \
+    case 8: SAPT_SGD(DPV, 8) break;                                               \
+    case 12: SAPT_SGD(DPV, 12) break;                                             \
+    case 16: SAPT_SGD(DPV, 16) break;                                             \
+    case 20: SAPT_SGD(DPV, 20) break;                                             \
+    default: set_error("sapt_langevin: O padded to %d unsupported", p->OP); return SAPT_ERR_UNSUPPORTED; \
+  }
+      switch ((p->D + 7) / 8) {  // features padded to a multiple of 8 only: the register-resident column is D8 doubles
+        case 1: SAPT_SGD_OP(8) break;
+        case 2: SAPT_SGD_OP(16) break;
+        case 3: SAPT_SGD_OP(24) break;
+        case 4: SAPT_SGD_OP(32) break;
+        case 5: SAPT_SGD_OP(40) break;
+        case 6: SAPT_SGD_OP(48) break;
+        case 7: SAPT_SGD_OP(56) break;
+        case 8: SAPT_SGD_OP(64) break;
+        default: set_error("sapt_langevin: D = %d unsupported", p->D); return SAPT_ERR_UNSUPPORTED;
+      }
+#undef SAPT_SGD_OP
+#undef SAPT_SGD
+      SAPT_CHECK_LAUNCH();
+      return SAPT_OK;
+    }
     const size_t smem = (size_t)(p->P + p->D + 2 * p->H + p->O) * sizeof(double);
     if (smem > 200 * 1024) { set_error("sapt_langevin: topology too large for the sgd_exact kernel"); return SAPT_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024) SAPT_CUDA(cudaFuncSetAttribute(langevin_sgd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -423,7 +423,7 @@ def test_cuda_graph_replay_equals_eager(lib, variant, use_sur, use_lg):
                            use_surrogate=use_sur, use_langevin=use_lg, learn_rate=0.05, seed=5)
         eng = PTEngine(prob, assign_temperatures(6, 4.0), cfg, surrogate_trainer=lambda batch, sig: sw[sig - 1])
         eng.initialize(g["W"][1])
-        eng.run(graph=graph); torch.cuda.synchronize()
+        eng.run(graph=graph, fused=False); torch.cuda.synchronize()
         return eng.results(), eng
 
     (a, ea), (b, eb) = run(False), run(True)
