@@ -300,8 +300,13 @@ extern "C" int sapt_swap_sweep_dev(int R_global, double* lik_post, const double*
                                    int32_t* num_swap, int32_t* src_slot, int row0, int R_local, int32_t* slot_of_row_local,
                                    void* stream) {
   SAPT_REQUIRE(R_global >= 1 && lik_post && temperature && row_of_slot, "sapt_swap_sweep");
-  // scratch: src[R] + old_rows[R] (int32) and post[R] (double), kept in a small per-process buffer
-  static int32_t* sc_i = nullptr; static double* sc_d = nullptr; static int sc_cap = 0;
+  // scratch: src[R] + old_rows[R] (int32) and post[R] (double), one small buffer per device of this process
+  constexpr int kMaxDev = 64;
+  static int32_t* sc_i_dev[kMaxDev] = {nullptr}; static double* sc_d_dev[kMaxDev] = {nullptr}; static int sc_cap_dev[kMaxDev] = {0};
+  int dev = 0;
+  SAPT_CUDA(cudaGetDevice(&dev));
+  SAPT_REQUIRE(dev >= 0 && dev < kMaxDev, "device ordinal");
+  int32_t*& sc_i = sc_i_dev[dev]; double*& sc_d = sc_d_dev[dev]; int& sc_cap = sc_cap_dev[dev];
   if (R_global > sc_cap) {
     SAPT_CUDA(cudaDeviceSynchronize());
     if (sc_i) { SAPT_CUDA(cudaFree(sc_i)); SAPT_CUDA(cudaFree(sc_d)); }
