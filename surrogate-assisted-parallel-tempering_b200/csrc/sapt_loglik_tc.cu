@@ -22,7 +22,10 @@ namespace sapt {
 constexpr int kTileM = 128;
 constexpr int kKA = 64;  // bf16 per A / B1 row
 
-bool tc_topology_supported(int D, int H, int O) { return D <= 16 && H <= 32 && O <= (H <= 16 ? 16 : 32) && O <= 20; }
+bool tc2_supported(int D, int H, int O);   // sapt_loglik_tc2.cu
+int tc2_a_row_elems(int D);
+int tc2_piece_width(int D);
+bool tc_topology_supported(int D, int H, int O) { return tc2_supported(D, H, O); }
 
 // ---- per-step operand packing -----------------------------------------------------------------
 // ---- host side ----------------------------------------------------------------------------------
@@ -65,10 +68,12 @@ static inline float bf2f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float v; 
 
 int tc_prepare_dataset(sapt_problem* p, int which, const float* x_host, int64_t n) {
   DataSet& ds = p->set[which];
-  std::vector<uint16_t> img((size_t)ds.n_pad * kKA, 0);
+  const int krow = tc2_a_row_elems(p->D);      // bf16 per row: [x1 | x2 | x3 | 1 1 1 0..] padded to 128-byte blocks
+  const int dw = tc2_piece_width(p->D);        // features per piece (padded to 16/32/64)
+  std::vector<uint16_t> img((size_t)ds.n_pad * krow, 0);
   const uint16_t one = f2bf(1.0f);
   for (int64_t i = 0; i < ds.n_pad; ++i) {
-    uint16_t* row = &img[(size_t)i * kKA];
+    uint16_t* row = &img[(size_t)i * krow];
     if (i < n) {
       for (int d = 0; d < p->D; ++d) {
         const float v = x_host[(size_t)i * p->DP + d];
@@ -76,15 +81,15 @@ int tc_prepare_dataset(sapt_problem* p, int which, const float* x_host, int64_t 
         pc[0] = f2bf(v); const float r1 = v - bf2f(pc[0]);
         pc[1] = f2bf(r1); const float r2 = r1 - bf2f(pc[1]);
         pc[2] = f2bf(r2);
-        row[d] = pc[0]; row[16 + d] = pc[1]; row[32 + d] = pc[2];
+        row[d] = pc[0]; row[dw + d] = pc[1]; row[2 * dw + d] = pc[2];
       }
     }
-    row[48] = one; row[49] = one; row[50] = one;
+    row[3 * dw] = one; row[3 * dw + 1] = one; row[3 * dw + 2] = one;
   }
   SAPT_CUDA(cudaMalloc(&ds.a_bf16, img.size() * 2));
   SAPT_CUDA(cudaMemcpy(ds.a_bf16, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
   ds.tmap = aligned_alloc(64, sizeof(CUtensorMap));
-  return tc_make_map_2d(reinterpret_cast<CUtensorMap*>(ds.tmap), ds.a_bf16, kKA, (uint64_t)ds.n_pad, kTileM);
+  return tc_make_map_2d(reinterpret_cast<CUtensorMap*>(ds.tmap), ds.a_bf16, (uint64_t)krow, (uint64_t)ds.n_pad, kTileM);
 }
 
 int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld, int R, const int32_t* rows, const int32_t* n_rows,

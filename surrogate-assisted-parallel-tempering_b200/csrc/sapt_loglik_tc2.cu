@@ -28,6 +28,7 @@
 // buffers of 4 HP columns, two D2 buffers of 4 ON columns. The epilogue is software pipelined (phase 1 of unit
 // u+1 before phase 2 of unit u) so that every MMA has a full unit of slack before its result is awaited.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "sapt_device.cuh"
@@ -38,19 +39,49 @@ namespace sapt {
 
 namespace v2 {
 constexpr int kTileM = 128;
-constexpr int kKA = 64;         // bf16 per A / B1 row: [p1 | p2 | p3 | bias chunk]
-constexpr int kUC = 4;          // chains per unit (one MMA-1)
-constexpr int kEPQ = 4;                 // epilogue warps per TMEM lane quarter
-constexpr int kEpiWarps = 4 * kEPQ;
-constexpr int kCPW = kUC / kEPQ;        // chains per epilogue warp and unit
+constexpr int kEpiWarps = 16;           // four per TMEM lane quarter
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 // The SMSP arbiter favours the highest warp id: the two single-thread roles that feed everyone else
 // (TMA producer, MMA issuer) sit above the epilogue warps so they are never starved by them.
 constexpr int kTmaWarp = kEpiWarps;
 constexpr int kMmaWarp = kEpiWarps + 1;
-constexpr uint32_t kAStageBytes = kTileM * 128;  // 16 KB
-constexpr uint32_t kB1Bytes = 256 * 128;         // 32 KB
+constexpr int kSmemLimit = 224 * 1024;
 }  // namespace v2
+
+// Compile-time geometry of one kernel variant. HP = padded hidden width (16/32/64), ON = padded output width
+// (16/32), DKC = 16-feature chunks per x piece (D <= 16 DKC).
+template <int HP, int ON, int DKC>
+struct TcCfg {
+  static constexpr int HALVES = (HP == 64) ? 2 : 1;       // epilogue warps sharing one chain's hidden units
+  static constexpr int UC = 4 / HALVES;                   // chains per unit (one MMA-1)
+  static constexpr int HW = HP / HALVES;                  // hidden units per epilogue warp
+  static constexpr int N1 = UC * HP;                      // MMA-1 N (<= 128)
+  static constexpr int KA = 48 * DKC + 16;                // used bf16 per A / B1 row: [x1|x2|x3|bias chunk]
+  static constexpr int KBA = (KA + 63) / 64;              // 128-byte K blocks per row
+  static constexpr int N2 = (ON == 16) ? 48 : 64;         // D2 columns per chain
+  static constexpr int PARTS = N2 / ON;
+  static constexpr int W2ROWS = 3 * ON;                   // W2 image rows per chain (pieces w1, w2, w3), K = HP <= 64
+  static constexpr uint32_t kAStage = KBA * 128 * 128;    // bytes per A stage
+  static constexpr int STAGES = (KBA == 1) ? 4 : ((KBA == 2) ? 3 : 2);
+  static constexpr uint32_t smem_bytes(int upt) {
+    const int ch = UC * upt;
+    return 1024u + (uint32_t)ch * HP * KBA * 128 + STAGES * kAStage + (uint32_t)ch * W2ROWS * 128 + (uint32_t)ch * ON * 4 + 2048u +
+           (uint32_t)ch * 4 * HALVES * 3 * 8;
+  }
+  static constexpr int pick_upt() {
+    for (int upt = 4; upt >= 1; upt >>= 1)
+      if (UC * upt * HP <= 256 && smem_bytes(upt) <= (uint32_t)v2::kSmemLimit) return upt;
+    return 0;
+  }
+  static constexpr int UPT = pick_upt();                  // units per row tile (0: variant does not fit)
+  static constexpr int CH = UC * (UPT > 0 ? UPT : 1);     // chains per CTA
+  static constexpr int kW2BoxMax = (ON == 16) ? 4 : 2;    // chains per W2 TMA box: box rows <= 256, divides CH
+  static constexpr int kW2Box = kW2BoxMax < CH ? kW2BoxMax : CH;
+  static constexpr int kD2Bufs = (2 * N1 + 2 * UC * N2 <= 512) ? 2 : 1;
+  static_assert(2 * N1 + kD2Bufs * UC * N2 <= 512, "TMEM budget");
+  static_assert(ON <= HP, "D2 partial sums reuse the chain's hidden width");
+  static_assert(CH % kW2Box == 0 && kW2Box * W2ROWS <= 256, "W2 TMA box");
+};
 
 struct Tc2Params {
   const int32_t* y; int64_t n_pad;
@@ -61,40 +92,42 @@ struct Tc2Params {
 };
 
 // ---- per-step operand packing ------------------------------------------------------------------------
-// B1: [group][CH*HP][64] = [w1 | w2 | w3 | b1 b2 b3 0..] per hidden unit (rows), 16 inputs per chunk
-// W2: [group][CH][3 pieces][ON][64]: row (p, o) = piece p of -log2(e) W2[:, o] over the HP hidden units (rest 0).
-//     MMA-2 reads rows [0, 3 ON) as one N = 3 ON operand against h1 and rows [0, ON) again against h2.
+// B1: [group][CH*HP rows][KBA*64] : row (chain, h) = [w1 (16 DKC) | w2 | w3 | b1 b2 b3 0..], w = -log2(e) W1[:, h]
+// W2: [group][CH][3 ON rows][64]  : row (p, o) = piece p of -log2(e) W2[:, o] over the HP hidden units (rest 0).
+//     MMA-2 reads rows [0, N2) as one operand against h1 and rows [0, 2 ON) again against h2.
 __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O,
-                                int HP, int ON, int CH, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2) {
+                                int HP, int ON, int CH, int DKC, int KROW, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2) {
   constexpr int KW = 64;
   const int nact = n_rows ? *n_rows : R;
   const int pos = blockIdx.x;
   const int n_pos_pad = ((nact + CH - 1) / CH) * CH;
   if (pos >= n_pos_pad) return;
   const int grp = pos / CH, within = pos - grp * CH;
-  __nv_bfloat16* brow0 = b1img + ((int64_t)grp * 256 + (int64_t)within * HP) * v2::kKA;
+  __nv_bfloat16* brow0 = b1img + ((int64_t)grp * CH * HP + (int64_t)within * HP) * KROW;
   __nv_bfloat16* wrow0 = w2img + ((int64_t)grp * CH + within) * (3 * ON) * KW;
   float* bb = bias2 + (int64_t)pos * ON;
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
   if (pos >= nact) {
-    for (int i = threadIdx.x; i < HP * v2::kKA; i += blockDim.x) brow0[i] = zero;
+    for (int i = threadIdx.x; i < HP * KROW; i += blockDim.x) brow0[i] = zero;
     for (int i = threadIdx.x; i < 3 * ON * KW; i += blockDim.x) wrow0[i] = zero;
     for (int i = threadIdx.x; i < ON; i += blockDim.x) bb[i] = 0.f;
     return;
   }
   const int row = rows ? rows[pos] : pos;
   const float* src = theta + (int64_t)row * ld;
-  for (int i = threadIdx.x; i < HP * 16; i += blockDim.x) {
-    const int h = i >> 4, d = i & 15;
-    __nv_bfloat16 p[3] = {zero, zero, zero}, b[3] = {zero, zero, zero};
-    if (h < H) {
-      if (d < D) split3(-kLog2e * src[d * H + h], p[0], p[1], p[2]);
-      if (d == 0) split3(kLog2e * src[D * H + H * O + h], b[0], b[1], b[2]);
-    }
-    __nv_bfloat16* dst = brow0 + (int64_t)h * v2::kKA;
-    dst[d] = p[0]; dst[16 + d] = p[1]; dst[32 + d] = p[2];
-    if (d == 0) { dst[48] = b[0]; dst[49] = b[1]; dst[50] = b[2]; }
-    else if (d >= 3) dst[48 + d] = zero;
+  const int DW = 16 * DKC;                      // features per piece (padded)
+  for (int i = threadIdx.x; i < HP * DW; i += blockDim.x) {
+    const int h = i / DW, d = i - h * DW;
+    __nv_bfloat16 p[3] = {zero, zero, zero};
+    if (h < H && d < D) split3(-kLog2e * src[d * H + h], p[0], p[1], p[2]);
+    __nv_bfloat16* dst = brow0 + (int64_t)h * KROW;
+    dst[d] = p[0]; dst[DW + d] = p[1]; dst[2 * DW + d] = p[2];
+  }
+  for (int i = threadIdx.x; i < HP * (KROW - 3 * DW); i += blockDim.x) {   // bias chunk + tail padding
+    const int h = i / (KROW - 3 * DW), q = i - h * (KROW - 3 * DW);
+    __nv_bfloat16 v = zero;
+    if (h < H && q < 3) { __nv_bfloat16 b[3]; split3(kLog2e * src[D * H + H * O + h], b[0], b[1], b[2]); v = b[q]; }
+    brow0[(int64_t)h * KROW + 3 * DW + q] = v;
   }
   for (int i = threadIdx.x; i < ON * KW; i += blockDim.x) {
     const int o = i / KW, h = i - o * KW;
@@ -120,48 +153,44 @@ __device__ __forceinline__ void sigmoid4(float t0, float t1, float t2, float t3,
   s0 = rab * a1; s1 = rab * a0; s2 = rcd * a3; s3 = rcd * a2;
 }
 
-template <int HP, int ON, int STAGES>
+template <int HP, int ON, int DKC>
 __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b1,
                                                                      const __grid_constant__ CUtensorMap map_w2, Tc2Params p) {
   using namespace v2;
-  constexpr int CH = 256 / HP;              // chains per CTA
-  constexpr int UPT = CH / kUC;             // units (MMA-1 issues) per row tile
-  constexpr int N1 = kUC * HP;              // MMA-1 N
-  // MMA-2 output width per chain. ON = 16: three partial sums side by side (h.[w1|w2|w3]). ON = 32: two
-  // ([w1|w2]); the w3 term is a separate N = ON MMA accumulating onto the first block (TMEM budget).
-  constexpr int N2 = (ON == 16) ? 3 * ON : 2 * ON;
-  constexpr int kParts = N2 / ON;
-  constexpr int kW2Rows = 3 * ON;                        // W2 image rows per chain: pieces w1, w2, w3
-  constexpr int kW2Box = (ON == 16) ? 4 : 2;             // chains per TMA box (box rows <= 256)
-  constexpr uint32_t kW2ChainBytes = kW2Rows * 128;
+  using C = TcCfg<HP, ON, DKC>;
+  constexpr int HALVES = C::HALVES, UC = C::UC, HW = C::HW, N1 = C::N1, KBA = C::KBA, N2 = C::N2, PARTS = C::PARTS;
+  constexpr int UPT = C::UPT, CH = C::CH, STAGES = C::STAGES, kD2Bufs = C::kD2Bufs;
+  static_assert(UPT >= 1, "variant does not fit in shared memory");
+  constexpr uint32_t kAStage = C::kAStage;
+  constexpr uint32_t kABlock = 128 * 128;                     // one K block of an A tile: 128 rows x 128 B
+  constexpr uint32_t kB1Block = CH * HP * 128;                // one K block of the B1 panel
+  constexpr uint32_t kB1Bytes = KBA * kB1Block;
+  constexpr uint32_t kW2ChainBytes = C::W2ROWS * 128;
   constexpr uint32_t kW2Bytes = CH * kW2ChainBytes;
-  // TMEM columns: [D1 | HV (A operand of MMA-2) | D2 buffers]. D2 of a chain is 3 ON wide: the three partial
-  // sums h.w1, h.w2, h.w3 land side by side (each A piece is read from TMEM once — an MMA with A in TMEM costs
-  // ~64 cycles whatever N is) and are added by the epilogue.
-  constexpr int kHvBufs = 1;
-  constexpr int kD2Bufs = (N1 + kUC * HP + 2 * kUC * N2 <= 512) ? 2 : 1;
+  // TMEM columns: [D1 | HV (A operand of MMA-2) | D2 buffers]. D2 of a chain is N2 wide: the partial sums h.w1,
+  // h.w2 (, h.w3) land side by side (each A piece is read from TMEM once — an MMA with A in TMEM costs ~64 cycles
+  // whatever N is) and are added by the epilogue.
   constexpr int kHvBase = N1;
-  constexpr int kD2Base = kHvBase + kHvBufs * kUC * HP;
-  static_assert(kD2Base + kD2Bufs * kUC * N2 <= 512, "TMEM budget");
+  constexpr int kD2Base = 2 * N1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB1 = smem;
   uint8_t* sA = sB1 + kB1Bytes;
-  uint8_t* sW2 = sA + STAGES * kAStageBytes;
+  uint8_t* sW2 = sA + STAGES * kAStage;
   float* sBias = reinterpret_cast<float*>(sW2 + kW2Bytes);          // [CH][ON]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + CH * ON);
   uint64_t* full_a = bars;                  // [STAGES]
   uint64_t* empty_a = full_a + STAGES;      // [STAGES]
   uint64_t* b_full = empty_a + STAGES;      // [1]
-  uint64_t* d1_full = b_full + 1;           // [2] (one used)
-  uint64_t* d1_empty = d1_full + 2;         // [2] (one used)
+  uint64_t* d1_full = b_full + 1;           // [1]
+  uint64_t* d1_empty = d1_full + 1;         // [1]
   // hv_full / d2_full are per (unit parity, chain): with one barrier per chain a fast warp could complete
   // phase u+1 before the waiter has looked at phase u, and a parity wait cannot see a barrier two phases ahead
-  uint64_t* hv_full = d1_empty + 2;         // [2][kUC]
-  uint64_t* d2_full = hv_full + 2 * kUC;    // [2][kUC]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d2_full + 2 * kUC);
-  double* red = reinterpret_cast<double*>(tmem_ptr + 2);  // [CH][4 quarters][3]
+  uint64_t* hv_full = d1_empty + 1;         // [2][UC]
+  uint64_t* d2_full = hv_full + 2 * UC;     // [2][UC]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d2_full + 2 * UC);
+  double* red = reinterpret_cast<double*>(tmem_ptr + 2);  // [CH][4 quarters * HALVES][3]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nact = p.n_rows ? *p.n_rows : p.R;
@@ -175,9 +204,9 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
     mbar_init(b_full, 1);
-    mbar_init(&d1_full[0], 1);
-    mbar_init(&d1_empty[0], kEpiWarps);
-    for (int c = 0; c < 2 * kUC; ++c) { mbar_init(&hv_full[c], 4); mbar_init(&d2_full[c], 1); }
+    mbar_init(d1_full, 1);
+    mbar_init(d1_empty, kEpiWarps);
+    for (int c = 0; c < 2 * UC; ++c) { mbar_init(&hv_full[c], 4 * HALVES); mbar_init(&d2_full[c], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -200,47 +229,51 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
     // ================= TMA producer =================
     if (lane == 0) {
       mbar_expect_tx(b_full, kB1Bytes + kW2Bytes);
-      tma_load_2d(&map_b1, b_full, sB1, 0, blockIdx.y * 256);
 #pragma unroll
-      for (int q = 0; q < CH / kW2Box; ++q)  // boxes of kW2Box chains x 3 ON rows
-        tma_load_2d(&map_w2, b_full, sW2 + q * kW2Box * kW2ChainBytes, 0, (blockIdx.y * CH + q * kW2Box) * kW2Rows);
+      for (int kb = 0; kb < KBA; ++kb) tma_load_2d(&map_b1, b_full, sB1 + kb * kB1Block, kb * 64, blockIdx.y * CH * HP);
+#pragma unroll
+      for (int q = 0; q < CH / C::kW2Box; ++q)  // boxes of kW2Box chains x 3 ON rows
+        tma_load_2d(&map_w2, b_full, sW2 + q * C::kW2Box * kW2ChainBytes, 0, (blockIdx.y * CH + q * C::kW2Box) * C::W2ROWS);
       for (int it = 0; it < n_my_tiles; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait<1000>(&empty_a[s], ph ^ 1);
-        mbar_expect_tx(&full_a[s], kAStageBytes);
-        tma_load_2d(&map_a, &full_a[s], sA + s * kAStageBytes, 0, (int)((t_begin + it) * kTileM));
+        mbar_expect_tx(&full_a[s], kAStage);
+#pragma unroll
+        for (int kb = 0; kb < KBA; ++kb)
+          tma_load_2d(&map_a, &full_a[s], sA + s * kAStage + kb * kABlock, kb * 64, (int)((t_begin + it) * kTileM));
       }
     }
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
-      const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint32_t idesc2a = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint32_t idesc2b = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * ON) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint32_t idesc2c = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ON >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      auto idesc = [](int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24); };
+      const uint32_t idesc1 = idesc(N1), idesc2a = idesc(N2), idesc2b = idesc(2 * ON), idesc2c = idesc(ON);
       const uint32_t b1_addr = smem_u32(sB1);
       const uint32_t w2_addr = smem_u32(sW2);
       mbar_wait(b_full, 0);
       auto issue_mma1 = [&](int u) {
         const int it = u / UPT, uu = u - it * UPT;
         const int s = it % STAGES;
-        if (u > 0) mbar_wait(&d1_empty[0], (u - 1) & 1);  // every warp holds D1(u-1) in registers
+        if (u > 0) mbar_wait(d1_empty, (u - 1) & 1);  // every warp holds D1(u-1) in registers
         if (uu == 0) mbar_wait(&full_a[s], (it / STAGES) & 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + s * kAStageBytes);
+        const uint32_t a_addr = smem_u32(sA + s * kAStage);
         const uint32_t b_addr = b1_addr + (uint32_t)(uu * N1) * 128;
-        // (A chunk, B chunk) pairs: x1w1 x1w2 x2w1 x1w3 x2w2 x3w1 + bias; a chunk = 16 elements = 32 bytes
-        constexpr int ia[7] = {0, 0, 1, 0, 1, 2, 3};
-        constexpr int ib[7] = {0, 1, 0, 2, 1, 0, 3};
+        // split product: (piece of x, piece of w) = x1w1 x1w2 x2w1 x1w3 x2w2 x3w1, DKC chunks of 16 features each,
+        // then the bias chunk. chunk c = 16 elements = 32 bytes inside K block c/4.
+        constexpr int pa[6] = {0, 0, 1, 0, 1, 2};
+        constexpr int pb[6] = {0, 1, 0, 2, 1, 0};
+        auto a_at = [&](int chunk) { return umma_desc_sw128(a_addr + (uint32_t)(chunk >> 2) * kABlock + (uint32_t)(chunk & 3) * 32); };
+        auto b_at = [&](int chunk) { return umma_desc_sw128(b_addr + (uint32_t)(chunk >> 2) * kB1Block + (uint32_t)(chunk & 3) * 32); };
 #pragma unroll
-        for (int k = 0; k < 7; ++k)
-#if defined(SAPT_EXP_NO_MMA1)
-          if (k == 0)
-#endif
-          tc_mma_bf16(tmem_base, umma_desc_sw128(a_addr + ia[k] * 32), umma_desc_sw128(b_addr + ib[k] * 32), idesc1, k > 0 ? 1u : 0u);
+        for (int q = 0; q < 6; ++q)
+#pragma unroll
+          for (int j = 0; j < DKC; ++j)
+            tc_mma_bf16(tmem_base, a_at(pa[q] * DKC + j), b_at(pb[q] * DKC + j), idesc1, (q | j) ? 1u : 0u);
+        tc_mma_bf16(tmem_base, a_at(3 * DKC), b_at(3 * DKC), idesc1, 1u);
         if (uu == UPT - 1) tc_commit(&empty_a[s]);
-        tc_commit(&d1_full[0]);
+        tc_commit(d1_full);
       };
       if (n_units > 0) issue_mma1(0);
       for (int u = 0; u < n_units; ++u) {
@@ -248,12 +281,12 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
         // D1(u+1) first: its trigger (all warps loaded D1(u)) precedes the HV(u) hand-over in every warp
         if (u + 1 < n_units) issue_mma1(u + 1);
 #pragma unroll
-        for (int c = 0; c < kUC; ++c) {
-          mbar_wait(&hv_full[(u & 1) * kUC + c], (u >> 1) & 1);
+        for (int c = 0; c < UC; ++c) {
+          mbar_wait(&hv_full[(u & 1) * UC + c], (u >> 1) & 1);
           tc_fence_after();
-          const uint32_t d2 = tmem_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (kUC * N2) + c * N2);
+          const uint32_t d2 = tmem_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (UC * N2) + c * N2);
           const uint32_t hv = tmem_hv + (uint32_t)(c * HP);
-          const uint32_t wb = w2_addr + (uint32_t)(uu * kUC + c) * kW2ChainBytes;
+          const uint32_t wb = w2_addr + (uint32_t)(uu * UC + c) * kW2ChainBytes;
           // ON=16: D2[:, 0:3ON] = h1.[w1|w2|w3], D2[:, 0:2ON] += h2.[w1|w2]
           // ON=32: D2[:, 0:2ON] = h1.[w1|w2],    D2[:, 0:ON] += h1.w3,  D2[:, 0:2ON] += h2.[w1|w2]   (h piece = HP/2 columns)
 #pragma unroll
@@ -267,80 +300,70 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
 #pragma unroll
           for (int half = 0; half < HP / 16; ++half)
             tc_mma_bf16_ts(d2, hv + (uint32_t)(HP / 2 + half * 8), umma_desc_sw128(wb + half * 32), idesc2b, 1u);
-          tc_commit(&d2_full[(u & 1) * kUC + c]);
+          tc_commit(&d2_full[(u & 1) * UC + c]);
         }
       }
     }
   } else {
     // ================= epilogue warps =================
-    const int ew = warp;
+    // warp (quarter q, index e): TMEM lanes 32q.., chain c = e / HALVES of every unit, hidden units
+    // [hf*HW, hf*HW + HW) with hf = e % HALVES. With HALVES = 2 the two warps of a chain alternate on phase 2.
     const int quarter = warp & 3;
-    const int e = ew >> 2;                    // this warp owns chains e*kCPW .. e*kCPW+kCPW-1 of every unit
+    const int e = warp >> 2;
+    const int c = e / HALVES, hf = e % HALVES;
     const int O = p.O;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    double accL[UPT][kCPW];
-    int accNc[UPT][kCPW], accSq[UPT][kCPW];
+    double accL[UPT];
+    int accNc[UPT], accSq[UPT];
 #pragma unroll
-    for (int a = 0; a < UPT; ++a)
-#pragma unroll
-      for (int b = 0; b < kCPW; ++b) { accL[a][b] = 0.0; accNc[a][b] = 0; accSq[a][b] = 0; }
+    for (int a = 0; a < UPT; ++a) { accL[a] = 0.0; accNc[a] = 0; accSq[a] = 0; }
     // Software pipeline over units: phase 1 of unit u+1 (sigmoid + split, SIMT) runs while the tensor pipe
     // computes MMA-2 of unit u, so the warp never waits for D2 right after handing over its activations.
-    uint32_t hv[kCPW][HP];  // [h1 pairs (HP/2) | h2 pairs (HP/2)] of the unit whose phase 1 ran last
+    uint32_t hv[HW];  // [h1 pairs (HW/2) | h2 pairs (HW/2)] of the unit whose phase 1 ran last
     auto phase1 = [&](int u) {
-      mbar_wait(&d1_full[0], u & 1);
+      mbar_wait(d1_full, u & 1);
       tc_fence_after();
-      uint32_t zr[kCPW][HP];
-#pragma unroll
-      for (int cc = 0; cc < kCPW; ++cc) {
-        const uint32_t taddr = tmem_base + lane_base + (uint32_t)((kCPW * e + cc) * HP);
-        if constexpr (HP == 32) tmem_ld32(taddr, zr[cc]); else tmem_ld16(taddr, zr[cc]);
-      }
+      uint32_t zr[HW];
+      const uint32_t taddr = tmem_base + lane_base + (uint32_t)(c * HP + hf * HW);
+      if constexpr (HW == 32) tmem_ld32(taddr, zr); else tmem_ld16(taddr, zr);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&d1_empty[0]);  // D1 is in registers: the next MMA-1 may overwrite it
-#if defined(SAPT_EXP_SKIP_P1)
+      if (lane == 0) mbar_arrive(d1_empty);  // D1 is in registers: the next MMA-1 may overwrite it
 #pragma unroll
-      for (int cc = 0; cc < kCPW; ++cc)
-#pragma unroll
-        for (int j = 0; j < HP; ++j) hv[cc][j] = zr[cc][j] & 0x3f803f80u;
-      return;
-#endif
-#pragma unroll
-      for (int cc = 0; cc < kCPW; ++cc) {
-#pragma unroll
-        for (int j = 0; j < HP / 4; ++j) {
-          float h0, h1, h2, h3;
-          sigmoid4(__uint_as_float(zr[cc][4 * j]), __uint_as_float(zr[cc][4 * j + 1]), __uint_as_float(zr[cc][4 * j + 2]),
-                   __uint_as_float(zr[cc][4 * j + 3]), h0, h1, h2, h3);
-          // h1 piece = h truncated to bf16 (one PRMT packs two), h2 piece = the exact, non-negative residual
-          // rounded half-up to bf16. The residual is not zero-mean, so MMA-2 also accumulates h2.w2.
-          const uint32_t u0 = __float_as_uint(h0), u1 = __float_as_uint(h1), u2 = __float_as_uint(h2), u3 = __float_as_uint(h3);
-          hv[cc][2 * j] = __byte_perm(u0, u1, 0x7632);
-          hv[cc][2 * j + 1] = __byte_perm(u2, u3, 0x7632);
-          const uint32_t r0 = __float_as_uint(h0 - __uint_as_float(u0 & 0xffff0000u)) + 0x8000u;
-          const uint32_t r1 = __float_as_uint(h1 - __uint_as_float(u1 & 0xffff0000u)) + 0x8000u;
-          const uint32_t r2 = __float_as_uint(h2 - __uint_as_float(u2 & 0xffff0000u)) + 0x8000u;
-          const uint32_t r3 = __float_as_uint(h3 - __uint_as_float(u3 & 0xffff0000u)) + 0x8000u;
-          hv[cc][HP / 2 + 2 * j] = __byte_perm(r0, r1, 0x7632);
-          hv[cc][HP / 2 + 2 * j + 1] = __byte_perm(r2, r3, 0x7632);
-        }
+      for (int j = 0; j < HW / 4; ++j) {
+        float h0, h1, h2, h3;
+        sigmoid4(__uint_as_float(zr[4 * j]), __uint_as_float(zr[4 * j + 1]), __uint_as_float(zr[4 * j + 2]),
+                 __uint_as_float(zr[4 * j + 3]), h0, h1, h2, h3);
+        // h1 piece = h truncated to bf16 (one PRMT packs two), h2 piece = the exact, non-negative residual
+        // rounded half-up to bf16. The residual is not zero-mean, so MMA-2 also accumulates h2.w2.
+        const uint32_t u0 = __float_as_uint(h0), u1 = __float_as_uint(h1), u2 = __float_as_uint(h2), u3 = __float_as_uint(h3);
+        hv[2 * j] = __byte_perm(u0, u1, 0x7632);
+        hv[2 * j + 1] = __byte_perm(u2, u3, 0x7632);
+        const uint32_t r0 = __float_as_uint(h0 - __uint_as_float(u0 & 0xffff0000u)) + 0x8000u;
+        const uint32_t r1 = __float_as_uint(h1 - __uint_as_float(u1 & 0xffff0000u)) + 0x8000u;
+        const uint32_t r2 = __float_as_uint(h2 - __uint_as_float(u2 & 0xffff0000u)) + 0x8000u;
+        const uint32_t r3 = __float_as_uint(h3 - __uint_as_float(u3 & 0xffff0000u)) + 0x8000u;
+        hv[HW / 2 + 2 * j] = __byte_perm(r0, r1, 0x7632);
+        hv[HW / 2 + 2 * j + 1] = __byte_perm(r2, r3, 0x7632);
       }
     };
     auto publish_hv = [&](int u) {  // activations of unit u -> TMEM (A operand of MMA-2), then tell the MMA warp
+      // chain HV region = [h1 pairs of all HP hidden units (HP/2 cols) | h2 pairs (HP/2 cols)]
+      const uint32_t hva = tmem_hv + lane_base + (uint32_t)(c * HP);
+      if constexpr (HALVES == 1) {
+        if constexpr (HW == 32) tmem_st32(hva, hv); else tmem_st16(hva, hv);
+      } else {
+        uint32_t lo[16], hi[16];
 #pragma unroll
-      for (int cc = 0; cc < kCPW; ++cc) {
-        const uint32_t hva = tmem_hv + lane_base + (uint32_t)((kCPW * e + cc) * HP);
-        if constexpr (HP == 32) tmem_st32(hva, hv[cc]); else tmem_st16(hva, hv[cc]);
+        for (int j = 0; j < 16; ++j) { lo[j] = hv[j]; hi[j] = hv[16 + j]; }
+        tmem_st16(hva + (uint32_t)(hf * 16), lo);
+        tmem_st16(hva + (uint32_t)(HP / 2 + hf * 16), hi);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-#pragma unroll
-        for (int cc = 0; cc < kCPW; ++cc) mbar_arrive(&hv_full[(u & 1) * kUC + kCPW * e + cc]);
-      }
+      if (lane == 0) mbar_arrive(&hv_full[(u & 1) * UC + c]);
     };
     if (n_units > 0) { phase1(0); publish_hv(0); }
     for (int it = 0; it < n_my_tiles; ++it) {
@@ -350,86 +373,68 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
       for (int uu = 0; uu < UPT; ++uu) {
         const int u = it * UPT + uu;
         const bool has_next = (u + 1 < n_units);
-        if (has_next) {
-          phase1(u + 1);
-          // two HV buffers: HV[(u+1)%2] was last read by MMA-2(u-1), whose completion this warp already observed
-          if constexpr (kHvBufs == 2) publish_hv(u + 1);
-        }
-        // ---- D2 of unit u: wait for MMA-2 (with one HV buffer this also frees it), pull it into registers ----
-        uint32_t dr0[kCPW][ON], dr1[kCPW][ON], dr2[kCPW][ON];  // the partial sums of D2 (dr2 unused when kParts == 2)
-#pragma unroll
-        for (int cc = 0; cc < kCPW; ++cc) {
-          const int c = kCPW * e + cc;
-          mbar_wait(&d2_full[(u & 1) * kUC + c], (u >> 1) & 1);
-        }
+        const bool mine = (HALVES == 1) || ((u & 1) == hf);   // which of the chain's warps runs phase 2 of this unit
+        if (has_next) phase1(u + 1);
+        // ---- D2 of unit u: wait for MMA-2 (this also frees the HV buffer), pull it into registers ----
+        uint32_t dr0[ON], dr1[ON], dr2[ON];  // the partial sums of D2 (dr2 unused when PARTS == 2)
+        mbar_wait(&d2_full[(u & 1) * UC + c], (u >> 1) & 1);
         tc_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < kCPW; ++cc) {
-          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (kUC * N2) + (kCPW * e + cc) * N2);
-          if constexpr (ON == 32) { tmem_ld32(taddr, dr0[cc]); tmem_ld32(taddr + ON, dr1[cc]); }
-          else { tmem_ld16(taddr, dr0[cc]); tmem_ld16(taddr + ON, dr1[cc]); tmem_ld16(taddr + 2 * ON, dr2[cc]); }
+        if (mine) {
+          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (UC * N2) + c * N2);
+          if constexpr (ON == 32) { tmem_ld32(taddr, dr0); tmem_ld32(taddr + ON, dr1); }
+          else { tmem_ld16(taddr, dr0); tmem_ld16(taddr + ON, dr1); tmem_ld16(taddr + 2 * ON, dr2); }
+          tmem_ld_wait();
         }
-        tmem_ld_wait();
-        if constexpr (kHvBufs == 1) { if (has_next) publish_hv(u + 1); }
+        if (has_next) publish_hv(u + 1);
+        if (!mine) continue;
         // ---- phase 2: output layer ----
+        const float* bias = sBias + (uu * UC + c) * ON;
+        float tmin = 0.f; int pm = 0; float sum = 0.f, oy = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < kCPW; ++cc) {
-          const int c = kCPW * e + cc;
-          const float* bias = sBias + (uu * kUC + c) * ON;
-          float tmin = 0.f; int pm = 0; float sum = 0.f, oy = 0.f;
-#if defined(SAPT_EXP_SKIP_P2)
-          sum = 2.0f; oy = __uint_as_float(dr0[cc][0]) + __uint_as_float(dr1[cc][ON - 1]) + bias[y & 3];
-#else
+        for (int g = 0; g < ON / 4; ++g) {
+          if (4 * g < O) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + 4 * g);
+            float t[4];
 #pragma unroll
-          for (int g = 0; g < ON / 4; ++g) {
-            if (4 * g < O) {
-              const float4 b = *reinterpret_cast<const float4*>(bias + 4 * g);
-              float t[4];
+            for (int k = 0; k < 4; ++k) {
+              const float bk = (k == 0 ? b.x : k == 1 ? b.y : k == 2 ? b.z : b.w);
+              if constexpr (PARTS == 3)
+                t[k] = (__uint_as_float(dr0[4 * g + k]) + __uint_as_float(dr1[4 * g + k])) + (__uint_as_float(dr2[4 * g + k]) + bk);
+              else
+                t[k] = (__uint_as_float(dr0[4 * g + k]) + __uint_as_float(dr1[4 * g + k])) + bk;
+            }
+            float s[4];
+            sigmoid4(t[0], t[1], t[2], t[3], s[0], s[1], s[2], s[3]);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float bk = (k == 0 ? b.x : k == 1 ? b.y : k == 2 ? b.z : b.w);
-                if constexpr (kParts == 3)
-                  t[k] = (__uint_as_float(dr0[cc][4 * g + k]) + __uint_as_float(dr1[cc][4 * g + k])) +
-                         (__uint_as_float(dr2[cc][4 * g + k]) + bk);
-                else
-                  t[k] = (__uint_as_float(dr0[cc][4 * g + k]) + __uint_as_float(dr1[cc][4 * g + k])) + bk;
-              }
-              float s[4];
-              sigmoid4(t[0], t[1], t[2], t[3], s[0], s[1], s[2], s[3]);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int o = 4 * g + k;
-                if (o < O) {
-                  if (o == 0 || t[k] < tmin) { tmin = t[k]; pm = o; }
-                  sum += ex2_approx(s[k] * kLog2e);
-                  if (o == y) oy = s[k];
-                }
+            for (int k = 0; k < 4; ++k) {
+              const int o = 4 * g + k;
+              if (o < O) {
+                if (o == 0 || t[k] < tmin) { tmin = t[k]; pm = o; }
+                sum += ex2_approx(s[k] * kLog2e);
+                if (o == y) oy = s[k];
               }
             }
           }
-#endif
-          if (y >= 0) {
-            accL[uu][cc] += (double)(oy - kLn2 * lg2_approx(sum));
-            accNc[uu][cc] += (pm == y);
-            const int d = pm - y;
-            accSq[uu][cc] += d * d;
-          }
+        }
+        if (y >= 0) {
+          accL[uu] += (double)(oy - kLn2 * lg2_approx(sum));
+          accNc[uu] += (pm == y);
+          const int d = pm - y;
+          accSq[uu] += d * d;
         }
       }
     }
 #pragma unroll
-    for (int uu = 0; uu < UPT; ++uu)
-#pragma unroll
-      for (int cc = 0; cc < kCPW; ++cc) {
-        const int chain = uu * kUC + kCPW * e + cc;
-        const double l = warp_sum(accL[uu][cc]);
-        const int a = warp_sum(accNc[uu][cc]);
-        const int b = warp_sum(accSq[uu][cc]);
-        if (lane == 0) {
-          double* r = red + (chain * 4 + quarter) * 3;
-          r[0] = l; r[1] = (double)a; r[2] = (double)b;
-        }
+    for (int uu = 0; uu < UPT; ++uu) {
+      const int chain = uu * UC + c;
+      const double l = warp_sum(accL[uu]);
+      const int a = warp_sum(accNc[uu]);
+      const int b = warp_sum(accSq[uu]);
+      if (lane == 0) {
+        double* r = red + ((chain * 4 + quarter) * HALVES + hf) * 3;
+        r[0] = l; r[1] = (double)a; r[2] = (double)b;
       }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -438,28 +443,78 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
   if (threadIdx.x < CH && g0 + (int)threadIdx.x < nact) {
-    const double* r = red + threadIdx.x * 12;
+    const double* r = red + threadIdx.x * (4 * HALVES * 3);
+    double l = 0.0, a = 0.0, b = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4 * HALVES; ++q) { l += r[3 * q]; a += r[3 * q + 1]; b += r[3 * q + 2]; }
     const int64_t o = (int64_t)blockIdx.x * p.R + (g0 + threadIdx.x);
-    p.partL[o] = (r[0] + r[3]) + (r[6] + r[9]);
-    p.partNc[o] = (int32_t)(r[1] + r[4] + r[7] + r[10]);
-    p.partSq[o] = (int32_t)(r[2] + r[5] + r[8] + r[11]);
+    p.partL[o] = l;
+    p.partNc[o] = (int32_t)a;
+    p.partSq[o] = (int32_t)b;
   }
 }
 
 // ---- host ------------------------------------------------------------------------------------------
 int tc_make_map_2d(CUtensorMap* map, void* base, uint64_t inner_elems, uint64_t rows, uint32_t box_rows);  // sapt_loglik_tc.cu
 
-template <int HP, int ON, int STAGES>
-static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb1, const CUtensorMap& mw2, const Tc2Params& a, dim3 grid, cudaStream_t st) {
-  constexpr int CH = 256 / HP;
-  const size_t smem = 1024 + v2::kB1Bytes + (size_t)STAGES * v2::kAStageBytes + (size_t)CH * 3 * ON * 128 + (size_t)CH * ON * 4 +
-                      (2 * STAGES + 1 + 2 * 2 + 4 * v2::kUC) * 8 + 16 + (size_t)CH * 12 * 8 + 64;
-  auto k = loglik_tc2_kernel<HP, ON, STAGES>;
-  SAPT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<grid, v2::kThreads, smem, st>>>(ma, mb1, mw2, a);
-  SAPT_CHECK_LAUNCH();
-  return SAPT_OK;
+struct Tc2Geom { int CH, KROW, W2BOX, UPT; size_t smem; };
+
+template <int HP, int ON, int DKC>
+static Tc2Geom geom_of() {
+  using C = TcCfg<HP, ON, DKC>;
+  return Tc2Geom{C::CH, C::KBA * 64, C::kW2Box, C::UPT, (size_t)C::smem_bytes(C::UPT > 0 ? C::UPT : 1)};
 }
+
+template <int HP, int ON, int DKC>
+static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb1, const CUtensorMap& mw2, const Tc2Params& a, dim3 grid, cudaStream_t st) {
+  using C = TcCfg<HP, ON, DKC>;
+  if constexpr (C::UPT < 1) {
+    set_error("tcgen05 path: variant HP=%d ON=%d DKC=%d does not fit in shared memory", HP, ON, DKC);
+    return SAPT_ERR_UNSUPPORTED;
+  } else {
+    const size_t smem = C::smem_bytes(C::UPT);
+    auto k = loglik_tc2_kernel<HP, ON, DKC>;
+    SAPT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, v2::kThreads, smem, st>>>(ma, mb1, mw2, a);
+    SAPT_CHECK_LAUNCH();
+    return SAPT_OK;
+  }
+}
+
+// dispatch over the compiled variants; fn is a generic lambda called with three integral_constants
+template <typename F>
+static int tc2_dispatch(int HP, int ON, int DKC, F&& fn) {
+#define SAPT_V(H, O, K) if (HP == H && ON == O && DKC == K) return fn(std::integral_constant<int, H>{}, std::integral_constant<int, O>{}, std::integral_constant<int, K>{});
+  SAPT_V(16, 16, 1) SAPT_V(16, 16, 2) SAPT_V(16, 16, 3) SAPT_V(16, 16, 4)
+  SAPT_V(32, 16, 1) SAPT_V(32, 16, 2) SAPT_V(32, 16, 3) SAPT_V(32, 16, 4)
+  SAPT_V(32, 32, 1) SAPT_V(32, 32, 2) SAPT_V(32, 32, 3) SAPT_V(32, 32, 4)
+  SAPT_V(64, 16, 1) SAPT_V(64, 16, 2) SAPT_V(64, 16, 3) SAPT_V(64, 16, 4)
+  SAPT_V(64, 32, 1) SAPT_V(64, 32, 2) SAPT_V(64, 32, 3) SAPT_V(64, 32, 4)
+#undef SAPT_V
+  set_error("tcgen05 path: no variant for HP=%d ON=%d DKC=%d", HP, ON, DKC);
+  return SAPT_ERR_UNSUPPORTED;
+}
+
+static int tc2_dkc(int D) { return D <= 16 ? 1 : (D + 15) / 16; }   // 16-feature chunks per x piece
+
+static void tc2_shape(const sapt_problem* p, int& HP, int& ON, int& DKC) {
+  HP = p->H <= 16 ? 16 : (p->H <= 32 ? 32 : 64);
+  ON = p->O <= 16 ? 16 : 32;
+  DKC = tc2_dkc(p->D);
+}
+
+bool tc2_supported(int D, int H, int O) {
+  if (D > 64 || H > 64 || O > 20) return false;
+  sapt_problem q{}; q.D = D; q.H = H; q.O = O;
+  int HP, ON, DKC; tc2_shape(&q, HP, ON, DKC);
+  if (ON > HP) return false;
+  int upt = 0;
+  tc2_dispatch(HP, ON, DKC, [&](auto h, auto o, auto k) { upt = TcCfg<h(), o(), k()>::UPT; return 0; });
+  return upt >= 1;
+}
+
+int tc2_a_row_elems(int D) { return ((48 * tc2_dkc(D) + 16 + 63) / 64) * 64; }
+int tc2_piece_width(int D) { return 16 * tc2_dkc(D); }
 
 static int gcd_int2(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
@@ -467,10 +522,13 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
                       double* L, int32_t* nc, double* sq, cudaStream_t st) {
   const DataSet& ds = p->set[which];
   if (R <= 0 || ds.n <= 0) return SAPT_OK;
-  const int HP = p->H <= 16 ? 16 : 32;
-  const int ON = (p->O <= 16) ? 16 : 32;
+  int HP, ON, DKC; tc2_shape(p, HP, ON, DKC);
   if (ON > HP) { set_error("tcgen05 path: O=%d needs H > 16", p->O); return SAPT_ERR_UNSUPPORTED; }
-  const int CH = 256 / HP;
+  Tc2Geom g{};
+  int rc = tc2_dispatch(HP, ON, DKC, [&](auto h, auto o, auto k) { g = geom_of<h(), o(), k()>(); return 0; });
+  if (rc) return rc;
+  if (g.UPT < 1) { set_error("tcgen05 path: topology %d-%d-%d does not fit", p->D, p->H, p->O); return SAPT_ERR_UNSUPPORTED; }
+  const int CH = g.CH;
   const int n_groups = (R + CH - 1) / CH;
   const int64_t n_tiles = ds.n_pad / v2::kTileM;
   const int base = p->num_sms / gcd_int2(n_groups, p->num_sms);
@@ -481,11 +539,11 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
 
   auto up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
-  const size_t b1_bytes = (size_t)n_groups * 256 * v2::kKA * 2;
+  const size_t b1_bytes = (size_t)n_groups * CH * HP * g.KROW * 2;
   const size_t w2_bytes = (size_t)n_groups * CH * 3 * ON * 64 * 2;
   const size_t bias_bytes = (size_t)n_groups * CH * ON * sizeof(float);
   const size_t part_bytes = (size_t)n_chunks * R * (sizeof(double) + 2 * sizeof(int32_t));
-  int rc = ensure_workspace(p, up(b1_bytes) + up(w2_bytes) + up(bias_bytes) + up(part_bytes));
+  rc = ensure_workspace(p, up(b1_bytes) + up(w2_bytes) + up(bias_bytes) + up(part_bytes));
   if (rc) return rc;
   uint8_t* ws = reinterpret_cast<uint8_t*>(p->ws);
   __nv_bfloat16* b1img = reinterpret_cast<__nv_bfloat16*>(ws);
@@ -495,21 +553,19 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   int32_t* partNc = reinterpret_cast<int32_t*>(partL + (size_t)n_chunks * R);
   int32_t* partSq = partNc + (size_t)n_chunks * R;
 
-  tc2_pack_kernel<<<n_groups * CH, 256, 0, st>>>(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, ON, CH, b1img, w2img, bias2);
+  tc2_pack_kernel<<<n_groups * CH, 256, 0, st>>>(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, ON, CH, DKC, g.KROW, b1img, w2img, bias2);
   SAPT_CHECK_LAUNCH();
   CUtensorMap mb1, mw2;
-  rc = tc_make_map_2d(&mb1, b1img, v2::kKA, (uint64_t)n_groups * 256, 256);
+  rc = tc_make_map_2d(&mb1, b1img, (uint64_t)g.KROW, (uint64_t)n_groups * CH * HP, (uint32_t)(CH * HP));
   if (rc) return rc;
-  rc = tc_make_map_2d(&mw2, w2img, 64, (uint64_t)n_groups * CH * 3 * ON, (uint32_t)((ON == 16 ? 4 : 2) * 3 * ON));
+  rc = tc_make_map_2d(&mw2, w2img, 64, (uint64_t)n_groups * CH * 3 * ON, (uint32_t)(g.W2BOX * 3 * ON));
   if (rc) return rc;
   Tc2Params a{};
   a.y = ds.y; a.n_pad = ds.n_pad; a.bias2 = bias2; a.n_rows = n_rows; a.R = R; a.O = p->O;
   a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.partL = partL; a.partNc = partNc; a.partSq = partSq;
   dim3 grid((unsigned)n_chunks, (unsigned)n_groups);
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(ds.tmap);
-  if (HP == 16) rc = launch_tc2<16, 16, 4>(ma, mb1, mw2, a, grid, st);
-  else if (ON == 16) rc = launch_tc2<32, 16, 4>(ma, mb1, mw2, a, grid, st);
-  else rc = launch_tc2<32, 32, 3>(ma, mb1, mw2, a, grid, st);
+  rc = tc2_dispatch(HP, ON, DKC, [&](auto h, auto o, auto k) { return launch_tc2<h(), o(), k()>(ma, mb1, mw2, a, grid, st); });
   if (rc) return rc;
   return launch_loglik_finalize(partL, partNc, partSq, (int)n_chunks, R, rows, n_rows, L, nc, sq, st);
 }
