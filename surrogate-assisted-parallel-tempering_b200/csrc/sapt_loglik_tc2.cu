@@ -42,7 +42,8 @@ constexpr int kTileM = 128;
 constexpr int kEpiWarps = 16;           // four per TMEM lane quarter
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 // The SMSP arbiter favours the highest warp id: the two single-thread roles that feed everyone else
-// (TMA producer, MMA issuer) sit above the epilogue warps so they are never starved by them.
+// (TMA producer, MMA issuer) sit above the epilogue warps so they are never starved by them. (Folding the
+// producer into the MMA thread was measured 2 % slower and frees no registers: warps are allocated in fours.)
 constexpr int kTmaWarp = kEpiWarps;
 constexpr int kMmaWarp = kEpiWarps + 1;
 constexpr int kSmemLimit = 224 * 1024;
@@ -87,7 +88,8 @@ struct Tc2Params {
   const int32_t* y; int64_t n_pad;
   const float* bias2;            // [pos][ON] log2(e) * B2
   const int32_t* n_rows; int R;
-  int O; int tiles_per_chunk; int64_t n_tiles;
+  int O; int fold_bias;          // fold_bias: H < HP, the output bias is row H of the W2 image
+  int tiles_per_chunk; int64_t n_tiles;
   double* partL; int32_t* partNc; int32_t* partSq;
 };
 
@@ -133,11 +135,12 @@ __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* r
     const int o = i / KW, h = i - o * KW;
     __nv_bfloat16 p[3] = {zero, zero, zero};
     if (o < O && h < H) split3(-kLog2e * src[D * H + h * O + o], p[0], p[1], p[2]);
+    else if (o < O && h == H && H < HP) split3(2.0f * kLog2e * src[D * H + H * O + H + o], p[0], p[1], p[2]);   // bias x 1/sigmoid(0)
     wrow0[(int64_t)o * KW + h] = p[0];
     wrow0[(int64_t)(ON + o) * KW + h] = p[1];
     wrow0[(int64_t)(2 * ON + o) * KW + h] = p[2];
   }
-  for (int i = threadIdx.x; i < ON; i += blockDim.x) bb[i] = (i < O) ? kLog2e * src[D * H + H * O + H + i] : 0.f;
+  for (int i = threadIdx.x; i < ON; i += blockDim.x) bb[i] = (i < O) ? kLog2e * src[D * H + H * O + H + i] : 0.f;   // used when H == HP (no spare hidden slot)
 }
 
 // four sigmoids with one reciprocal:  s_i = 1 / a_i,  a_i = 1 + 2^min(t_i, 30)  (clamp: |error| < 1e-9,
@@ -149,6 +152,35 @@ __device__ __forceinline__ void sigmoid4(float t0, float t1, float t2, float t3,
   const float a3 = 1.0f + ex2_approx(fminf(t3, 30.0f));
   const float ab = a0 * a1, cd = a2 * a3;
   const float r = rcp_approx(ab * cd);
+  const float rab = r * cd, rcd = r * ab;
+  s0 = rab * a1; s1 = rab * a0; s2 = rcd * a3; s3 = rcd * a2;
+}
+
+// same with the clamp limit in a register (see phase 1)
+__device__ __forceinline__ void sigmoid4_lim(float t0, float t1, float t2, float t3, float lim, float& s0, float& s1, float& s2,
+                                             float& s3) {
+  const float a0 = 1.0f + ex2_approx(fminf(t0, lim));
+  const float a1 = 1.0f + ex2_approx(fminf(t1, lim));
+  const float a2 = 1.0f + ex2_approx(fminf(t2, lim));
+  const float a3 = 1.0f + ex2_approx(fminf(t3, lim));
+  const float ab = a0 * a1, cd = a2 * a3;
+  const float r = rcp_approx(ab * cd);
+  const float rab = r * cd, rcd = r * ab;
+  s0 = rab * a1; s1 = rab * a0; s2 = rcd * a3; s3 = rcd * a2;
+}
+#ifndef SAPT_P1_CHAIN
+#define SAPT_P1_CHAIN 2   // quads per ordered group in phase 1 (0: let ptxas schedule freely)
+#endif
+
+// same, times a common factor: s_i = scale / a_i (the factor rides on the shared reciprocal)
+__device__ __forceinline__ void sigmoid4_scaled(float t0, float t1, float t2, float t3, float scale, float& s0, float& s1, float& s2,
+                                                float& s3) {
+  const float a0 = 1.0f + ex2_approx(fminf(t0, 30.0f));
+  const float a1 = 1.0f + ex2_approx(fminf(t1, 30.0f));
+  const float a2 = 1.0f + ex2_approx(fminf(t2, 30.0f));
+  const float a3 = 1.0f + ex2_approx(fminf(t3, 30.0f));
+  const float ab = a0 * a1, cd = a2 * a3;
+  const float r = rcp_approx(ab * cd) * scale;
   const float rab = r * cd, rcd = r * ab;
   s0 = rab * a1; s1 = rab * a0; s2 = rcd * a3; s3 = rcd * a2;
 }
@@ -330,11 +362,19 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(d1_empty);  // D1 is in registers: the next MMA-1 may overwrite it
+      // ptxas would hoist all HW MUFU.EX2 to the front: a warp then monopolises the SFU queue for ~40 x 8 cycles
+      // and leaves it idle for the ~200 instructions that follow, and so do its three SMSP neighbours. Chaining
+      // the clamp limit of quad group k+1 to a result of group k (times zero: one FFMA per group, not foldable
+      // under IEEE rules) keeps the groups in order, so SFU work and FP32/integer work alternate finely.
+      float lim = 30.0f;
 #pragma unroll
       for (int j = 0; j < HW / 4; ++j) {
         float h0, h1, h2, h3;
-        sigmoid4(__uint_as_float(zr[4 * j]), __uint_as_float(zr[4 * j + 1]), __uint_as_float(zr[4 * j + 2]),
-                 __uint_as_float(zr[4 * j + 3]), h0, h1, h2, h3);
+        sigmoid4_lim(__uint_as_float(zr[4 * j]), __uint_as_float(zr[4 * j + 1]), __uint_as_float(zr[4 * j + 2]),
+                     __uint_as_float(zr[4 * j + 3]), lim, h0, h1, h2, h3);
+#if SAPT_P1_CHAIN > 0
+        if (j % SAPT_P1_CHAIN == SAPT_P1_CHAIN - 1) lim = fmaf(h0, 0.0f, 30.0f);
+#endif
         // h1 piece = h truncated to bf16 (one PRMT packs two), h2 piece = the exact, non-negative residual
         // rounded half-up to bf16. The residual is not zero-mean, so MMA-2 also accumulates h2.w2.
         const uint32_t u0 = __float_as_uint(h0), u1 = __float_as_uint(h1), u2 = __float_as_uint(h2), u3 = __float_as_uint(h3);
@@ -387,37 +427,53 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
         }
         if (has_next) publish_hv(u + 1);
         if (!mine) continue;
-        // ---- phase 2: output layer ----
-        const float* bias = sBias + (uu * UC + c) * ON;
-        float tmin = 0.f; int pm = 0; float sum = 0.f, oy = 0.f;
+        // ---- phase 2: output layer (exactly O outputs: quads, then a pair and / or a single one) ----
+        // s is kept as log2(e) * sigmoid. With FOLD the output bias rides in the MMA: hidden slot H is padding whose
+        // activation is sigmoid(0) = 1/2, and its W2 row holds twice the bias (tc2_pack_kernel).
+        float tmin = 3.0e38f; int pm = 0; float sum = 0.f, oy = 0.f;
+        auto phase2 = [&](auto fold_tag) {
+          constexpr bool FOLD = decltype(fold_tag)::value;
+          const float* bias = sBias + (uu * UC + c) * ON;
+          auto tval = [&](int o) {  // o is a compile-time constant after unrolling
+            float v;
+            if constexpr (PARTS == 3) v = (__uint_as_float(dr0[o]) + __uint_as_float(dr1[o])) + __uint_as_float(dr2[o]);
+            else v = __uint_as_float(dr0[o]) + __uint_as_float(dr1[o]);
+            if constexpr (!FOLD) v += bias[o];
+            return v;
+          };
+          auto emit = [&](int o, float t, float sv) {
+            if (t < tmin) { tmin = t; pm = o; }
+            sum += ex2_approx(sv);
+            if (o == y) oy = sv;
+          };
+          auto single = [&](int o) {
+            const float t = tval(o);
+            emit(o, t, kLog2e * rcp_approx(1.0f + ex2_approx(fminf(t, 30.0f))));
+          };
 #pragma unroll
-        for (int g = 0; g < ON / 4; ++g) {
-          if (4 * g < O) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + 4 * g);
-            float t[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float bk = (k == 0 ? b.x : k == 1 ? b.y : k == 2 ? b.z : b.w);
-              if constexpr (PARTS == 3)
-                t[k] = (__uint_as_float(dr0[4 * g + k]) + __uint_as_float(dr1[4 * g + k])) + (__uint_as_float(dr2[4 * g + k]) + bk);
-              else
-                t[k] = (__uint_as_float(dr0[4 * g + k]) + __uint_as_float(dr1[4 * g + k])) + bk;
-            }
-            float s[4];
-            sigmoid4(t[0], t[1], t[2], t[3], s[0], s[1], s[2], s[3]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int o = 4 * g + k;
-              if (o < O) {
-                if (o == 0 || t[k] < tmin) { tmin = t[k]; pm = o; }
-                sum += ex2_approx(s[k] * kLog2e);
-                if (o == y) oy = s[k];
+          for (int g = 0; g < ON / 4; ++g) {
+            const int rem = O - 4 * g;   // warp-uniform
+            if (rem >= 4) {
+              const float t0 = tval(4 * g), t1 = tval(4 * g + 1), t2 = tval(4 * g + 2), t3 = tval(4 * g + 3);
+              float s0, s1, s2, s3;
+              sigmoid4_scaled(t0, t1, t2, t3, kLog2e, s0, s1, s2, s3);
+              emit(4 * g, t0, s0); emit(4 * g + 1, t1, s1); emit(4 * g + 2, t2, s2); emit(4 * g + 3, t3, s3);
+            } else if (rem > 0) {
+              if (rem & 2) {
+                const float t0 = tval(4 * g), t1 = tval(4 * g + 1);
+                const float a0 = 1.0f + ex2_approx(fminf(t0, 30.0f)), a1 = 1.0f + ex2_approx(fminf(t1, 30.0f));
+                const float r = rcp_approx(a0 * a1) * kLog2e;
+                emit(4 * g, t0, r * a1); emit(4 * g + 1, t1, r * a0);
+                if (rem & 1) single(4 * g + 2);
+              } else {
+                single(4 * g);
               }
             }
           }
-        }
+        };
+        if (p.fold_bias) phase2(std::true_type{}); else phase2(std::false_type{});
         if (y >= 0) {
-          accL[uu] += (double)(oy - kLn2 * lg2_approx(sum));
+          accL[uu] += (double)(kLn2 * (oy - lg2_approx(sum)));
           accNc[uu] += (pm == y);
           const int d = pm - y;
           accSq[uu] += d * d;
@@ -561,7 +617,7 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   rc = tc_make_map_2d(&mw2, w2img, 64, (uint64_t)n_groups * CH * 3 * ON, (uint32_t)(g.W2BOX * 3 * ON));
   if (rc) return rc;
   Tc2Params a{};
-  a.y = ds.y; a.n_pad = ds.n_pad; a.bias2 = bias2; a.n_rows = n_rows; a.R = R; a.O = p->O;
+  a.y = ds.y; a.n_pad = ds.n_pad; a.bias2 = bias2; a.n_rows = n_rows; a.R = R; a.O = p->O; a.fold_bias = (p->H < HP) ? 1 : 0;
   a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.partL = partL; a.partNc = partNc; a.partSq = partSq;
   dim3 grid((unsigned)n_chunks, (unsigned)n_groups);
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(ds.tmap);
