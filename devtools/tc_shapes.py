@@ -6,7 +6,7 @@ from sapt_b200 import _lib
 from sapt_b200.problem import Problem
 
 rs = np.random.RandomState(0)
-for (D, H, O) in ((9, 12, 2), (16, 30, 10), (34, 50, 2), (54, 64, 7), (64, 64, 18), (36, 25, 18), (4, 12, 3)):
+for (D, H, O) in ((9, 12, 2), (16, 30, 10), (34, 50, 2), (54, 64, 7), (64, 64, 18), (36, 25, 18), (4, 12, 3), (6, 25, 18), (8, 16, 4), (12, 16, 2), (10, 20, 3), (11, 50, 10), (20, 50, 2), (34, 15, 2), (9, 8, 2), (4, 8, 3)):
     n, R = 262144, 512
     x = rs.standard_normal((n, D)).astype(np.float32); y = rs.randint(0, O, n).astype(np.int32)
     P = D * H + H * O + H + O

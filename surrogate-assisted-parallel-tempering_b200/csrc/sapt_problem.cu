@@ -143,7 +143,9 @@ extern "C" int sapt_loglik(sapt_problem_t* p, int which, const float* theta, int
   SAPT_REQUIRE(theta && L && R >= 0 && ld_theta >= p->P, "theta / outputs");
   SAPT_REQUIRE((rows == nullptr) == (n_rows == nullptr), "rows and n_rows come together");
   if (path == SAPT_PATH_TC && !p->tc_ok) { set_error("tcgen05 path unavailable for topology %d-%d-%d on this device", p->D, p->H, p->O); return SAPT_ERR_UNSUPPORTED; }
-  const bool tc = (path == SAPT_PATH_TC) || (path == SAPT_PATH_AUTO && p->tc_ok);
+  // AUTO: below ~220 multiply-adds per evaluation (9-12-2, 8-16-4 ...) the fp32 tiles win (measured crossover:
+  // 8-16-4 fp32 +10 %, 12-16-2 tcgen05 +16 %), above it the tensor-core path is 1.1x-4x faster.
+  const bool tc = (path == SAPT_PATH_TC) || (path == SAPT_PATH_AUTO && p->tc_ok && p->D * p->H + p->H * p->O >= 220);
   if (tc) return launch_loglik_tc(p, which, theta, ld_theta, R, rows, n_rows, L, ncorrect, sqerr, (cudaStream_t)stream);
   return launch_loglik_f32(p, which, theta, ld_theta, R, rows, n_rows, L, ncorrect, sqerr, (cudaStream_t)stream);
 }
