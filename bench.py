@@ -96,7 +96,7 @@ def run_reference(args):
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
                                   sample=f"{cores} processes x {sample_rows} rows per step, reference per-row numpy loop"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -281,12 +281,34 @@ def run_ours(args):
         if res is not None:
             line["accept_rate"] = float(np.mean(res["naccept"]) / max(1, args.steps + n_warm))
             line["exchanges_in_timed_region"] = sum(1 for k in range(args.steps) if (n_warm + k) % W["swap_interval"] == 0)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner on the
+    first communicator), so fd 1 is pointed at stderr for the whole run and the result goes to the saved fd."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
