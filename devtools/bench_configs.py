@@ -38,8 +38,19 @@ if "c4" in which:
     eng = PTEngine(prob, assign_temperatures(R, 4.0), cfg)
     eng.initialize(np.random.RandomState(3).randn(prob.P) * 0.5)
     ms, eps = timed_steps(eng, 2, 4)
+    def time_op(fn, n=3):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n): fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+    th = eng.theta if hasattr(eng, "theta") else torch.randn(R, prob.P, device="cuda") * 0.3
+    ms_ll = time_op(lambda: prob.loglik(th, 0))
+    ms_lg = time_op(lambda: prob.langevin(th, 0.5, mode=1, batch_scale=1.0 / N))
     out["C4 covtype-shape 54-64-7, 581012 rows, 256 chains, Langevin(batch, mean) p=0.5"] = dict(
-        ms_per_step=ms, loglik_evals_per_s=eps, samples_per_s=R / (ms * 1e-3), path="fp32 (D=54 outside the tcgen05 envelope)")
+        ms_per_step=ms, loglik_evals_per_s=eps, samples_per_s=R / (ms * 1e-3), path="auto (tcgen05)",
+        loglik_train_256_chains_ms=ms_ll, langevin_batch_256_chains_ms=ms_lg)
     print(json.dumps(out), flush=True)
     del eng, prob
     torch.cuda.empty_cache()
@@ -55,7 +66,7 @@ if "c5" in which:
         eng.initialize(np.random.RandomState(3).randn(prob.P) * 0.5)
         ms, eps = timed_steps(eng, 10, 8)
         out[f"C5 chess-shape 6-25-18, 16833+11223 rows, {R} chains, surrogate_prob 0.5 (fixed MLP P-200-50-1)"] = dict(
-            ms_per_step=ms, loglik_evals_per_s=eps, samples_per_s=R / (ms * 1e-3), path="fp32 (O=18 outside the tcgen05 envelope)")
+            ms_per_step=ms, loglik_evals_per_s=eps, samples_per_s=R / (ms * 1e-3), path="auto (tcgen05)")
         print(json.dumps(out), flush=True)
         del eng, prob
         torch.cuda.empty_cache()

@@ -197,7 +197,7 @@ def _load_threaded(variant: str):
     ref_loader._install_stubs()
     import importlib.util
     real_mp = sys.modules.get("multiprocessing")
-    sys.modules["multiprocessing"] = _fake_multiprocessing(auto_reset=(variant == "LG"))
+    sys.modules["multiprocessing"] = _fake_multiprocessing(auto_reset=(variant in ("LG", "LS")))
     try:
         path = os.path.join(ref_loader.REFERENCE_ROOT, ref_loader.VARIANTS[variant])
         spec = importlib.util.spec_from_file_location(f"_sapt_reference_threaded_{variant}", path)
@@ -493,7 +493,131 @@ def main():
     make_run("lg", "ions", "ions", R=3, samples_per_chain=24, swap_interval=100000, surrogate_interval=6,
              surrogate_prob=0.5, maxtemp=2.0, use_langevin=True, learn_rate=0.01, surrogate_topology=3,
              seed=34, n_train=48, n_test=24)
+    make_run_local("cancer", "cancer", R=4, samples_per_chain=60, swap_interval=7, surrogate_interval=12,
+                   surrogate_prob=0.4, maxtemp=3.0, seed=36, n_train=80, n_test=30)
 
 
 if __name__ == "__main__":
     main()
+
+
+# ----------------------------------------------------------------------------------------
+# N4: local-surrogate fork (LS). Same thread/stream harness; the fork's own coordinator is racy in the same
+# way as LG's (LS:1108 waits on a stale index), so the chains are driven by a barrier that sweeps the fork's
+# own swap_procedure, as for LG. The per-chain 4-10-1 networks train inside the reference code (numpy only).
+# ----------------------------------------------------------------------------------------
+def _run_ls_barrier(pt):
+    R = pt.num_chains
+    for ch in pt.chains:
+        ch.start()
+    S = pt.NumSamples
+    for i in range(S - 1):
+        if i % pt.swap_interval == 0:
+            for k in range(R):
+                pt.wait_chain[k].wait()
+            for k in range(R - 1):
+                res = pt.swap_procedure(pt.parameter_queue[k], pt.parameter_queue[k + 1])
+                assert res is not None
+                p1, p2 = res
+                pt.parameter_queue[k].put(p1); pt.parameter_queue[k + 1].put(p2)
+            for k in range(R):
+                pt.event[k].set()
+    for ch in pt.chains:
+        ch.join()
+
+
+def make_run_local(tag: str, problem: str, R: int, samples_per_chain: int, swap_interval: int, surrogate_interval: int,
+                   surrogate_prob: float, maxtemp: float, seed: int, n_train: int, n_test: int):
+    mod = _load_threaded("LS")
+    tr, te, topo = load_problem(problem)
+    tr, te = tr[:n_train].copy(), te[:n_test].copy()
+    P = so.num_param(topo)
+    rec = _Recorder(seed)
+    mod.np = _NpProxy(rec)
+    mod.random = types.SimpleNamespace(uniform=rec.py_uniform)
+    tmp = tempfile.mkdtemp(prefix="sapt_golden_")
+    for sub in ("posterior/pos_w", "posterior/pos_likelihood", "posterior/surg_likelihood", "posterior/accept_list",
+                "predictions", "surrogate", "surrogate/learnsurrogate_data"):
+        os.makedirs(os.path.join(tmp, sub), exist_ok=True)
+    train_log = []   # (chain, init flag, windows/limit, rmse, weights after)
+    orig_train = mod.surrogate.train
+
+    def logged_train(self, model_signature, temperature, X, Y):
+        rmse = orig_train(self, model_signature, temperature, X, Y)
+        k = rec.index_of.get(threading.current_thread(), -1)
+        f = self.fnn
+        train_log.append((k, bool(model_signature), np.column_stack((X, Y)).copy(), float(rmse),
+                          np.concatenate([f.W1.ravel(), f.W2.ravel(), f.B1.ravel(), f.B2.ravel()]).copy()))
+        return rmse
+
+    mod.surrogate.train = logged_train
+    NumSample = samples_per_chain * R
+    with contextlib.redirect_stdout(io.StringIO()):
+        pt = mod.ParallelTempering(True, False, 0.5, False, tr, te, topo, R, maxtemp, NumSample, swap_interval,
+                                   surrogate_interval, surrogate_prob, tmp, tmp)
+        pt.initialize_chains(0.25)
+    for k, ch in enumerate(pt.chains):
+        rec.index_of[ch] = k
+    w0 = rec.log[(-1, "randn")][-1][1].copy()
+    temps = np.array(pt.temperatures, dtype=np.float64)
+    saved = {}
+
+    def savetxt(fname, arr, *a, **k):
+        if not hasattr(fname, "write"):
+            saved[os.path.relpath(str(fname), tmp)] = np.array(arr, dtype=np.float64)
+        np.savetxt(fname, arr, *a, **k)
+
+    mod.np.savetxt = savetxt
+    import warnings
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _run_ls_barrier(pt)
+    S = samples_per_chain
+    z1 = np.zeros((S - 1, R, P)); ku = np.zeros((S - 1, R)); u = np.zeros((S - 1, R))
+    net_init = np.zeros((R, 61))
+    for k in range(R):
+        normals = [v for (t, v) in rec.log[(k, "normal")]]
+        pys = [v for (t, v) in rec.log[(k, "py")]]
+        assert len(normals) == S - 1 and len(pys) == 2 * (S - 1), (len(normals), len(pys))
+        z1[:, k] = np.array(normals)
+        ku[:, k] = np.array(pys[0::2]).reshape(-1); u[:, k] = np.array(pys[1::2]).reshape(-1)
+        # randn log of a chain: w_proposal (LS:473), the classifier's create_network (4 draws, overwritten by
+        # decode), then the local network's create_network at the first training: W1, B1, W2, B2
+        rl = [v for (t, v) in rec.log[(k, "randn")]]
+        assert [len(v) for v in rl[-4:]] == [40, 10, 10, 1], [len(v) for v in rl]
+        net_init[k] = np.concatenate(rl[-4:])
+    main_u = [v for (t, v) in rec.log.get((-1, "uniform"), [])]
+    swap_u = np.array(main_u, dtype=np.float64).reshape(-1, R - 1)
+    traces = {}
+    for k in range(R):
+        tstr = str(pt.temperatures[k])
+        traces.setdefault("rmse_test", []).append(saved[f"predictions/rmse_test_chain_{tstr}.txt"])
+        traces.setdefault("rmse_train", []).append(saved[f"predictions/rmse_train_chain_{tstr}.txt"])
+        traces.setdefault("acc_test", []).append(saved[f"predictions/acc_test_chain_{tstr}.txt"])
+        traces.setdefault("acc_train", []).append(saved[f"predictions/acc_train_chain_{tstr}.txt"])
+        traces.setdefault("surg_likeh_list", []).append(saved[f"posterior/surg_likelihood/chain_{tstr}.txt"])
+        traces.setdefault("likeh_list", []).append(saved[f"posterior/pos_likelihood/chain_{tstr}.txt"])
+        traces.setdefault("accept_list", []).append(saved[f"posterior/accept_list/chain_{tstr}.txt"])
+        traces.setdefault("accept_ratio", []).append(saved[f"posterior/accept_list/chain_{tstr}_accept.txt"])
+    out = {f"trace_{k}": np.array(v) for k, v in traces.items()}
+    # trainer log, ordered (call number, chain)
+    n_calls = len(train_log) // R
+    tl = sorted(range(len(train_log)), key=lambda j: (sum(1 for q in train_log[:j] if q[0] == train_log[j][0]), train_log[j][0]))
+    for pos, j in enumerate(tl):
+        k, init, data, rmse, wts = train_log[j]
+        c = pos // R
+        assert k == pos % R
+        out[f"ls_train{c}_data_{k}"] = data
+        out[f"ls_train{c}_weights_{k}"] = wts
+        out[f"ls_train{c}_rmse_{k}"] = np.array(rmse)
+        out[f"ls_train{c}_init_{k}"] = np.array(init)
+    out.update(train=tr, test=te, topology=np.array(topo), temperatures=temps, w0=w0, samples=np.array(S),
+               swap_interval=np.array(swap_interval), surrogate_interval=np.array(surrogate_interval),
+               surrogate_prob=np.array(surrogate_prob), swap_u=swap_u, num_swap=np.array(pt.num_swap),
+               total_swap_proposals=np.array(pt.total_swap_proposals), n_train_calls=np.array(n_calls),
+               z1=z1, ku=ku, u=u, net_init=net_init)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"run_ls_{tag}.npz"), **out)
+    acc = [float(a[0]) if np.ndim(a) else float(a) for a in traces["accept_ratio"]]
+    sur_steps = int(np.sum(~np.isnan(np.array(traces["surg_likeh_list"])[:, 1:, 1])))
+    print(f"run_ls_{tag}: R={R} S={S} swaps={pt.num_swap}/{pt.total_swap_proposals} train_calls={n_calls} "
+          f"surrogate_steps={sur_steps} accept%={np.round(acc, 1)}")

@@ -660,3 +660,183 @@ def run_pt(variant: str, traindata, testdata, topology, temperatures, w0, sample
                 total_swap_proposals=total_swap_proposals, surr_batches=surr_batches,
                 likelihood=likelihood, likelihood_copy=likelihood_copy, prior_current=prior_current,
                 min_y=surrogate.min_y, max_y=surrogate.max_y, signature=surrogate.signature)
+
+
+# --------------------------------------------------------------------------------------
+# N4  local-surrogate fork (LS = localsurrogates/surrogate_pt_classifier_rw_localsurrogate.py)
+# --------------------------------------------------------------------------------------
+# Every replica owns a 4 -> 10 -> 1 sigmoid MLP that predicts the next tempered likelihood from the last four
+# entries of surg_likeh_list[:, 2] (lag-2 windows of five, "Takens embedding"), retrained online for 200 epochs
+# at every surrogate interval. Quirks kept on purpose (they define the reference's traces):
+#   * BackwardPass one-hot encodes int(desired) (LS:90-93): the regression target y/limit lies in [0, 0.5], so the
+#     network is always trained towards 1.0 and a target >= 1 would raise IndexError in the reference;
+#   * limit = 2 * min(y) is fixed at the first training (LS:791) and later windows are scaled by the same value;
+#   * the window fed to predict() is rows i-4 .. i-1, i.e. it skips the newest entry (LS:592);
+#   * the prediction is used as the tempered likelihood directly: no 1/T, no moving-average blend (LS:598-602);
+#   * an ACCEPTED surrogate proposal leaves `likelihood` a 1-element array and the reference then dies in
+#     np.concatenate at the next exchange (LS:757); the restatement keeps the scalar and goes on.
+
+LS_BLOCK = 5        # LS:548
+LS_LAG = 2          # LS:779
+LS_HIDDEN = 10      # LS:243
+LS_LRATE = 0.1      # LS:262
+LS_EPOCHS = 200     # LS:253
+
+
+def takens_windows(y: np.ndarray, blocksize: int = LS_BLOCK, lag: int = LS_LAG):
+    """LS:773-787. Returns (windows [nb, blocksize], the trimmed series)."""
+    y = np.asarray(y, dtype=np.float64)
+    n = y.shape[0] % blocksize
+    y = y[n:]
+    nb = int((y.shape[0] - blocksize) / lag)
+    v = np.zeros((nb, blocksize))
+    for b in range(nb):
+        v[b, :] = y[b * lag: b * lag + blocksize]
+    return v, y
+
+
+def local_net_init(z: np.ndarray, n_in: int = LS_BLOCK - 1, hidden: int = LS_HIDDEN) -> Dict[str, np.ndarray]:
+    """create_network (LS:57-70) from n_in*hidden + hidden + hidden + 1 standard normals in the order the
+    reference draws them: W1, B1, W2, B2."""
+    z = np.asarray(z, dtype=np.float64).reshape(-1)
+    a, b, c = n_in * hidden, n_in * hidden + hidden, n_in * hidden + 2 * hidden
+    return dict(W1=z[:a].reshape(n_in, hidden) / np.sqrt(n_in), B1=z[a:b].reshape(1, hidden) / np.sqrt(hidden),
+                W2=z[b:c].reshape(hidden, 1) / np.sqrt(hidden), B2=z[c:c + 1].reshape(1, 1) / np.sqrt(hidden))
+
+
+def local_net_forward(x: np.ndarray, net: Dict[str, np.ndarray]):
+    """ForwardPass (LS:80-87) -> (hidout [1,h], out [1,1])."""
+    hid = sigmoid(np.asarray(x, dtype=np.float64).reshape(1, -1) @ net["W1"] - net["B1"])
+    out = sigmoid(hid @ net["W2"] - net["B2"])
+    return hid, out
+
+
+def local_net_train(data: np.ndarray, net: Dict[str, np.ndarray], lrate: float = LS_LRATE, epochs: int = LS_EPOCHS) -> float:
+    """backprop_train (LS:152-177) + BackwardPass (LS:90-101), in place. The desired output is the one-hot of
+    int(target) over ONE output neuron, i.e. 1.0 (IndexError in the reference if target >= 1)."""
+    data = np.asarray(data, dtype=np.float64)
+    n_in = net["W1"].shape[0]
+    sse = 0.0
+    for _ in range(epochs):
+        for row in data:
+            x = row[:n_in].reshape(1, n_in)
+            hid, out = local_net_forward(x, net)
+            out_delta = (1.0 - out) * (out * (1 - out))
+            hid_delta = (out_delta @ net["W2"].T) * (hid * (1 - hid))
+            net["W2"] += hid.T @ (out_delta * lrate)
+            net["B2"] += -1 * lrate * out_delta
+            net["W1"] += x.T @ (hid_delta * lrate)
+            net["B1"] += -1 * lrate * hid_delta
+            sse += float(np.sum(np.square(out - row[n_in:])) / 1.0)   # sampleEr against the raw target (LS:75-78)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return float(np.sqrt(np.float64(sse) / len(data) * 1))
+
+
+def run_pt_local(traindata, testdata, topology, temperatures, w0, samples: int, swap_interval: int,
+                 surrogate_interval: int, surrogate_prob: float, streams: Streams, net_init: np.ndarray):
+    """R x ptReplica.run of the local-surrogate fork (LS:447-836) in lock-step with a barrier coordinator that
+    sweeps swap_procedure (LS:1056-1084) over k = 0..R-2 at every i % swap_interval == 0 (the fork's own
+    run_chains is racy in the same way as LG's, LS:1108). `net_init[r]` = the 61 standard normals chain r draws
+    in create_network at its first training."""
+    traindata = np.asarray(traindata, dtype=np.float64)
+    testdata = np.asarray(testdata, dtype=np.float64)
+    R = len(temperatures)
+    P = num_param(topology)
+    d = topology[0]
+    y_train = traindata[:, d]
+    y_test = testdata[:, d]
+    T = np.asarray(temperatures, dtype=np.float64)
+    w = np.tile(np.asarray(w0, dtype=np.float64), (R, 1))
+    lhood_list = np.zeros((R, samples))
+    rmse_train = np.zeros((R, samples)); rmse_test = np.zeros((R, samples))
+    acc_train = np.zeros((R, samples)); acc_test = np.zeros((R, samples))
+    likeh_list = np.zeros((R, samples, 2)); likeh_list[:, 0, :] = -100
+    surg = np.zeros((R, samples, 3))
+    accept_list = np.zeros((R, samples))
+    is_surrogate_step = np.zeros((R, samples), dtype=bool)
+    accepted = np.zeros((R, samples), dtype=bool)
+    naccept = np.zeros(R, dtype=np.int64)
+    likelihood = np.zeros(R); likelihood_copy = np.zeros(R); prior_current = np.zeros(R)
+    rmsetrain = np.zeros(R); rmsetest = np.zeros(R)
+    pred_train = [None] * R; pred_test = [None] * R
+    likl_without_temp = np.zeros(R)
+    for r in range(R):
+        prior_current[r] = prior_likelihood(SIGMA_SQUARED, 0, 0, w[r], topology)
+        lik, pred_train[r], rmsetrain[r], _ = likelihood_func(traindata, w[r], topology, T[r])
+        _, pred_test[r], rmsetest[r], lwt = likelihood_func(testdata, w[r], topology, T[r])
+        likelihood[r] = lik; likelihood_copy[r] = lik; likl_without_temp[r] = lwt   # LS:500-501
+    nets: List[Optional[Dict[str, np.ndarray]]] = [None] * R
+    limit = np.zeros(R)
+    train_rmse: List[np.ndarray] = []
+    swap_decisions: List[np.ndarray] = []
+    num_swap = 0; total_swap_proposals = 0; sweep = 0
+    for i in range(samples - 1):
+        for r in range(R):
+            w_proposal = w[r] + STEP_W * streams.z1[i, r]
+            ku = streams.ku[i, r]
+            if ku < surrogate_prob and i >= surrogate_interval + 1:                      # LS:588
+                is_true = False
+                x = surg[r, i - (LS_BLOCK - 1):i, 2] / limit[r]                           # LS:592
+                _, out = local_net_forward(x, nets[r])
+                likelihood_proposal = float(out[0, 0] * limit[r])                          # LS:598
+                lt, pred_train[r], rmsetrain[r], likl_without_temp[r] = likelihood_func(traindata, w_proposal, topology, T[r])
+                surg[r, i + 1, 0] = lt
+                surg[r, i + 1, 1] = likelihood_proposal
+                surg[r, i + 1, 2] = np.mean(x) * limit[r]                                 # LS:617
+            else:
+                is_true = True
+                surg[r, i + 1, 1] = np.nan
+                likelihood_proposal, pred_train[r], rmsetrain[r], likl_without_temp[r] = likelihood_func(
+                    traindata, w_proposal, topology, T[r])
+                _, pred_test[r], rmsetest[r], _ = likelihood_func(testdata, w_proposal, topology, T[r])   # LS:630
+                surg[r, i + 1, 0] = likelihood_proposal
+                surg[r, i + 1, 2] = likelihood_proposal
+            is_surrogate_step[r, i + 1] = not is_true
+            prior_prop = prior_likelihood(SIGMA_SQUARED, 0, 0, w_proposal, topology)
+            mh = mh_probability(likelihood_proposal - likelihood_copy[r], prior_prop - prior_current[r])
+            accept_list[r, i + 1] = naccept[r]
+            likeh_list[r, i + 1, 0] = likl_without_temp[r]
+            if streams.u[i, r] < mh:
+                accepted[r, i + 1] = True
+                naccept[r] += 1
+                likelihood[r] = likelihood_proposal; likelihood_copy[r] = likelihood_proposal
+                prior_current[r] = prior_prop
+                w[r] = w_proposal
+                if is_true:
+                    lhood_list[r, i + 1] = likelihood[r] * T[r]
+                    rmse_train[r, i + 1] = rmsetrain[r]; rmse_test[r, i + 1] = rmsetest[r]
+                    acc_train[r, i + 1] = accuracy(pred_train[r], y_train)
+                    acc_test[r, i + 1] = accuracy(pred_test[r], y_test)
+                else:
+                    lhood_list[r, i + 1] = rmse_train[r, i + 1] = rmse_test[r, i + 1] = np.inf
+                    acc_train[r, i + 1] = acc_test[r, i + 1] = np.inf
+            else:
+                if is_true:
+                    lhood_list[r, i + 1] = likelihood_proposal * T[r]
+                    rmse_train[r, i + 1] = rmse_train[r, i]; rmse_test[r, i + 1] = rmse_test[r, i]
+                    acc_train[r, i + 1] = acc_train[r, i]; acc_test[r, i + 1] = acc_test[r, i]
+                else:
+                    lhood_list[r, i + 1] = rmse_train[r, i + 1] = rmse_test[r, i + 1] = np.inf
+                    acc_train[r, i + 1] = acc_test[r, i + 1] = np.inf
+        if i % swap_interval == 0 and R > 1:                                              # LS:756-768: tempered L posted
+            src, sw = swap_sweep(likelihood.copy(), streams.swap_u[sweep])
+            sweep += 1
+            num_swap += int(sw.sum()); total_swap_proposals += R - 1
+            w = w[src].copy()                                                             # only w is taken back (LS:765)
+            swap_decisions.append(sw)
+        if i % surrogate_interval == 0 and i != 0:                                        # LS:771
+            rm = np.zeros(R)
+            for r in range(R):
+                if nets[r] is None:
+                    v, ytrim = takens_windows(surg[r, 0:i, 2])
+                    limit[r] = np.amin(ytrim) * 2                                         # LS:791
+                    nets[r] = local_net_init(net_init[r])
+                else:
+                    v, _ = takens_windows(surg[r, i - surrogate_interval:i, 2])
+                rm[r] = local_net_train(v / limit[r], nets[r])
+            train_rmse.append(rm)
+    return dict(lhood_list=lhood_list, rmse_train=rmse_train, rmse_test=rmse_test, acc_train=acc_train, acc_test=acc_test,
+                likeh_list=likeh_list, surg_likeh_list=surg, accept_list=accept_list, naccept=naccept, w_final=w,
+                is_surrogate_step=is_surrogate_step, accepted=accepted, swap_decisions=swap_decisions, num_swap=num_swap,
+                total_swap_proposals=total_swap_proposals, likelihood=likelihood, likelihood_copy=likelihood_copy,
+                prior_current=prior_current, limit=limit, nets=nets, train_rmse=train_rmse)

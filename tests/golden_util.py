@@ -41,3 +41,15 @@ def compare_traces(g, out, rtol, atol, keys=TRACE_KEYS):
         assert np.array_equal(np.isinf(a), np.isinf(b)), k
         m = np.isfinite(a)
         np.testing.assert_allclose(b[m], a[m], rtol=rtol, atol=atol, err_msg=k)
+
+
+LS_TRACE_KEYS = ("rmse_train", "rmse_test", "acc_train", "acc_test", "surg_likeh_list", "likeh_list", "accept_list")
+
+
+def run_local_inputs(g):
+    """kwargs for oracle.run_pt_local / the device engine (variant 'ls') from a run_ls_* fixture."""
+    streams = so.Streams(z1=g["z1"], z2=None, lx2=None, ku=g["ku"], u=g["u"], swap_u=g["swap_u"])
+    return dict(traindata=g["train"], testdata=g["test"], topology=[int(v) for v in g["topology"]],
+                temperatures=g["temperatures"], w0=g["w0"], samples=int(g["samples"]),
+                swap_interval=int(g["swap_interval"]), surrogate_interval=int(g["surrogate_interval"]),
+                surrogate_prob=float(g["surrogate_prob"]), streams=streams, net_init=g["net_init"])

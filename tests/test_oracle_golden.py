@@ -102,3 +102,38 @@ def test_full_run_traces(name):
         np.testing.assert_allclose(out["min_y"], float(g["min_y"]), rtol=1e-13)
     if bool(g["use_langevin"]):
         assert out["langevin_step"].sum() > 0
+
+
+def test_local_surrogate_fork_traces():
+    """N4: oracle.run_pt_local == the local-surrogate fork's ptReplica.run x R (LS:447-836), including the
+    per-chain 4-10-1 networks trained by the reference's own backprop_train."""
+    g = gu.load("run_ls_cancer")
+    out = so.run_pt_local(**gu.run_local_inputs(g))
+    assert np.array_equal(out["accept_list"], g["trace_accept_list"])          # every accept decision
+    gu.compare_traces(g, out, rtol=1e-12, atol=1e-11, keys=gu.LS_TRACE_KEYS)
+    assert out["num_swap"] == int(g["num_swap"])
+    assert out["is_surrogate_step"].sum() > 0
+    R = len(g["temperatures"])
+    nc = int(g["n_train_calls"])
+    assert nc == len(out["train_rmse"]) and nc >= 2
+    for c in range(nc):
+        for k in range(R):
+            np.testing.assert_allclose(out["train_rmse"][c][k], float(g[f"ls_train{c}_rmse_{k}"]), rtol=1e-10)
+    for k in range(R):
+        net = out["nets"][k]
+        w = np.concatenate([net["W1"].ravel(), net["W2"].ravel(), net["B1"].ravel(), net["B2"].ravel()])
+        np.testing.assert_allclose(w, g[f"ls_train{nc - 1}_weights_{k}"], rtol=1e-10, atol=1e-12)
+
+
+def test_local_surrogate_units():
+    """Takens windows and one training call against what the reference's surrogate.train received / produced."""
+    g = gu.load("run_ls_cancer")
+    v, y = so.takens_windows(np.arange(23.0))
+    assert y.shape[0] == 20 and v.shape == (7, 5) and np.array_equal(v[3], np.arange(3.0, 8.0) + 6.0)
+    k = 1
+    data0 = g[f"ls_train0_data_{k}"]
+    net = so.local_net_init(g["net_init"][k])
+    rm = so.local_net_train(data0, net)
+    np.testing.assert_allclose(rm, float(g[f"ls_train0_rmse_{k}"]), rtol=1e-10)
+    w = np.concatenate([net["W1"].ravel(), net["W2"].ravel(), net["B1"].ravel(), net["B2"].ravel()])
+    np.testing.assert_allclose(w, g[f"ls_train0_weights_{k}"], rtol=1e-10, atol=1e-12)
