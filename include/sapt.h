@@ -55,7 +55,8 @@ enum {
   SAPT_STREAM_KU = 3,  /* surrogate coin                   random.uniform    LG:553 */
   SAPT_STREAM_LX2 = 4, /* Langevin coin                    np.random.uniform LG:647 */
   SAPT_STREAM_U = 5,   /* Metropolis-Hastings coin         random.uniform    LG:704 */
-  SAPT_STREAM_SWAP = 6 /* exchange coin                    np.random.uniform RW:888 */
+  SAPT_STREAM_SWAP = 6, /* exchange coin                   np.random.uniform RW:888 */
+  SAPT_STREAM_LS_INIT = 7 /* local-surrogate net init        np.random.randn   LS:62-65 */
 };
 
 /* behaviour switches of the reference's forks (SURVEY.md §2 "variant differences") */
@@ -65,7 +66,8 @@ enum {
   SAPT_F_DENORM_HALF_MIN = 1 << 2, /* surrogate de-normalisation s*minY/2 (LG:325), else s*(maxY-minY)+minY (RV:320) */
   SAPT_F_COMPARE_SURROGATE = 1 << 3, /* also evaluate the true train likelihood on surrogate steps (RV:543-544) */
   SAPT_F_REDRAW_ON_SURROGATE = 1 << 4, /* surrogate branch redraws the proposal from stream Z2 (LG:560) */
-  SAPT_F_RECORD_POS = 1 << 5       /* keep the full pos_w history on the device */
+  SAPT_F_RECORD_POS = 1 << 5,      /* keep the full pos_w history on the device */
+  SAPT_F_LOCAL_SURROGATE = 1 << 6  /* surrogate steps take sapt_local_surrogate_predict's value as is (LS:598,615-617) */
 };
 
 typedef struct sapt_problem sapt_problem_t; /* opaque: topology + device-resident data sets */
@@ -77,9 +79,9 @@ const char* sapt_last_error(void);
  * (bench.py's "gpu_launches" is read from here, not guessed) */
 long long sapt_launch_count(void);
 void sapt_launch_count_reset(void);
-/* sizeof() of sapt_propose_args, sapt_chain_state, sapt_history, sapt_accept_args,
- * sapt_lg_first_args, sapt_fused_args — lets an FFI binding verify its struct mirrors at load time */
-int sapt_struct_sizes(int32_t out[6]);
+/* sizeof() of sapt_propose_args, sapt_chain_state, sapt_history, sapt_accept_args, sapt_lg_first_args,
+ * sapt_fused_args, sapt_local_surrogate — lets an FFI binding verify its struct mirrors at load time */
+int sapt_struct_sizes(int32_t out[7]);
 
 /* ---- data + topology: replaces Network.__init__(Topo, Train, Test, lr) RV:49-60 -------
  * train_host/test_host: row-major float64 [n][D+1], features then the class index as a
@@ -228,6 +230,8 @@ typedef struct {
   /* LG: the first evaluation's tempered likelihood feeds surg[:,0/2] and the window */
   const double* surg_first; /* [R] or NULL */
   const int32_t* step_dev;  /* see sapt_propose_args.step_dev */
+  /* local-surrogate fork (SAPT_F_LOCAL_SURROGATE): outputs of sapt_local_surrogate_predict, [R] each */
+  const double* ls_pred; const double* ls_avg;
 } sapt_accept_args;
 int sapt_mh_accept(const sapt_accept_args* a, void* stream);
 
@@ -290,6 +294,38 @@ int sapt_advance(int32_t* counter, int delta, void* stream);
 int sapt_philox_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* fills u[n] (kind uniform) or z[n] (normals) on the device exactly as the kernels draw them */
 int sapt_philox_fill(uint32_t seed, int kind, int step, int chain, int n, int normal, float* out, void* stream);
+
+/* ---- N4: per-chain "local" surrogate of the fork localsurrogates/surrogate_pt_classifier_rw_localsurrogate.py (LS).
+ * Every chain owns a 4 -> 10 -> 1 sigmoid network (LS:57-101) that predicts its next tempered likelihood from
+ * the last four entries of surg_likeh_list[:, 2] (LS:592-598); it is retrained online at every surrogate
+ * interval on lag-2 windows of five consecutive entries (LS:771-832) for 200 epochs of per-row SGD
+ * (backprop_train LS:152-177). Weight layout per chain: W1[4][10] | W2[10] | B1[10] | B2 (= Network.encode order). */
+#define SAPT_LS_INPUTS 4
+#define SAPT_LS_HIDDEN 10
+#define SAPT_LS_WEIGHTS (SAPT_LS_INPUTS * SAPT_LS_HIDDEN + 2 * SAPT_LS_HIDDEN + 1)
+typedef struct {
+  double* weights;             /* [n_slots][SAPT_LS_WEIGHTS] */
+  double* limit;               /* [n_slots] 2 * min(y), fixed by the first training (LS:791) */
+  const double* surg;          /* history surg_likeh_list [samples][n_slots][3] (sapt_history.surg) */
+  int n_slots;
+  const int32_t* slot_of_row;  /* [R] chains hosted by this rank */
+  int R;
+} sapt_local_surrogate;
+
+/* Trains the networks of the R local chains on history rows [row_lo, row_hi) of column 2: the series is trimmed to
+ * a multiple of five from the front, cut into (len-5)/2 windows with lag 2 and divided by limit (LS:773-797).
+ * first != 0: limit = 2*min(series) and the weights are initialised like create_network (LS:62-65) from
+ * init_inject[slot][61] standard normals (order W1, B1, W2, B2) or Philox stream LS_INIT. The regression target
+ * is what the reference's BackwardPass makes of it: one_hot(int(target)) over one output = 1.0 (LS:90-93).
+ * rmse[slot] (optional) = sqrt(sum of squared errors against the raw targets / windows) (LS:171-173).
+ * Replaces ptReplica.local_surrogatetrainer LS:432-446 + surrogate.train LS:229-262 for all chains at once. */
+int sapt_local_surrogate_train(const sapt_local_surrogate* m, int row_lo, int row_hi, int first, const double* init_inject,
+                               uint32_t seed, double lrate, int epochs, double* rmse, void* stream);
+
+/* For the listed rows (rows/n_rows as in sapt_loglik): x = surg[step-4 .. step-1][slot][2] / limit,
+ * pred[row] = net(x) * limit, avg[row] = mean(x) * limit (surrogate.predict LS:313-325, LS:592-617). */
+int sapt_local_surrogate_predict(const sapt_local_surrogate* m, int step, const int32_t* step_dev, const int32_t* rows,
+                                 const int32_t* n_rows, double* pred, double* avg, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,9 +13,9 @@ LIB_PATH = os.environ.get("SAPT_LIB", os.path.join(_HERE, "libsapt.so"))  # SAPT
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 PATH_AUTO, PATH_F32, PATH_TC = 0, 1, 2
-STREAM_Z1, STREAM_Z2, STREAM_LX1, STREAM_KU, STREAM_LX2, STREAM_U, STREAM_SWAP = range(7)
-F_POST_TEMPERED, F_TAKE_POST_LIK, F_DENORM_HALF_MIN, F_COMPARE_SURROGATE, F_REDRAW_ON_SURROGATE, F_RECORD_POS = (
-    1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5)
+STREAM_Z1, STREAM_Z2, STREAM_LX1, STREAM_KU, STREAM_LX2, STREAM_U, STREAM_SWAP, STREAM_LS_INIT = range(8)
+F_POST_TEMPERED, F_TAKE_POST_LIK, F_DENORM_HALF_MIN, F_COMPARE_SURROGATE, F_REDRAW_ON_SURROGATE, F_RECORD_POS, F_LOCAL_SURROGATE = (
+    1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6)
 
 vp = C.c_void_p
 i32, i64, u32, f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_double
@@ -49,7 +49,8 @@ class AcceptArgs(C.Structure):
                 ("L_train", vp), ("nc_train", vp), ("sq_train", vp), ("L_test", vp), ("nc_test", vp), ("sq_test", vp),
                 ("n_train", i64), ("n_test", i64), ("prior_prop", vp), ("sur_s", vp), ("min_y", f64), ("max_y", f64),
                 ("seed", u32), ("u_inject", vp), ("train_theta", vp), ("train_L", vp), ("train_count", vp),
-                ("train_cap", C.c_int), ("capture", C.c_int), ("surg_first", vp), ("step_dev", vp)]
+                ("train_cap", C.c_int), ("capture", C.c_int), ("surg_first", vp), ("step_dev", vp),
+                ("ls_pred", vp), ("ls_avg", vp)]
 
 
 class LgFirstArgs(C.Structure):
@@ -65,6 +66,13 @@ class FusedArgs(C.Structure):
                 ("use_surrogate", C.c_int), ("surrogate_ready", C.c_int), ("surrogate_prob", f64), ("gate", C.c_int),
                 ("W1", vp), ("b1", vp), ("h1", C.c_int), ("W2", vp), ("b2", vp), ("h2", C.c_int), ("W3", vp), ("b3", vp),
                 ("acc", AcceptArgs), ("n_steps", C.c_int)]
+
+
+class LocalSurrogate(C.Structure):
+    _fields_ = [("weights", vp), ("limit", vp), ("surg", vp), ("n_slots", C.c_int), ("slot_of_row", vp), ("R", C.c_int)]
+
+
+LS_WEIGHTS = 61
 
 
 class SaptError(RuntimeError):
@@ -108,10 +116,12 @@ def lib():
     L.sapt_philox_host.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     L.sapt_philox_fill.argtypes = [u32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.sapt_fused_steps.argtypes = [vp, C.POINTER(FusedArgs), vp]
+    L.sapt_local_surrogate_train.argtypes = [C.POINTER(LocalSurrogate), C.c_int, C.c_int, C.c_int, vp, u32, f64, C.c_int, vp, vp]
+    L.sapt_local_surrogate_predict.argtypes = [C.POINTER(LocalSurrogate), C.c_int, vp, vp, vp, vp, vp, vp]
     L.sapt_struct_sizes.argtypes = [C.POINTER(i32)]
-    sizes = (i32 * 6)()
+    sizes = (i32 * 7)()
     L.sapt_struct_sizes(sizes)
-    mine = [C.sizeof(t) for t in (ProposeArgs, ChainState, History, AcceptArgs, LgFirstArgs, FusedArgs)]
+    mine = [C.sizeof(t) for t in (ProposeArgs, ChainState, History, AcceptArgs, LgFirstArgs, FusedArgs, LocalSurrogate)]
     if list(sizes) != mine:
         raise ImportError(f"struct layout mismatch between include/sapt.h and _lib.py: C={list(sizes)} ctypes={mine}")
     if L.sapt_abi_version() != 1:
@@ -133,4 +143,5 @@ EXPORTS = [
     "sapt_problem_rows", "sapt_problem_tc_supported", "sapt_loglik", "sapt_loglik_host", "sapt_evaluate_proposal",
     "sapt_prior", "sapt_propose", "sapt_fused_steps", "sapt_langevin", "sapt_surrogate_predict", "sapt_mh_accept", "sapt_lg_first_eval",
     "sapt_swap_sweep", "sapt_swap_sweep_dev", "sapt_advance", "sapt_philox_host", "sapt_philox_fill",
+    "sapt_local_surrogate_train", "sapt_local_surrogate_predict",
 ]

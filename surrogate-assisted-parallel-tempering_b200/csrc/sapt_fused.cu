@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kFT) fused_steps_kernel(FusedData d, sapt_fuse
     const bool sur = s_sur != 0;
     MhInputs in;
     in.sur = sur; in.sur_s = 0.f; in.L_train = 0.0; in.nc_train = 0; in.sq_train = 0.0; in.L_test = 0.0; in.nc_test = 0; in.sq_test = 0.0;
-    in.prior_prop = prior_prop; in.has_surg_first = false; in.surg_first = 0.0;
+    in.prior_prop = prior_prop; in.has_surg_first = false; in.surg_first = 0.0; in.ls_pred = 0.0; in.ls_avg = 0.0;
     const bool need_train = !sur || (m.flags & SAPT_F_COMPARE_SURROGATE);
     if (need_train) {
       stage_chain_weights<DP, OP>(pr, sw, d.D, d.H, d.O, d.HP, tid, kFT);

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(128) mh_accept_kernel(sapt_accept_args a) {
     in.L_test = a.n_test > 0 ? a.L_test[row] : 0.0; in.nc_test = a.n_test > 0 ? a.nc_test[row] : 0; in.sq_test = a.n_test > 0 ? a.sq_test[row] : 0.0;
     in.prior_prop = a.prior_prop[row];
     in.has_surg_first = a.surg_first != nullptr; in.surg_first = a.surg_first ? a.surg_first[row] : 0.0;
+    in.ls_pred = a.ls_pred ? a.ls_pred[row] : 0.0; in.ls_avg = a.ls_avg ? a.ls_avg[row] : 0.0;
     int cnt;
     s_accept = mh_decide(a, slot, step_i, in, &cnt) ? 1 : 0;
     s_cnt = cnt;

@@ -16,6 +16,7 @@ struct MhInputs {
   double L_test; int nc_test; double sq_test;
   double prior_prop;
   bool has_surg_first; double surg_first;   // LG: tempered likelihood of the first evaluation
+  double ls_pred, ls_avg;                   // local-surrogate fork: prediction * limit, mean(window) * limit
 };
 
 // returns accept; *cnt_out = index of the training-set row to fill with the proposal (or -1)
@@ -31,7 +32,16 @@ __device__ __forceinline__ bool mh_decide(const sapt_accept_args& a, int slot, i
     double acc_tr = a.st.last_acc_train[slot], acc_te = a.st.last_acc_test[slot];
     double rm_tr_new = 0, rm_te_new = 0, ac_tr_new = 0, ac_te_new = 0;
     int cnt = -1;
-    if (sur) {
+    if (sur && (a.flags & SAPT_F_LOCAL_SURROGATE)) {
+      // LS:598: the network's output times limit IS the (tempered) proposal likelihood: no 1/T, no window blend
+      Lprop = in.ls_pred;
+      double ltrue = 0.0;
+      if (a.flags & SAPT_F_COMPARE_SURROGATE) {                              // LS:607-608
+        ltrue = in.L_train / T;
+        a.st.likl_wo_temp[slot] = in.L_train;
+      }
+      s0 = ltrue; s1 = Lprop; s2 = in.ls_avg;                                // LS:615-617
+    } else if (sur) {
       // RV:319-320 / LG:325: float32 network output times float64 scalars
       const double s = (double)in.sur_s;
       double pred = (a.flags & SAPT_F_DENORM_HALF_MIN) ? (s * a.min_y / 2.0) : (s * (a.max_y - a.min_y) + a.min_y);

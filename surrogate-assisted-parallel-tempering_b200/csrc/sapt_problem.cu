@@ -184,12 +184,13 @@ extern "C" int sapt_evaluate_proposal(sapt_problem_t* p, int which, const float*
 }
 
 // layout self-check for FFI bindings: sizes of the argument structs, in header order
-extern "C" int sapt_struct_sizes(int32_t out[6]) {
+extern "C" int sapt_struct_sizes(int32_t out[7]) {
   out[0] = (int32_t)sizeof(sapt_propose_args);
   out[1] = (int32_t)sizeof(sapt_chain_state);
   out[2] = (int32_t)sizeof(sapt_history);
   out[3] = (int32_t)sizeof(sapt_accept_args);
   out[4] = (int32_t)sizeof(sapt_lg_first_args);
   out[5] = (int32_t)sizeof(sapt_fused_args);
+  out[6] = (int32_t)sizeof(sapt_local_surrogate);
   return SAPT_OK;
 }

@@ -40,13 +40,20 @@ class VariantSpec:
     compare_surrogate: bool     # RW:371 / RV:370 True, LG:381 False
     lg_flow: bool               # LG: redraw on surrogate, Langevin re-proposal, first-eval bookkeeping
     ship_zero_row: bool         # RW:496,626 / LG:543,822 ship surr_train_set with its all-zero first row
+    local_surrogate: bool = False  # LS fork: one 4-10-1 network per chain over its own likelihood history
 
 
 VARIANTS = {
     "rw": VariantSpec("rw", True, False, False, False, True, True, False, True, False, True),
     "lg": VariantSpec("lg", True, True, True, True, False, False, True, False, True, True),
     "rv": VariantSpec("rv", False, False, False, False, False, False, False, True, False, False),
+    # localsurrogates/surrogate_pt_classifier_rw_localsurrogate.py: exchanges like LG (tempered L posted at
+    # i % swap_interval == 0 including 0, LS:756-757) but only w is taken back (LS:765); the surrogate is gated on
+    # surrogate_interval (LS:588) and always compared with the true train likelihood (LS:607-608)
+    "ls": VariantSpec("ls", True, True, True, False, False, False, False, True, False, False, True),
 }
+
+LS_LRATE, LS_EPOCHS, LS_BLOCK = 0.1, 200, 5   # LS:262, LS:253, LS:548
 
 
 @dataclass
@@ -152,7 +159,24 @@ class PTEngine:
         self.total_swap_proposals = 0
         self.train_cap = 0
         self.train_theta = self.train_L = self.train_count = None
-        if cfg.use_surrogate:
+        self.ls = None
+        if self.spec.local_surrogate and cfg.use_surrogate:
+            if self.hist is None:
+                raise ValueError("the local-surrogate fork reads its inputs from the surg_likeh_list history: record_history is required")
+            if cfg.surrogate_interval < LS_BLOCK:
+                raise ValueError("local surrogate: surrogate_interval must be >= 5 (LS:781 builds windows of five)")
+            self.ls_weights = torch.zeros((self.Rg, _lib.LS_WEIGHTS), **f64)
+            self.ls_limit = torch.zeros(self.Rg, **f64)
+            self.ls_pred = torch.zeros(self.R, **f64); self.ls_avg = torch.zeros(self.R, **f64)
+            self.ls_rmse = torch.zeros(self.Rg, **f64)
+            self.ls_ready = False
+            self.ls_synced_row = 0          # surg history rows < this are complete on every rank
+            self.ls_train_rmse: List[torch.Tensor] = []
+            self.ls = _lib.LocalSurrogate()
+            self.ls.weights = self.ls_weights.data_ptr(); self.ls.limit = self.ls_limit.data_ptr()
+            self.ls.surg = self.hist["surg"].data_ptr(); self.ls.n_slots = self.Rg
+            self.ls.slot_of_row = self.slot_of_row.data_ptr(); self.ls.R = self.R
+        if cfg.use_surrogate and not self.spec.local_surrogate:
             interval = cfg.swap_interval if self.spec.common_interval else cfg.surrogate_interval
             self.train_cap = int(cfg.train_cap if cfg.train_cap is not None else min(interval + 1, S))
             self.train_theta = torch.zeros((self.Rg, self.train_cap, self.P), dtype=torch.float32, device=dev)
@@ -170,6 +194,8 @@ class PTEngine:
                 if inject.get(k) is not None:
                     self.inj[k] = torch.as_tensor(np.ascontiguousarray(inject[k], dtype=np.float64)).to(dev)
             self.inj_weights = inject.get("surrogate_weights_per_signature")
+            if inject.get("net_init") is not None:   # LS: the 61 create_network normals of every chain
+                self.inj["net_init"] = torch.as_tensor(np.ascontiguousarray(inject["net_init"], dtype=np.float64)).to(dev)
         self.flags = 0
         sp = self.spec
         if sp.post_tempered: self.flags |= _lib.F_POST_TEMPERED
@@ -177,6 +203,7 @@ class PTEngine:
         if sp.denorm_half_min: self.flags |= _lib.F_DENORM_HALF_MIN
         if sp.compare_surrogate: self.flags |= _lib.F_COMPARE_SURROGATE
         if sp.lg_flow: self.flags |= _lib.F_REDRAW_ON_SURROGATE
+        if sp.local_surrogate: self.flags |= _lib.F_LOCAL_SURROGATE
         if cfg.record_history and cfg.record_pos: self.flags |= _lib.F_RECORD_POS
         self.evals = 0  # replica x row likelihood evaluations issued (host-side count of the worst case)
         # device-side step / sweep counters: kernels read step = base + *counter, so a captured CUDA graph of
@@ -258,7 +285,8 @@ class PTEngine:
         z1 = self._inj("z1", i); a.z_inject = z1.data_ptr() if z1 is not None else None
         a.decide = 1 if use_sur else 0
         a.redraw = 1 if sp.lg_flow else 0
-        a.surrogate_ready = 1 if self.surrogate.ready else 0
+        sur_ready = self.ls_ready if self.ls is not None else self.surrogate.ready
+        a.surrogate_ready = 1 if sur_ready else 0
         a.surrogate_prob = cfg.surrogate_prob; a.gate = gate
         z2 = self._inj("z2", i); a.z2_inject = z2.data_ptr() if z2 is not None else None
         ku = self._inj("ku", i); a.ku_inject = ku.data_ptr() if ku is not None else None
@@ -266,10 +294,13 @@ class PTEngine:
         a.sur_rows = self.sur_rows.data_ptr(); a.n_sur = self.counters[1:2].data_ptr()
         _lib.check(L.sapt_propose(C.byref(a), st), "sapt_propose")
 
-        sur_possible = use_sur and self.surrogate.ready and cfg.surrogate_prob > 0 and (self._graph_mode or i >= gate + 1)
+        sur_possible = use_sur and sur_ready and cfg.surrogate_prob > 0 and (self._graph_mode or i >= gate + 1)
         true_rows = self.true_rows if use_sur else None
         n_true = self.counters[0:1] if use_sur else None
-        if sur_possible:
+        if sur_possible and self.ls is not None:
+            _lib.check(L.sapt_local_surrogate_predict(C.byref(self.ls), i, sdev, _ptr(self.sur_rows), _ptr(self.counters[1:2]),
+                                                      _ptr(self.ls_pred), _ptr(self.ls_avg), st), "sapt_local_surrogate_predict")
+        elif sur_possible:
             w = self.surrogate.weights
             _lib.check(L.sapt_surrogate_predict(_ptr(self.prop), self.ld, self.R, self.P, _ptr(self.sur_rows), _ptr(self.counters[1:2]),
                                                 _ptr(w["W1"]), _ptr(w["b1"]), self.surrogate.h1, _ptr(w["W2"]), _ptr(w["b2"]),
@@ -339,6 +370,8 @@ class PTEngine:
             m.train_count = self.train_count.data_ptr(); m.train_cap = self.train_cap
         m.capture = 0 if sp.lg_flow else 1
         m.surg_first = self.surg_first.data_ptr() if sp.lg_flow else None
+        if self.ls is not None:
+            m.ls_pred = self.ls_pred.data_ptr(); m.ls_avg = self.ls_avg.data_ptr()
         _lib.check(L.sapt_mh_accept(C.byref(m), st), "sapt_mh_accept")
 
     # ------------------------------------------------------------------------------------
@@ -352,6 +385,9 @@ class PTEngine:
         args = (self.lik_cur, self.lik_post, self.prior_cur, self.likl_wo_temp, self.last, self.mov, self.naccept)
         pack = parallel.sync_hosted(parallel.pack_state(*args), self._hosted_mask(), self.pg)
         parallel.unpack_state(pack, *args)
+        if self.ls is not None:   # the local network and its limit belong to the chain (slot), not to the theta row
+            net = parallel.sync_hosted(torch.cat([self.ls_weights.t(), self.ls_limit[None]], dim=0), self._hosted_mask(), self.pg)
+            self.ls_weights.copy_(net[:-1].t()); self.ls_limit.copy_(net[-1])
 
     def swap(self, i: int):
         """Replica exchange at a rendezvous (RW:1095-1099)."""
@@ -373,6 +409,8 @@ class PTEngine:
                                           self.cfg.seed & 0xFFFFFFFF, self.sweep_count, _ptr(u), _ptr(swapped),
                                           _ptr(self.counters[3:4]), None, self.row0, self.R, _ptr(self.slot_of_row),
                                           current_stream_ptr()), "sapt_swap_sweep")
+        if self.ls is not None and self.cfg.world > 1:
+            self._ls_sync_history(i + 2)
         self.swap_log.append(swapped)
         self._segments.append((i + 2, self._hosted_mask()))  # history rows >= i+2 are written under the new binding
         self.sweep_count += 1
@@ -403,7 +441,32 @@ class PTEngine:
         self.train_count.zero_()
         return batch
 
+    def _ls_sync_history(self, upto: int):
+        """Multi-rank LS: a chain's surg_likeh_list rows live on whichever rank hosted the chain when they were
+        written. Between two exchanges the binding is fixed, so in the rows written since the last sync every
+        (row, chain) entry is non-zero on exactly one rank: a plain sum makes them complete everywhere (NaN
+        markers survive the sum), and the new host of a chain can feed its network."""
+        import torch.distributed as dist
+        lo = self.ls_synced_row
+        if upto > lo:
+            dist.all_reduce(self.hist["surg"][lo:upto], group=self.pg)
+            self.ls_synced_row = upto
+
+    def local_surrogate_train(self, i: int):
+        """LS:771-832 for every local chain: first call = series surg[0:i, 2], limit, fresh network; later calls
+        = the last surrogate_interval entries, same limit, training continues."""
+        first = not self.ls_ready
+        lo = 0 if first else i - self.cfg.surrogate_interval
+        init = self.inj.get("net_init") if (self.inj is not None and first) else None
+        _lib.check(self.L.sapt_local_surrogate_train(C.byref(self.ls), lo, i, 1 if first else 0, _ptr(init), self.cfg.seed & 0xFFFFFFFF,
+                                                     LS_LRATE, LS_EPOCHS, _ptr(self.ls_rmse), current_stream_ptr()),
+                   "sapt_local_surrogate_train")
+        self.ls_train_rmse.append(self.ls_rmse.clone())
+        self.ls_ready = True
+
     def surrogate_rendezvous(self, i: int):
+        if self.ls is not None:
+            return self.local_surrogate_train(i)
         batch = self.gather_training_rows()
         self.surr_batches.append(batch)
         if batch.shape[0] == 0:
@@ -435,7 +498,7 @@ class PTEngine:
     # ------------------------------------------------------------------------------------
     def fused_supported(self) -> bool:
         """Small problems (the reference's own runnable cases) run n steps per launch in the fused kernel."""
-        return (not self.spec.lg_flow and self.inj is None and (self.p.n[0] + self.p.n[1]) <= 8192
+        return (not self.spec.lg_flow and self.ls is None and self.inj is None and (self.p.n[0] + self.p.n[1]) <= 8192
                 and self.p.topology[0] <= 64 and self.p.topology[2] <= 20 and self.p.topology[1] <= 128)
 
     def fused_steps(self, i0: int, n: int):
@@ -555,7 +618,9 @@ class PTEngine:
                 if "pos_w" in hist:
                     # rows synchronised at exchanges are present on every rank: keep only hosted-at-write entries
                     hist["pos_w"] = self._pos_w_owned()
-                hist = {k: parallel.merge_history(v, self.pg) for k, v in hist.items()}
+                if self.ls is not None:
+                    self._ls_sync_history(self.cfg.samples)   # surg is then complete on every rank: not merged again
+                hist = {k: (v if (k == "surg" and self.ls is not None) else parallel.merge_history(v, self.pg)) for k, v in hist.items()}
                 hist["likeh"][0].fill_(-100.0)
                 if "pos_w" in hist:
                     hist["pos_w"][0].fill_(1.0)
@@ -578,6 +643,9 @@ class PTEngine:
         out["row_of_slot"] = self.row_of_slot.cpu().numpy()
         out["likelihood"] = self.lik_post.cpu().numpy(); out["likelihood_copy"] = self.lik_cur.cpu().numpy()
         out["prior_current"] = self.prior_cur.cpu().numpy()
+        if self.ls is not None:
+            out["ls_weights"] = self.ls_weights.cpu().numpy(); out["ls_limit"] = self.ls_limit.cpu().numpy()
+            out["ls_train_rmse"] = [t.cpu().numpy() for t in self.ls_train_rmse]
         return out
 
     def _pos_w_owned(self):

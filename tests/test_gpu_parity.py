@@ -248,6 +248,87 @@ def test_full_run_matches_reference_traces(lib, name, path_name):
     np.testing.assert_allclose(res["min_y"], float(g["min_y"]), rtol=1e-5)
 
 
+@pytest.mark.parametrize("path_name", ["f32", "tc"])
+def test_local_surrogate_fork_matches_reference_traces(lib, path_name):
+    """N4, variant 'ls': per-chain 4-10-1 networks trained on the device (sapt_local_surrogate_train) from the
+    chain's own surg_likeh_list history and used on surrogate steps (sapt_local_surrogate_predict); the recorded
+    streams of the unmodified fork are injected and every decision / trace must match."""
+    from sapt_b200.engine import EngineConfig, PTEngine
+    from sapt_b200.problem import Problem
+    g = gu.load("run_ls_cancer")
+    kw = gu.run_local_inputs(g)
+    path = lib.PATH_F32 if path_name == "f32" else lib.PATH_TC
+    prob = Problem(kw["topology"], kw["traindata"], kw["testdata"], path=path)
+    cfg = EngineConfig(variant="ls", samples=kw["samples"], swap_interval=kw["swap_interval"], surrogate_interval=kw["surrogate_interval"],
+                       surrogate_prob=kw["surrogate_prob"], use_surrogate=True, seed=1, record_history=True, record_pos=False, path=path)
+    st = kw["streams"]
+    eng = PTEngine(prob, kw["temperatures"], cfg, inject=dict(z1=st.z1, ku=st.ku, u=st.u, swap_u=st.swap_u, net_init=kw["net_init"]))
+    eng.initialize(kw["w0"])
+    eng.run()
+    torch.cuda.synchronize()
+    res = eng.results()
+    ora = so.run_pt_local(**kw)
+    assert np.array_equal(res["accepted"], ora["accepted"]), "accept/reject decisions differ"
+    assert np.array_equal(res["is_surrogate_step"], ora["is_surrogate_step"]) and ora["is_surrogate_step"].sum() > 0
+    assert np.array_equal(res["accept_list"], g["trace_accept_list"])
+    for a, b in zip(res["swap_decisions"], ora["swap_decisions"]):
+        assert np.array_equal(a, b), "swap decisions differ"
+    assert res["num_swap"] == int(g["num_swap"])
+    np.testing.assert_allclose(eng.current_w(), ora["w_final"], rtol=0, atol=5e-6)
+    for k in ("acc_train", "acc_test", "rmse_train", "rmse_test"):
+        a, b = res[k], g["trace_" + k]
+        assert np.array_equal(np.isinf(a), np.isinf(b)), k
+        m = np.isfinite(b)
+        np.testing.assert_allclose(a[m], b[m], rtol=1e-12, atol=0, err_msg=k)
+    gu.compare_traces(g, res, rtol=2e-5, atol=2e-4, keys=("surg_likeh_list", "likeh_list"))
+    # the networks themselves: limit, training error of every call, final weights (fp64 on the device; their
+    # inputs are fp32-path likelihoods, hence the tolerance)
+    np.testing.assert_allclose(res["ls_limit"], ora["limit"], rtol=2e-6)
+    assert len(res["ls_train_rmse"]) == int(g["n_train_calls"])
+    for c, rm in enumerate(res["ls_train_rmse"]):
+        np.testing.assert_allclose(rm, [float(g[f"ls_train{c}_rmse_{k}"]) for k in range(len(kw["temperatures"]))], rtol=1e-4)
+    nc = int(g["n_train_calls"])
+    for k in range(len(kw["temperatures"])):
+        np.testing.assert_allclose(res["ls_weights"][k], g[f"ls_train{nc - 1}_weights_{k}"], rtol=1e-3, atol=1e-4)
+
+
+def test_local_surrogate_train_kernel_against_reference_call(lib):
+    """One sapt_local_surrogate_train call on exactly the series the reference's first training saw (fp64 in,
+    fp64 out): weights and rmse to 1e-9."""
+    import ctypes as C
+    from sapt_b200._lib import LocalSurrogate, LS_WEIGHTS
+    g = gu.load("run_ls_cancer")
+    R = len(g["temperatures"]); i = int(g["surrogate_interval"])
+    surg = np.transpose(g["trace_surg_likeh_list"], (1, 0, 2)).copy()     # [samples][chain][3]
+    d_surg = torch.as_tensor(surg).cuda()
+    w = torch.zeros((R, LS_WEIGHTS), dtype=torch.float64, device="cuda"); lim = torch.zeros(R, dtype=torch.float64, device="cuda")
+    rm = torch.zeros(R, dtype=torch.float64, device="cuda")
+    sor = torch.arange(R, dtype=torch.int32, device="cuda")
+    init = torch.as_tensor(g["net_init"]).cuda()
+    m = LocalSurrogate(); m.weights = w.data_ptr(); m.limit = lim.data_ptr(); m.surg = d_surg.data_ptr(); m.n_slots = R
+    m.slot_of_row = sor.data_ptr(); m.R = R
+    lib.check(lib.lib().sapt_local_surrogate_train(C.byref(m), 0, i, 1, init.data_ptr(), 1, 0.1, 200, rm.data_ptr(), None))
+    torch.cuda.synchronize()
+    for k in range(R):
+        np.testing.assert_allclose(w[k].cpu().numpy(), g[f"ls_train0_weights_{k}"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(rm[k].item(), float(g[f"ls_train0_rmse_{k}"]), rtol=1e-9)
+    # the prediction the reference made from these weights: check against the oracle forward
+    pred = torch.zeros(R, dtype=torch.float64, device="cuda"); avg = torch.zeros(R, dtype=torch.float64, device="cuda")
+    step = i + 3
+    lib.check(lib.lib().sapt_local_surrogate_predict(C.byref(m), step, None, None, None, pred.data_ptr(), avg.data_ptr(), None))
+    torch.cuda.synchronize()
+    for k in range(R):
+        net = so.local_net_init(np.zeros(61))
+        wk = w[k].cpu().numpy()
+        net = dict(W1=wk[:40].reshape(4, 10), W2=wk[40:50].reshape(10, 1), B1=wk[50:60].reshape(1, 10), B2=wk[60:61].reshape(1, 1))
+        x = surg[step - 4:step, k, 2] / lim[k].item()
+        _, out = so.local_net_forward(x, net)
+        np.testing.assert_allclose(pred[k].item(), out[0, 0] * lim[k].item(), rtol=1e-12)
+        np.testing.assert_allclose(avg[k].item(), np.mean(x) * lim[k].item(), rtol=1e-12)
+    with pytest.raises(ValueError):
+        lib.check(lib.lib().sapt_local_surrogate_train(C.byref(m), 0, 3, 1, None, 1, 0.1, 200, None, None))
+
+
 def test_large_shape_properties(lib):
     """C3-shape (16-30-10) at a size the oracle cannot finish: size-independent properties.
     (1) identical chains give identical L; (2) L is additive over a split of the rows;
