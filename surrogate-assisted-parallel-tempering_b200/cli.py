@@ -1,10 +1,10 @@
 """Command line of the reference (_revamp.py:1402-1411,1563-1570):
 
     python -m sapt_b200.cli problem samples surrogate_prob surrogate_intervalratio foldername num_chains
-           [--data-root DIR] [--variant rw|lg|rv] [--hidden H] [--seed S] [--no-dump]
+           [--data-root DIR] [--variant rw|lg|rv|ls] [--hidden H] [--seed S] [--no-dump]
 
 Same six positional arguments; constants as in the chosen fork's main() (rv: maxtemp 2, swap_interval 5,
-burn_in 0.6, learn_rate 0.01; rw: 4, 50, 0.2, 0.5; lg: as rw with Langevin gradients, swap_interval 100000)."""
+burn_in 0.6, learn_rate 0.01; rw: 4, 50, 0.2, 0.5; lg: as rw with Langevin gradients, swap_interval 100000; ls: the local-surrogate fork, 4, 100000, 0.6, 0.01)."""
 from __future__ import annotations
 
 import argparse
@@ -18,6 +18,7 @@ FORK_CONSTANTS = {  # (maxtemp, swap_interval, burn_in, use_langevin, learn_rate
     "rv": (2, 5, 0.6, False, 0.01),          # _revamp.py:1555-1608
     "rw": (4, 50, 0.2, False, 0.5),          # surrogate_rw_common_interval.py:1484-1486
     "lg": (4, 100000, 0.2, True, 0.5),       # surrogate_pt_classifier_langevingrad.py:1672,1723-1725
+    "ls": (4, 100000, 0.6, False, 0.01),     # localsurrogates/surrogate_pt_classifier_rw_localsurrogate.py:1543-1546,1600-1602
 }
 
 
@@ -47,7 +48,8 @@ def main(argv=None):
     R.make_directories(path)
     t0 = time.time()
     pt = ParallelTempering(a.surrogate_prob > 0, use_lg, lr, False, traindata, testdata, topology, a.num_chains, maxtemp, a.samples,
-                           swap_interval, max(1, surrogate_interval), a.surrogate_prob, path, path, sur_topo, variant=a.variant, seed=a.seed)
+                           swap_interval, max(1, surrogate_interval), a.surrogate_prob, path, path, sur_topo, variant=a.variant, seed=a.seed,
+                           record_pos=not a.no_dump or a.variant != "ls")
     pt.initialize_chains(burn_in)
     (pos_w, fx_train, fx_test, rmse_train, rmse_test, acc_train, acc_test, accept_list, swap_perc, likelihood_rep, rmse_surr,
      surr_list, accept) = pt.run_chains()

@@ -3,7 +3,9 @@
 Constructor, `initialize_chains(burn_in)` and `run_chains()` keep the reference's names,
 positional order and return tuple. What changes underneath: no processes, queues or events; the
 R chains are rows of one device-resident state and every step is a few kernel launches.
-Extra keyword arguments (all optional) select the reference fork to mimic and the seed."""
+Extra keyword arguments (all optional) select the reference fork to mimic and the seed. Calling it with the
+local-surrogate fork's 15 positional arguments (no surrogate_topology, LS:894) selects variant "ls"
+(that fork comments out its pos_w files, LS:846; the engine keeps pos_w unless record_pos=False)."""
 from __future__ import annotations
 
 import numpy as np
@@ -19,7 +21,7 @@ from .surrogate import SurrogateTrainer
 class ParallelTempering:
     def __init__(self, use_surrogate, use_langevin_gradients, learn_rate, save_surrogate_data, traindata, testdata,
                  topology, num_chains, maxtemp, NumSample, swap_interval, surrogate_interval, surrogate_prob, path,
-                 path_db, surrogate_topology, *, variant=None, seed=1, langevin_mode="sgd_exact", langevin_batch_scale=1.0,
+                 path_db, surrogate_topology=None, *, variant=None, seed=1, langevin_mode="sgd_exact", langevin_batch_scale=1.0,
                  kernel_path=_lib.PATH_AUTO, record_pos=True, process_group=None):
         self.traindata = traindata
         self.testdata = testdata
@@ -50,6 +52,11 @@ class ParallelTempering:
         self.save_surrogate_data = save_surrogate_data
         self.use_langevin_gradients = bool(use_langevin_gradients)
         self.learn_rate = learn_rate
+        # the 15-argument constructor (no surrogate_topology) is the local-surrogate fork's (LS:894): per-chain networks
+        if surrogate_topology is None and variant is None:
+            variant = "ls"
+        if surrogate_topology is None:
+            self.surrogate_topology = surrogate_topology = 1
         self.variant = variant or ("lg" if self.use_langevin_gradients else "rw")
         self.seed = int(seed)
         self._langevin_mode = langevin_mode
@@ -87,7 +94,7 @@ class ParallelTempering:
                            seed=self.seed, record_history=True, record_pos=self._record_pos, path=self._kernel_path,
                            rank=rank, world=world)
         trainer = None
-        if self.use_surrogate:
+        if self.use_surrogate and self.variant != "ls":   # 'ls' trains its per-chain networks on the device
             trainer = SurrogateTrainer(self.num_param, int(self.surrogate_topology), self.problem.device, seed=self.seed)
         self._trainer = trainer
         self.engine = PTEngine(self.problem, self.temperatures, cfg, surrogate_trainer=trainer, process_group=self._pg)

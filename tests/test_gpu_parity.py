@@ -562,6 +562,33 @@ def test_cli_reference_command_line(lib, tmp_path, monkeypatch):
     assert os.path.isfile(tmp_path / "master_result_file.txt")
 
 
+def test_local_surrogate_fork_class_surface(lib):
+    """The fork's 15-argument ParallelTempering (LS:894, no surrogate_topology) selects variant 'ls' and runs on Philox
+    streams: surrogate steps happen after the first training and their proposals carry prediction * limit."""
+    from sapt_b200.parallel_tempering import ParallelTempering
+    g = gu.load("unit_cancer")
+    topo = [int(v) for v in g["topology"]]
+    pt = ParallelTempering(True, False, 0.01, False, g["train"], g["test"], topo, 4, 4.0, 4 * 400, 10, 40, 0.5, "", "", seed=5)
+    assert pt.variant == "ls"
+    pt.initialize_chains(0.5)
+    out = pt.run_chains()
+    res = pt.results
+    sur = res["is_surrogate_step"]
+    assert sur[:, :42].sum() == 0 and sur[:, 42:].sum() > 100          # gate: i >= surrogate_interval + 1 (LS:588)
+    s1 = res["surg_likeh_list"][:, :, 1]
+    assert np.array_equal(~np.isnan(s1[:, 1:]), sur[:, 1:])
+    lim = res["ls_limit"]
+    assert np.all(lim < 0)
+    # every prediction is sigmoid * limit: between limit and 0, and (network trained towards 1.0) close to limit
+    for k in range(4):
+        v = s1[k][sur[k]]
+        assert np.all(v <= 0) and np.all(v >= lim[k])
+    assert len(res["ls_train_rmse"]) == (400 - 2) // 40
+    acc_tr = out[5]
+    fin = acc_tr[np.isfinite(acc_tr)]
+    assert fin.size > 0 and np.all((fin >= 0) & (fin <= 100)) and np.isinf(acc_tr).sum() > 0   # inf marks surrogate steps (LS:702-705)
+
+
 @pytest.mark.parametrize("use_sur,variant", [(False, "rw"), (True, "rw"), (True, "rv")])
 def test_fused_small_problem_kernel_equals_multi_kernel_path(lib, use_sur, variant):
     """sapt_fused_steps (n steps per launch, theta in shared memory) must give the same chains as the

@@ -17,13 +17,16 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _cfg(world, rank):
+def _cfg(world, rank, variant="rw"):
     from sapt_b200.engine import EngineConfig
+    if variant == "ls":   # local-surrogate fork: Philox streams, networks and history windows follow the chains across ranks
+        return EngineConfig(variant="ls", samples=40, swap_interval=4, surrogate_interval=10, surrogate_prob=0.5,
+                            use_surrogate=True, seed=22, record_history=True, record_pos=False, rank=rank, world=world)
     return EngineConfig(variant="rw", samples=30, swap_interval=3, surrogate_interval=3, surrogate_prob=0.0,
                         use_surrogate=False, seed=21, record_history=True, record_pos=True, rank=rank, world=world)
 
 
-def _run(rank, world, port, q):
+def _run(rank, world, port, q, variant="rw"):
     import torch.distributed as dist
     from sapt_b200.engine import PTEngine
     from sapt_b200.ladder import assign_temperatures
@@ -35,12 +38,16 @@ def _run(rank, world, port, q):
     g = gu.load("unit_cancer")
     topo = [int(v) for v in g["topology"]]
     prob = Problem(topo, g["train"], g["test"], device=rank)
-    eng = PTEngine(prob, assign_temperatures(8, 4.0), _cfg(world, rank))
+    eng = PTEngine(prob, assign_temperatures(8, 4.0), _cfg(world, rank, variant))
     eng.initialize(g["W"][0])
     eng.run()
     torch.cuda.synchronize()
     res = eng.results()
-    out = {k: res[k] for k in ("pos_w", "accepted", "accept_list", "lhood_list", "acc_train", "naccept", "row_of_slot")}
+    keys = ("pos_w", "accepted", "accept_list", "lhood_list", "acc_train", "naccept", "row_of_slot")
+    if variant == "ls":
+        keys = ("accepted", "accept_list", "lhood_list", "acc_train", "naccept", "row_of_slot", "surg_likeh_list", "is_surrogate_step",
+                "ls_weights", "ls_limit")
+    out = {k: res[k] for k in keys}
     out["swaps"] = np.array([s for s in res["swap_decisions"]])
     out["num_swap"] = res["num_swap"]
     if world > 1:
@@ -67,3 +74,26 @@ def test_two_gpu_run_equals_one_gpu_run():
     assert np.array_equal(one["naccept"], two["naccept"])
     np.testing.assert_allclose(one["lhood_list"], two["lhood_list"], rtol=1e-12)
     assert one["swaps"].sum() > 0
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_local_surrogate_equals_one_gpu():
+    """Variant 'ls' over two ranks: the per-chain networks, their limits and the surg_likeh_list windows they read
+    must follow the chains through the exchanges (engine._ls_sync_history, sync_slots)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_run, args=(0, 1, 0, q, "ls")); p.start(); one = q.get(timeout=300); p.join()
+    port = _free_port()
+    procs = [ctx.Process(target=_run, args=(r, 2, port, q, "ls")) for r in range(2)]
+    for p in procs: p.start()
+    two = q.get(timeout=300)
+    for p in procs: p.join()
+    assert one["is_surrogate_step"].sum() > 0 and one["swaps"].sum() > 0
+    for k in ("accepted", "is_surrogate_step", "swaps", "row_of_slot", "naccept"):
+        assert np.array_equal(one[k], two[k]), k
+    a, b = one["surg_likeh_list"], two["surg_likeh_list"]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(b[~np.isnan(a)], a[~np.isnan(a)], rtol=1e-12)
+    np.testing.assert_allclose(two["lhood_list"][np.isfinite(one["lhood_list"])], one["lhood_list"][np.isfinite(one["lhood_list"])], rtol=1e-12)
+    np.testing.assert_allclose(two["ls_limit"], one["ls_limit"], rtol=1e-12)
