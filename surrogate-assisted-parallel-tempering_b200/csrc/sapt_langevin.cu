@@ -448,6 +448,17 @@ __global__ void langevin_batch_finalize(const float* part, int n_chunks, int R, 
   theta_gd[(int64_t)row * ld + i] = (float)((double)theta[(int64_t)row * ld + i] + lr_scale * s);
 }
 
+int launch_langevin_batch_finalize(const float* part, int n_chunks, int R, int P, const float* theta, float* theta_gd, int64_t ld,
+                                   const int32_t* rows, const int32_t* n_rows, double lr_scale, cudaStream_t st) {
+  langevin_batch_finalize<<<dim3((P + 127) / 128, R), 128, 0, st>>>(part, n_chunks, R, P, theta, theta_gd, ld, rows, n_rows, lr_scale);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}
+
+bool langevin_tc_supported(const sapt_problem* p);   // sapt_langevin_tc.cu
+int launch_langevin_tc(sapt_problem* p, const float* theta, float* theta_gd, int64_t ld, int R, const int32_t* rows, const int32_t* n_rows,
+                       double lr_scale, cudaStream_t st);
+
 }  // namespace sapt
 
 using namespace sapt;
@@ -494,7 +505,8 @@ extern "C" int sapt_langevin(sapt_problem_t* p, const float* theta, float* theta
     SAPT_CHECK_LAUNCH();
     return SAPT_OK;
   }
-  if (mode == 1) {
+  if (mode == 1 && langevin_tc_supported(p)) return launch_langevin_tc(p, theta, theta_gd, ld, R, rows, n_rows, lrate * batch_scale, st);
+  if (mode == 1 || mode == 2) {   // 2: the CUDA-core kernels even where the tensor-core path applies
     const int P = p->P;
     const int64_t n_tiles = (ds.n + kBT - 1) / kBT;
     int64_t n_chunks = std::min<int64_t>(n_tiles, std::max<int64_t>(1, ((int64_t)p->num_sms * 4 + R - 1) / R));

@@ -1,0 +1,528 @@
+// tcgen05 / TMEM / TMA batch-Langevin gradient (sm_100a only): the fixed-theta restatement of
+// Network.langevin_gradient (LG:138-156, BackwardPass LG:96-106)
+//     theta_gd = theta + lr * scale * sum_rows g_row(theta)
+// with ALL five contractions on the tensor cores. Per chain and per 128-row tile:
+//
+//   MMA-1  D1[rows, HP]   = X . W1'                      smem (K-major) x smem -> TMEM   forward layer 1
+//   P1     h = sigmoid(D1) -> bf16 pieces [h1 | h2] -> shared memory Hs (row-major, SWIZZLE_128B)
+//   MMA-2  D2[rows, 3 ON] = Hs . [w1|w2|w3], += h2 . [w1|w2]   Hs read K-major               forward layer 2
+//   P2     out = sigmoid(D2 + b2); do = (1[y] - out) out (1 - out) -> pieces [do_hi | do_lo] -> Ds
+//   G2     G2[2 HP, 2 ON] += Hs^T . Ds                    both operands read MN-major, K = rows   grad W2
+//   MMA-3  D3[rows, HP]   = Ds . W2^T                     Ds read K-major                         back-propagation
+//   P3     dh = D3 * h (1 - h) -> pieces [dh_hi | dh_lo] -> Hs (overwrites h)
+//   G1     G1[x columns, 2 HP] += X^T . Hs                X tile and Hs read MN-major, K = rows   grad W1 (+ B1)
+//
+// The row contractions (G1, G2) accumulate in TMEM over all tiles of the CTA's row chunk; at the end of a chain
+// the epilogue warps fold the bf16-piece partial products into one fp32 gradient vector in shared memory and write
+// it to part[chunk][chain][P]; langevin_batch_finalize (sapt_langevin.cu) sums the chunks and applies the step.
+// The same bytes of Hs / Ds / the X tile serve as K-major operands (forward / back-propagation: K = features)
+// and as MN-major operands (gradients: K = rows): only the descriptor changes.
+// B1 gradient: a column of ones in the X image (the bias chunk, or for D > 32 the first spare column of the x1
+// piece) makes -sum(dh) a row of G1. B2 gradient: per-thread sums of do, reduced at the end of the chain.
+// fp32-grade accuracy from bf16 operands as in sapt_loglik_tc2.cu: x = x1 + x2 (+ x3 dropped: 2^-17), w = w1 + w2 + w3,
+// h, do, dh = two pieces each; the cross terms kept are listed at each MMA.
+//
+// CTA = (row chunk, chain group); chains of the group run one after the other (the accumulators are per chain).
+// Warp 16 lane 0: TMA producer (X tile ring; per-chain weight panels). Warp 17: TMEM alloc + MMA issue. Warps 0-15:
+// epilogue, warp (quarter q = TMEM lanes 32q.., slice s = HP/4 hidden units); P2 of tile t is done by slice t % 4.
+#include <algorithm>
+#include <type_traits>
+#include <vector>
+
+#include "sapt_device.cuh"
+#include "sapt_internal.h"
+#include "sapt_tc_ptx.cuh"
+
+namespace sapt {
+
+int launch_tc2_pack(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O, int HP, int ON, int CH,
+                    int DKC, int KROW, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2, int n_blocks, cudaStream_t st);   // sapt_loglik_tc2.cu
+int tc_make_map_2d(CUtensorMap* map, void* base, uint64_t inner_elems, uint64_t rows, uint32_t box_rows);                       // sapt_loglik_tc.cu
+int launch_langevin_batch_finalize(const float* part, int n_chunks, int R, int P, const float* theta, float* theta_gd, int64_t ld,
+                                   const int32_t* rows, const int32_t* n_rows, double lr_scale, cudaStream_t st);                // sapt_langevin.cu
+
+namespace lt {
+constexpr int kTileM = 128;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int ON = 16;                    // outputs padded (O <= 16)
+constexpr int N2 = 3 * ON;
+constexpr uint32_t kBlk = 128 * 128;      // one 64-column block of a 128-row tile
+
+template <int HP, int DKC>
+struct Cfg {
+  static constexpr int DW = 16 * DKC;                         // features per x piece (padded)
+  static constexpr int KBA = (3 * DKC + 1 + 3) / 4;           // 128-byte K blocks of an image row
+  static constexpr int NSLOT = (DKC == 4) ? 3 : KBA;          // X blocks kept in shared memory: x1, x2, bias (x3 skipped)
+  static constexpr int BIAS_SLOT_CHUNK = (DKC == 4) ? 8 : 3 * DKC;   // bias chunk index inside the shared-memory tile
+  static constexpr int NBH = (2 * HP + 63) / 64;              // blocks of Hs: [piece 1 (HP) | piece 2 (HP)]
+  static constexpr int HW = HP / 4;                           // hidden units per epilogue warp
+  static constexpr int NG1 = NBH * 64;                        // G1 columns
+  static constexpr int STAGES = 2;
+  static constexpr uint32_t kAStage = NSLOT * kBlk;
+  static constexpr uint32_t kB1Bytes = HP * KBA * 128;
+  static constexpr uint32_t kW2Bytes = N2 * 128;
+  static constexpr uint32_t kW2TBytes = HP * 128;
+  static constexpr uint32_t kHsBytes = NBH * kBlk;
+  __host__ __device__ static constexpr uint32_t smem_bytes() {
+    return 1024u + STAGES * kAStage + ((kB1Bytes + 1023u) & ~1023u) + 8192u + ((kW2TBytes + 1023u) & ~1023u) + kHsBytes + kBlk + 1024u;
+  }
+  // TMEM columns
+  static constexpr int kDS = 0, kG1 = 64, kG2 = 64 + NG1, kCols = 256;
+  static_assert(64 + NG1 + 64 <= kCols && HP <= 64 && N2 <= 64, "TMEM budget");
+  // column of ones in the X image that turns -sum(dh) into a row of G1 (see tc_prepare_dataset)
+  __host__ __device__ static constexpr int ones_col(int D) { return DKC <= 2 ? 3 * DW : D; }
+};
+
+struct Params {
+  const int32_t* y;
+  const float* bias2;                 // [pos][ON] log2(e) * B2 (used when the bias is not folded into the W2 image)
+  const int32_t* n_rows; int R;
+  int D, H, O, fold_bias;
+  int tiles_per_chunk; int64_t n_tiles;
+  int chains_per_cta;
+  float* part;                        // [chunk][R][P]
+  int P;
+};
+
+__device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {   // MN-major, SWIZZLE_128B
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between 64-element blocks along M / N
+  d |= (uint64_t)(1024 >> 4) << 32;                    // stride between groups of 8 K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t idesc_bf16(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+template <int N>
+__device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 16) tmem_ld16(taddr, r);
+  else if constexpr (N == 8) tmem_ld8(taddr, r);
+  else tmem_ld4(taddr, r);
+}
+// two bf16 pieces of v (round to nearest): v ~ hi + lo to 2^-17 relative
+__device__ __forceinline__ void split2(float v, float& hi, float& lo) {
+  hi = __bfloat162float(__float2bfloat16_rn(v));
+  lo = v - hi;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
+
+// writes n bf16 values (n = 4, 8 or 16) of one data row into a swizzled [128 rows][64 bf16] block at column col0
+template <int N>
+__device__ __forceinline__ void store_row_bf16(uint8_t* block, int row, int col0, const float (&v)[N]) {
+  uint32_t w[N / 2];
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  uint8_t* rowp = block + row * 128;
+  if constexpr (N == 4) {
+    const int chunk = col0 >> 3;
+    *reinterpret_cast<uint2*>(rowp + (((chunk ^ (row & 7)) << 4) | ((col0 & 7) * 2))) = make_uint2(w[0], w[1]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < N / 8; ++c) {
+      const int chunk = (col0 >> 3) + c;
+      *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+    }
+  }
+}
+
+// W2^T image for MMA-3: row h = [w1 (16 outputs) | w2 (16 outputs) | 0 ..] of +W2[h][:] (unscaled)
+__global__ void lt_pack_w2t_kernel(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O, int HP,
+                                   __nv_bfloat16* img) {
+  const int nact = n_rows ? *n_rows : R;
+  const int pos = blockIdx.x;
+  __nv_bfloat16* dst = img + (int64_t)pos * HP * 64;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  if (pos >= nact) { for (int i = threadIdx.x; i < HP * 64; i += blockDim.x) dst[i] = zero; return; }
+  const int row = rows ? rows[pos] : pos;
+  const float* src = theta + (int64_t)row * ld;
+  for (int i = threadIdx.x; i < HP * 64; i += blockDim.x) {
+    const int h = i >> 6, c = i & 63, o = c & 15, piece = c >> 4;
+    __nv_bfloat16 v = zero;
+    if (h < H && o < O && piece < 2) {
+      const float w = src[D * H + h * O + o];
+      const __nv_bfloat16 p1 = __float2bfloat16_rn(w);
+      v = (piece == 0) ? p1 : __float2bfloat16_rn(w - __bfloat162float(p1));
+    }
+    dst[i] = v;
+  }
+}
+
+template <int HP, int DKC>
+__global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b1,
+                                                                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2t,
+                                                                  Params p) {
+  using C = Cfg<HP, DKC>;
+  constexpr int DW = C::DW, KBA = C::KBA, NSLOT = C::NSLOT, NBH = C::NBH, HW = C::HW, NG1 = C::NG1, STAGES = C::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB1 = sA + STAGES * C::kAStage;
+  uint8_t* sW2 = sB1 + ((C::kB1Bytes + 1023u) & ~1023u);
+  uint8_t* sW2T = sW2 + 8192;
+  uint8_t* sHs = sW2T + ((C::kW2TBytes + 1023u) & ~1023u);
+  uint8_t* sDs = sHs + C::kHsBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDs + kBlk);
+  uint64_t* full_a = bars;                  // [STAGES]
+  uint64_t* empty_a = full_a + STAGES;      // [STAGES]
+  uint64_t* w_full = empty_a + STAGES;      // weight panels of the current chain landed
+  uint64_t* w_free = w_full + 1;            // all MMAs of the chain done: the panels may be overwritten
+  uint64_t* d1_full = w_free + 1;
+  uint64_t* hs_full = d1_full + 1;          // 16 warps
+  uint64_t* d2_full = hs_full + 1;
+  uint64_t* ds_full = d2_full + 1;          // 4 warps
+  uint64_t* d3_full = ds_full + 1;
+  uint64_t* dh_full = d3_full + 1;          // 16 warps
+  uint64_t* g_full = dh_full + 1;           // G1 / G2 of the chain complete
+  uint64_t* g_free = g_full + 1;            // 16 warps: accumulators read out
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(g_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nact = p.n_rows ? *p.n_rows : p.R;
+  const int pos0 = blockIdx.y * p.chains_per_cta;
+  if (pos0 >= nact) return;
+  const int n_chains = min(p.chains_per_cta, nact - pos0);
+  const int64_t t_begin = (int64_t)blockIdx.x * p.tiles_per_chunk;
+  const int n_tiles = (int)max((int64_t)0, min(t_begin + (int64_t)p.tiles_per_chunk, p.n_tiles) - t_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    mbar_init(w_full, 1); mbar_init(w_free, 1);
+    mbar_init(d1_full, 1); mbar_init(hs_full, kEpiWarps); mbar_init(d2_full, 1); mbar_init(ds_full, 4);
+    mbar_init(d3_full, 1); mbar_init(dh_full, kEpiWarps); mbar_init(g_full, 1); mbar_init(g_free, kEpiWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(C::kCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == kTmaWarp) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int it = 0;
+      for (int c = 0; c < n_chains; ++c) {
+        if (c > 0) mbar_wait<500>(w_free, (c - 1) & 1);
+        mbar_expect_tx(w_full, C::kB1Bytes + C::kW2Bytes + C::kW2TBytes);
+#pragma unroll
+        for (int kb = 0; kb < KBA; ++kb) tma_load_2d(&map_b1, w_full, sB1 + kb * HP * 128, kb * 64, (pos0 + c) * HP);
+        tma_load_2d(&map_w2, w_full, sW2, 0, (pos0 + c) * N2);
+        tma_load_2d(&map_w2t, w_full, sW2T, 0, (pos0 + c) * HP);
+        for (int t = 0; t < n_tiles; ++t, ++it) {
+          const int s = it % STAGES;
+          mbar_wait<500>(&empty_a[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_a[s], C::kAStage);
+#pragma unroll
+          for (int j = 0; j < NSLOT; ++j) {
+            const int blk = (DKC == 4 && j == 2) ? 3 : j;       // DKC = 4: the x3 block is not needed
+            tma_load_2d(&map_a, &full_a[s], sA + s * C::kAStage + j * kBlk, blk * 64, (int)((t_begin + t) * kTileM));
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const uint32_t id1 = idesc_bf16(kTileM, HP, false, false);
+      const uint32_t id2a = idesc_bf16(kTileM, N2, false, false), id2b = idesc_bf16(kTileM, 2 * ON, false, false);
+      const uint32_t id3 = idesc_bf16(kTileM, HP, false, false);
+      const uint32_t idg2 = idesc_bf16(128, 64, true, true), idg1 = idesc_bf16(128, NG1, true, true);
+      const uint32_t b1a = smem_u32(sB1), w2a = smem_u32(sW2), w2ta = smem_u32(sW2T), hsa = smem_u32(sHs), dsa = smem_u32(sDs);
+      const uint32_t tD = tmem_base + C::kDS, tG1 = tmem_base + C::kG1, tG2 = tmem_base + C::kG2;
+      // shared-memory chunk (16 bf16 = 32 B) -> address inside a tile / panel made of 64-column blocks
+      auto a_chunk = [&](uint32_t base, int chunk) { return base + (uint32_t)(chunk >> 2) * kBlk + (uint32_t)(chunk & 3) * 32; };
+      auto b1_chunk = [&](int chunk) { return b1a + (uint32_t)(chunk >> 2) * (HP * 128) + (uint32_t)(chunk & 3) * 32; };
+      int it = 0;
+      uint32_t ph = 0;   // per-tile barriers complete once per tile
+      for (int c = 0; c < n_chains; ++c) {
+        mbar_wait(w_full, c & 1);
+        if (c > 0) mbar_wait(g_free, (c - 1) & 1);     // accumulators of the previous chain have been read out
+        for (int t = 0; t < n_tiles; ++t, ++it, ph ^= 1) {
+          const int s = it % STAGES;
+          const uint32_t xa = smem_u32(sA + s * C::kAStage);
+          mbar_wait(&full_a[s], (it / STAGES) & 1);
+          tc_fence_after();
+          // ---- MMA-1: x1w1 x1w2 x2w1 x1w3 x2w2 + bias. x chunks: x1 = [0, DKC), x2 = [DKC, 2 DKC) ----
+          {
+            constexpr int pa[5] = {0, 0, 1, 0, 1};
+            constexpr int pb[5] = {0, 1, 0, 2, 1};
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+#pragma unroll
+              for (int j = 0; j < DKC; ++j)
+                tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, pa[q] * DKC + j)), umma_desc_sw128(b1_chunk(pb[q] * DKC + j)), id1, (q | j) ? 1u : 0u);
+            tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, C::BIAS_SLOT_CHUNK)), umma_desc_sw128(b1_chunk(3 * DKC)), id1, 1u);
+            tc_commit(d1_full);
+          }
+          // ---- MMA-2: D2 = h1.[w1|w2|w3] + h2.[w1|w2], A = Hs read K-major ----
+          mbar_wait(hs_full, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, k)), umma_desc_sw128(w2a + k * 32), id2a, k ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, HP / 16 + k)), umma_desc_sw128(w2a + k * 32), id2b, 1u);
+          tc_commit(d2_full);
+          // ---- G2 += Hs^T . Ds (K = rows), then MMA-3: D3 = do_hi.w1 + do_hi.w2 + do_lo.w1 ----
+          mbar_wait(ds_full, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kTileM / 16; ++k)
+            tc_mma_bf16(tG2, desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), desc_mn(dsa + k * 2048, 0), idg2, (t | k) ? 1u : 0u);
+          tc_mma_bf16(tD, umma_desc_sw128(dsa), umma_desc_sw128(w2ta), id3, 0u);
+          tc_mma_bf16(tD, umma_desc_sw128(dsa), umma_desc_sw128(w2ta + 32), id3, 1u);
+          tc_mma_bf16(tD, umma_desc_sw128(dsa + 32), umma_desc_sw128(w2ta), id3, 1u);
+          tc_commit(d3_full);
+          // ---- G1 += X^T . Hs(dh) (K = rows) ----
+          mbar_wait(dh_full, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kTileM / 16; ++k)
+            tc_mma_bf16(tG1, desc_mn(xa + k * 2048, NSLOT > 1 ? kBlk : 0), desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), idg1, (t | k) ? 1u : 0u);
+          tc_commit(&empty_a[s]);
+        }
+        tc_commit(g_full);
+        tc_commit(w_free);
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int quarter = warp & 3, slice = warp >> 2;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int O = p.O, D = p.D, H = p.H;
+    float* sGrad = reinterpret_cast<float*>(sHs);        // [P] fp32 at the end of a chain (Hs is idle then)
+    uint32_t ph = 0;
+    for (int c = 0; c < n_chains; ++c) {
+      const int pos = pos0 + c;
+      float accB2[ON];
+#pragma unroll
+      for (int o = 0; o < ON; ++o) accB2[o] = 0.f;
+      for (int t = 0; t < n_tiles; ++t, ph ^= 1) {
+        const int y = __ldg(p.y + (t_begin + t) * kTileM + row_in_tile);
+        // ---- P1: h = sigmoid(D1), pieces -> Hs ----
+        float h[HW];
+        {
+          mbar_wait(d1_full, ph);
+          tc_fence_after();
+          uint32_t zr[HW];
+          tmem_ldN<HW>(tmem_base + lane_base + (uint32_t)(C::kDS + slice * HW), zr);
+          tmem_ld_wait();
+          float h1[HW], h2[HW];
+#pragma unroll
+          for (int j = 0; j < HW; ++j) {
+            h[j] = rcp_approx(1.0f + ex2_approx(fminf(__uint_as_float(zr[j]), 60.0f)));
+            split2(h[j], h1[j], h2[j]);
+          }
+          store_row_bf16<HW>(sHs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, h1);
+          store_row_bf16<HW>(sHs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, h2);
+          fence_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(hs_full);
+        }
+        // ---- P2 (one slice per tile): output layer and its delta -> Ds ----
+        if (slice == (t & 3)) {
+          mbar_wait(d2_full, ph);
+          tc_fence_after();
+          uint32_t d0[ON], d1[ON], d2[ON];
+          const uint32_t ta = tmem_base + lane_base + C::kDS;
+          tmem_ld16(ta, d0); tmem_ld16(ta + ON, d1); tmem_ld16(ta + 2 * ON, d2);
+          tmem_ld_wait();
+          float dhi[ON], dlo[ON];
+#pragma unroll
+          for (int o = 0; o < ON; ++o) {
+            float dv = 0.f;
+            if (o < O && y >= 0) {
+              float tt = (__uint_as_float(d0[o]) + __uint_as_float(d1[o])) + __uint_as_float(d2[o]);
+              if (!p.fold_bias) tt += __ldg(p.bias2 + (int64_t)pos * ON + o);
+              const float out = rcp_approx(1.0f + ex2_approx(fminf(tt, 60.0f)));
+              dv = ((o == y ? 1.0f : 0.0f) - out) * (out * (1.0f - out));     // LG:100
+              accB2[o] += dv;
+            }
+            split2(dv, dhi[o], dlo[o]);
+          }
+          store_row_bf16<ON>(sDs, row_in_tile, 0, dhi);
+          store_row_bf16<ON>(sDs, row_in_tile, ON, dlo);
+          fence_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ds_full);
+        }
+        // ---- P3: dh = (do . W2^T) h (1 - h), pieces -> Hs ----
+        {
+          mbar_wait(d3_full, ph);
+          tc_fence_after();
+          uint32_t zr[HW];
+          tmem_ldN<HW>(tmem_base + lane_base + (uint32_t)(C::kDS + slice * HW), zr);
+          tmem_ld_wait();
+          float g1[HW], g2[HW];
+#pragma unroll
+          for (int j = 0; j < HW; ++j) split2(__uint_as_float(zr[j]) * (h[j] * (1.0f - h[j])), g1[j], g2[j]);   // LG:101
+          store_row_bf16<HW>(sHs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, g1);
+          store_row_bf16<HW>(sHs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, g2);
+          fence_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dh_full);
+        }
+      }
+      // ---- end of the chain: fold the accumulators into one fp32 gradient vector ----
+      mbar_wait(g_full, c & 1);
+      tc_fence_after();
+      const int P = p.P;
+      for (int i = threadIdx.x; i < P; i += 32 * kEpiWarps) sGrad[i] = 0.f;
+      epi_sync();
+      {
+        // G1: TMEM lane m = column m of the X image tile; this warp reads columns [slice * NG1/4, +NG1/4)
+        const int m = row_in_tile;
+        const int piece = m / DW, d = m - piece * DW;
+        const bool is_w = (piece < (DKC <= 2 ? 3 : 2)) && (d < D);   // DKC = 1: lanes >= 64 repeat the block and fall out here
+        const bool is_b = (m == C::ones_col(D));
+        constexpr int CW = NG1 / 4;       // 16 or 32 columns per warp
+        uint32_t r[CW];
+        const uint32_t ta = tmem_base + lane_base + (uint32_t)(C::kG1 + slice * CW);
+        if constexpr (CW == 32) tmem_ld32(ta, r); else tmem_ld16(ta, r);
+        tmem_ld_wait();
+        if (is_w || is_b) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const int n = slice * CW + j;                 // [dh_hi (HP) | dh_lo (HP)]
+            const int hh = n < HP ? n : n - HP;
+            if (n < 2 * HP && hh < H) {
+              const float v = __uint_as_float(r[j]);
+              if (is_w) atomicAdd(&sGrad[d * H + hh], v);                       // LG:104: W1 += x^T dh
+              else atomicAdd(&sGrad[D * H + H * O + hh], -v);                   // LG:105: B1 += -dh
+            }
+          }
+        }
+        // G2: TMEM lane m = [h1 (HP) | h2 (HP)] hidden index; columns [do_hi (16) | do_lo (16)]; slice s reads 8 of the 32
+        const int hh2 = m < HP ? m : m - HP;
+        uint32_t r2[8];
+        tmem_ld8(tmem_base + lane_base + (uint32_t)(C::kG2 + slice * 8), r2);
+        tmem_ld_wait();
+        if (m < 2 * HP && hh2 < H) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = slice * 8 + j, o = n & 15;
+            if (o < O) atomicAdd(&sGrad[D * H + hh2 * O + o], __uint_as_float(r2[j]));   // LG:102: W2 += h^T do
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < ON; ++o) {
+          const float sres = warp_sum(accB2[o]);
+          if (lane == 0 && o < O) atomicAdd(&sGrad[D * H + H * O + H + o], -sres);       // LG:103: B2 += -do
+        }
+      }
+      tc_fence_before();
+      epi_sync();
+      float* dst = p.part + ((int64_t)blockIdx.x * p.R + pos) * P;
+      for (int i = threadIdx.x; i < P; i += 32 * kEpiWarps) dst[i] = sGrad[i];
+      epi_sync();
+      fence_async_smem();     // Hs goes back to being an MMA operand
+      if (lane == 0) mbar_arrive(g_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kCols));
+  }
+}
+
+template <int HP, int DKC>
+static int launch_variant(const CUtensorMap& ma, const CUtensorMap& mb1, const CUtensorMap& mw2, const CUtensorMap& mw2t, const Params& a, dim3 grid,
+                          cudaStream_t st) {
+  using C = Cfg<HP, DKC>;
+  constexpr size_t smem = C::smem_bytes();
+  if constexpr (smem > 227 * 1024) {
+    set_error("tcgen05 Langevin: variant HP=%d DKC=%d does not fit in shared memory", HP, DKC);
+    return SAPT_ERR_UNSUPPORTED;
+  } else {
+    auto k = langevin_tc_kernel<HP, DKC>;
+    SAPT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kThreads, smem, st>>>(ma, mb1, mw2, mw2t, a);
+    SAPT_CHECK_LAUNCH();
+    return SAPT_OK;
+  }
+}
+}  // namespace lt
+
+// the tensor-core batch-Langevin path covers O <= 16, H <= 64, D <= 64; for D > 32 it needs a spare column in the
+// x1 piece of the operand image for the column of ones (D not a multiple of 16)
+bool langevin_tc_supported(const sapt_problem* p) {
+  if (!p->tc_ok || p->O > 16 || p->H > 64 || p->D > 64) return false;
+  const int dkc = p->D <= 16 ? 1 : (p->D + 15) / 16;
+  if (dkc >= 3 && p->D == 16 * dkc) return false;
+  return true;
+}
+
+int launch_langevin_tc(sapt_problem* p, const float* theta, float* theta_gd, int64_t ld, int R, const int32_t* rows, const int32_t* n_rows,
+                       double lr_scale, cudaStream_t st) {
+  using namespace lt;
+  const DataSet& ds = p->set[0];
+  const int HP = p->H <= 16 ? 16 : (p->H <= 32 ? 32 : 64);
+  const int DKC = p->D <= 16 ? 1 : (p->D + 15) / 16;
+  const int KROW = ((48 * DKC + 16 + 63) / 64) * 64;
+  const int P = p->P;
+  const int64_t n_tiles = ds.n_pad / kTileM;
+  // CTAs = row chunks x chain groups; a chain group runs its chains one after the other
+  int groups = std::min(R, std::max(1, p->num_sms / 8));
+  int chains_per_cta = (R + groups - 1) / groups;
+  groups = (R + chains_per_cta - 1) / chains_per_cta;
+  int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_tiles / 8, (p->num_sms * 2 + groups - 1) / groups));
+  const int tiles_per_chunk = (int)((n_tiles + n_chunks - 1) / n_chunks);
+  n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+
+  auto up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
+  const size_t b1_bytes = (size_t)R * HP * KROW * 2, w2_bytes = (size_t)R * N2 * 64 * 2, w2t_bytes = (size_t)R * HP * 64 * 2;
+  const size_t bias_bytes = (size_t)R * ON * sizeof(float), part_bytes = (size_t)n_chunks * R * P * sizeof(float);
+  int rc = ensure_workspace(p, up(part_bytes) + up(b1_bytes) + up(w2_bytes) + up(w2t_bytes) + up(bias_bytes));
+  if (rc) return rc;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p->ws);
+  float* part = reinterpret_cast<float*>(ws);
+  __nv_bfloat16* b1img = reinterpret_cast<__nv_bfloat16*>(ws + up(part_bytes));
+  __nv_bfloat16* w2img = reinterpret_cast<__nv_bfloat16*>(ws + up(part_bytes) + up(b1_bytes));
+  __nv_bfloat16* w2timg = reinterpret_cast<__nv_bfloat16*>(ws + up(part_bytes) + up(b1_bytes) + up(w2_bytes));
+  float* bias2 = reinterpret_cast<float*>(ws + up(part_bytes) + up(b1_bytes) + up(w2_bytes) + up(w2t_bytes));
+
+  if ((rc = launch_tc2_pack(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, ON, 1, DKC, KROW, b1img, w2img, bias2, R, st))) return rc;
+  lt_pack_w2t_kernel<<<R, 256, 0, st>>>(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, w2timg);
+  SAPT_CHECK_LAUNCH();
+  CUtensorMap mb1, mw2, mw2t;
+  if ((rc = tc_make_map_2d(&mb1, b1img, (uint64_t)KROW, (uint64_t)R * HP, (uint32_t)HP))) return rc;
+  if ((rc = tc_make_map_2d(&mw2, w2img, 64, (uint64_t)R * N2, (uint32_t)N2))) return rc;
+  if ((rc = tc_make_map_2d(&mw2t, w2timg, 64, (uint64_t)R * HP, (uint32_t)HP))) return rc;
+  Params a{};
+  a.y = ds.y; a.bias2 = bias2; a.n_rows = n_rows; a.R = R; a.D = p->D; a.H = p->H; a.O = p->O; a.fold_bias = (p->H < HP) ? 1 : 0;
+  a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.chains_per_cta = chains_per_cta; a.part = part; a.P = P;
+  dim3 grid((unsigned)n_chunks, (unsigned)groups);
+  const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(ds.tmap);
+#define SAPT_LT(H_, K_) if (HP == H_ && DKC == K_) rc = launch_variant<H_, K_>(ma, mb1, mw2, mw2t, a, grid, st); else
+  SAPT_LT(16, 1) SAPT_LT(16, 2) SAPT_LT(16, 3) SAPT_LT(16, 4) SAPT_LT(32, 1) SAPT_LT(32, 2) SAPT_LT(32, 3) SAPT_LT(32, 4)
+  SAPT_LT(64, 1) SAPT_LT(64, 2) SAPT_LT(64, 3) SAPT_LT(64, 4) { set_error("tcgen05 Langevin: no variant for HP=%d DKC=%d", HP, DKC); rc = SAPT_ERR_UNSUPPORTED; }
+#undef SAPT_LT
+  if (rc) return rc;
+  return launch_langevin_batch_finalize(part, (int)n_chunks, R, P, theta, theta_gd, ld, rows, n_rows, lr_scale, st);
+}
+
+}  // namespace sapt

@@ -85,6 +85,9 @@ int tc_prepare_dataset(sapt_problem* p, int which, const float* x_host, int64_t 
       }
     }
     row[3 * dw] = one; row[3 * dw + 1] = one; row[3 * dw + 2] = one;
+    // batch-Langevin gradient (sapt_langevin_tc.cu): for D > 32 the bias chunk lies outside the 128 image columns its
+    // X^T.dh contraction covers, so the first spare column of the x1 piece carries the ones (its weights are zero)
+    if (dw >= 48 && p->D < dw) row[p->D] = one;
   }
   SAPT_CUDA(cudaMalloc(&ds.a_bf16, img.size() * 2));
   SAPT_CUDA(cudaMemcpy(ds.a_bf16, img.data(), img.size() * 2, cudaMemcpyHostToDevice));

@@ -143,6 +143,13 @@ __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* r
   for (int i = threadIdx.x; i < ON; i += blockDim.x) bb[i] = (i < O) ? kLog2e * src[D * H + H * O + H + i] : 0.f;   // used when H == HP (no spare hidden slot)
 }
 
+int launch_tc2_pack(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O, int HP, int ON, int CH,
+                    int DKC, int KROW, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2, int n_blocks, cudaStream_t st) {
+  tc2_pack_kernel<<<n_blocks, 256, 0, st>>>(theta, ld, rows, n_rows, R, D, H, O, HP, ON, CH, DKC, KROW, b1img, w2img, bias2);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}
+
 // four sigmoids with one reciprocal:  s_i = 1 / a_i,  a_i = 1 + 2^min(t_i, 30)  (clamp: |error| < 1e-9,
 // keeps the product of four below 2^120)
 __device__ __forceinline__ void sigmoid4(float t0, float t1, float t2, float t3, float& s0, float& s1, float& s2, float& s3) {
