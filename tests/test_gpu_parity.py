@@ -452,6 +452,38 @@ def test_c4_langevin_batch_and_exact_at_covtype_topology(lib):
         assert np.max(np.abs(got - g)) <= 1e-4 * np.max(np.abs(g)) + 2e-4
 
 
+@pytest.mark.parametrize("topo", [[9, 12, 2], [16, 30, 10], [34, 50, 2], [54, 64, 7], [20, 50, 2], [4, 8, 3]])
+def test_langevin_batch_tensor_core_path(lib, topo):
+    """sapt_langevin mode 1 = the tcgen05 kernel (forward, back-propagation and both row contractions as MMAs,
+    sapt_langevin_tc.cu) wherever it applies; checked against the oracle's batch gradient (LG:96-106 at fixed theta)
+    and against the CUDA-core kernels (mode 2). Sizes chosen to cover several row chunks per chain, several chains
+    per CTA, a ragged last tile and a row subset."""
+    from sapt_b200.problem import Problem
+    n, R = 2700, 23
+    data = _synthetic(topo[0], topo[2], n, 21)
+    P = so.num_param(topo)
+    W = (np.random.RandomState(4).standard_normal((R, P)) * 0.4).astype(np.float32)
+    prob = Problem(topo, data, None)
+    th = torch.as_tensor(W).cuda()
+    lr = 0.002
+    rows = torch.as_tensor(np.array([3, 0, 22, 7, 11, 5], dtype=np.int32)).cuda()
+    n_rows = torch.as_tensor(np.array([5], dtype=np.int32)).cuda()           # only the first five listed rows are active
+    o1 = prob.langevin(th, lr, mode=1, batch_scale=1.0 / n).cpu().numpy().astype(np.float64)
+    o2 = prob.langevin(th, lr, mode=2, batch_scale=1.0 / n).cpu().numpy().astype(np.float64)
+    s1 = prob.langevin(th, lr, mode=1, batch_scale=1.0 / n, rows=rows, n_rows=n_rows).cpu().numpy().astype(np.float64)
+    for k in range(R):
+        g = so.langevin_batch_gradient(data, W[k].astype(np.float64), topo) / n
+        tol = 1e-4 * np.max(np.abs(g)) + 6e-5      # 6e-5: fp32 rounding of theta + lr * g, divided by lr
+        assert np.max(np.abs((o1[k] - W[k]) / lr - g)) <= tol, (topo, k)
+        assert np.max(np.abs((o2[k] - W[k]) / lr - g)) <= tol, (topo, k)
+    active = [3, 0, 22, 7, 11]
+    for k in range(R):
+        if k in active:
+            np.testing.assert_allclose(s1[k], o1[k], rtol=0, atol=1e-6)
+        else:
+            assert np.array_equal(s1[k], W[k].astype(np.float64))              # untouched rows keep theta
+
+
 def test_c5_engine_with_surrogate_at_chess_topology(lib):
     """C5-shape (6-25-18) chains with surrogate_prob 0.5 and a fixed surrogate MLP (topology 3), injected
     streams generated here; the device engine must reproduce the oracle's decisions."""
