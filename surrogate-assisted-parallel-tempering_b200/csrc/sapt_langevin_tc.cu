@@ -59,18 +59,18 @@ struct Cfg {
   static constexpr int NBH = (2 * HP + 63) / 64;              // blocks of Hs: [piece 1 (HP) | piece 2 (HP)]
   static constexpr int HW = HP / 4;                           // hidden units per epilogue warp
   static constexpr int NG1 = NBH * 64;                        // G1 columns
-  static constexpr int STAGES = 2;
   static constexpr uint32_t kAStage = NSLOT * kBlk;
   static constexpr uint32_t kB1Bytes = HP * KBA * 128;
   static constexpr uint32_t kW2Bytes = N2 * 128;
   static constexpr uint32_t kW2TBytes = HP * 128;
   static constexpr uint32_t kHsBytes = NBH * kBlk;
-  __host__ __device__ static constexpr uint32_t smem_bytes() {
-    return 1024u + STAGES * kAStage + ((kB1Bytes + 1023u) & ~1023u) + 8192u + ((kW2TBytes + 1023u) & ~1023u) + kHsBytes + kBlk + 1024u;
+  __host__ __device__ static constexpr uint32_t smem_bytes() {   // two tile buffers of X and Hs, one shared Ds block
+    return 1024u + 2 * kAStage + 2 * kHsBytes + kBlk + ((kB1Bytes + 1023u) & ~1023u) + ((kW2TBytes + 1023u) & ~1023u) +
+           ((kW2Bytes + 1023u) & ~1023u) + 512u;
   }
-  // TMEM columns
-  static constexpr int kDS = 0, kG1 = 64, kG2 = 64 + NG1, kCols = 256;
-  static_assert(64 + NG1 + 64 <= kCols && HP <= 64 && N2 <= 64, "TMEM budget");
+  // TMEM columns: scratch D1/D2/D3 per tile buffer | G1 | G2 per tile buffer
+  static constexpr int kDS = 0, kG1 = 128, kG2 = 128 + NG1, kCols = 512;
+  static_assert(128 + NG1 + 128 <= kCols && HP <= 64 && N2 <= 64, "TMEM budget");
   // column of ones in the X image that turns -sum(dh) into a row of G1 (see tc_prepare_dataset)
   __host__ __device__ static constexpr int ones_col(int D) { return DKC <= 2 ? 3 * DW : D; }
 };
@@ -167,27 +167,28 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
                                                                   const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2t,
                                                                   Params p) {
   using C = Cfg<HP, DKC>;
-  constexpr int DW = C::DW, KBA = C::KBA, NSLOT = C::NSLOT, NBH = C::NBH, HW = C::HW, NG1 = C::NG1, STAGES = C::STAGES;
+  constexpr int DW = C::DW, KBA = C::KBA, NSLOT = C::NSLOT, NBH = C::NBH, HW = C::HW, NG1 = C::NG1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB1 = sA + STAGES * C::kAStage;
-  uint8_t* sW2 = sB1 + ((C::kB1Bytes + 1023u) & ~1023u);
-  uint8_t* sW2T = sW2 + 8192;
-  uint8_t* sHs = sW2T + ((C::kW2TBytes + 1023u) & ~1023u);
-  uint8_t* sDs = sHs + C::kHsBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDs + kBlk);
-  uint64_t* full_a = bars;                  // [STAGES]
-  uint64_t* empty_a = full_a + STAGES;      // [STAGES]
-  uint64_t* w_full = empty_a + STAGES;      // weight panels of the current chain landed
+  uint8_t* sA = smem;                                          // [2 buffers][NSLOT blocks]
+  uint8_t* sHs = sA + 2 * C::kAStage;                          // [2 buffers][NBH blocks]
+  uint8_t* sDs = sHs + 2 * C::kHsBytes;                        // ONE block: buffer b owns columns [32 b, 32 b + 32)
+  uint8_t* sB1 = sDs + kBlk;
+  uint8_t* sW2T = sB1 + ((C::kB1Bytes + 1023u) & ~1023u);
+  uint8_t* sW2 = sW2T + ((C::kW2TBytes + 1023u) & ~1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW2 + ((C::kW2Bytes + 1023u) & ~1023u));
+  // per tile buffer b (two tiles are in flight: while one waits for an MMA the other one computes)
+  uint64_t* full_a = bars;                  // [2]
+  uint64_t* empty_a = full_a + 2;           // [2]
+  uint64_t* d1_full = empty_a + 2;          // [2]
+  uint64_t* hs_full = d1_full + 2;          // [2] 16 warps
+  uint64_t* d2_full = hs_full + 2;          // [2]
+  uint64_t* ds_full = d2_full + 2;          // [2] 4 warps
+  uint64_t* d3_full = ds_full + 2;          // [2]
+  uint64_t* dh_full = d3_full + 2;          // [2] 16 warps
+  uint64_t* w_full = dh_full + 2;           // weight panels of the current chain landed
   uint64_t* w_free = w_full + 1;            // all MMAs of the chain done: the panels may be overwritten
-  uint64_t* d1_full = w_free + 1;
-  uint64_t* hs_full = d1_full + 1;          // 16 warps
-  uint64_t* d2_full = hs_full + 1;
-  uint64_t* ds_full = d2_full + 1;          // 4 warps
-  uint64_t* d3_full = ds_full + 1;
-  uint64_t* dh_full = d3_full + 1;          // 16 warps
-  uint64_t* g_full = dh_full + 1;           // G1 / G2 of the chain complete
+  uint64_t* g_full = w_free + 1;            // G1 / G2 of the chain complete
   uint64_t* g_free = g_full + 1;            // 16 warps: accumulators read out
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(g_free + 1);
 
@@ -198,12 +199,15 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
   const int n_chains = min(p.chains_per_cta, nact - pos0);
   const int64_t t_begin = (int64_t)blockIdx.x * p.tiles_per_chunk;
   const int n_tiles = (int)max((int64_t)0, min(t_begin + (int64_t)p.tiles_per_chunk, p.n_tiles) - t_begin);
+  const int n_pairs = (n_tiles + 1) / 2;      // tile 2 q uses buffer 0, tile 2 q + 1 buffer 1 (absent in a ragged last pair)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
-    mbar_init(w_full, 1); mbar_init(w_free, 1);
-    mbar_init(d1_full, 1); mbar_init(hs_full, kEpiWarps); mbar_init(d2_full, 1); mbar_init(ds_full, 4);
-    mbar_init(d3_full, 1); mbar_init(dh_full, kEpiWarps); mbar_init(g_full, 1); mbar_init(g_free, kEpiWarps);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&full_a[b], 1); mbar_init(&empty_a[b], 1);
+      mbar_init(&d1_full[b], 1); mbar_init(&hs_full[b], kEpiWarps); mbar_init(&d2_full[b], 1); mbar_init(&ds_full[b], 4);
+      mbar_init(&d3_full[b], 1); mbar_init(&dh_full[b], kEpiWarps);
+    }
+    mbar_init(w_full, 1); mbar_init(w_free, 1); mbar_init(g_full, 1); mbar_init(g_free, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
   if (warp == kTmaWarp) {
     // ================= TMA producer =================
     if (lane == 0) {
-      int it = 0;
+      uint32_t use[2] = {0, 0};               // how often each X buffer has been filled
       for (int c = 0; c < n_chains; ++c) {
         if (c > 0) mbar_wait<500>(w_free, (c - 1) & 1);
         mbar_expect_tx(w_full, C::kB1Bytes + C::kW2Bytes + C::kW2TBytes);
@@ -227,14 +231,15 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
         for (int kb = 0; kb < KBA; ++kb) tma_load_2d(&map_b1, w_full, sB1 + kb * HP * 128, kb * 64, (pos0 + c) * HP);
         tma_load_2d(&map_w2, w_full, sW2, 0, (pos0 + c) * N2);
         tma_load_2d(&map_w2t, w_full, sW2T, 0, (pos0 + c) * HP);
-        for (int t = 0; t < n_tiles; ++t, ++it) {
-          const int s = it % STAGES;
-          mbar_wait<500>(&empty_a[s], ((it / STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full_a[s], C::kAStage);
+        for (int t = 0; t < n_tiles; ++t) {
+          const int b = t & 1;
+          mbar_wait<500>(&empty_a[b], (use[b] & 1) ^ 1);
+          ++use[b];
+          mbar_expect_tx(&full_a[b], C::kAStage);
 #pragma unroll
           for (int j = 0; j < NSLOT; ++j) {
             const int blk = (DKC == 4 && j == 2) ? 3 : j;       // DKC = 4: the x3 block is not needed
-            tma_load_2d(&map_a, &full_a[s], sA + s * C::kAStage + j * kBlk, blk * 64, (int)((t_begin + t) * kTileM));
+            tma_load_2d(&map_a, &full_a[b], sA + b * C::kAStage + j * kBlk, blk * 64, (int)((t_begin + t) * kTileM));
           }
         }
       }
@@ -246,58 +251,71 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
       const uint32_t id2a = idesc_bf16(kTileM, N2, false, false), id2b = idesc_bf16(kTileM, 2 * ON, false, false);
       const uint32_t id3 = idesc_bf16(kTileM, HP, false, false);
       const uint32_t idg2 = idesc_bf16(128, 64, true, true), idg1 = idesc_bf16(128, NG1, true, true);
-      const uint32_t b1a = smem_u32(sB1), w2a = smem_u32(sW2), w2ta = smem_u32(sW2T), hsa = smem_u32(sHs), dsa = smem_u32(sDs);
-      const uint32_t tD = tmem_base + C::kDS, tG1 = tmem_base + C::kG1, tG2 = tmem_base + C::kG2;
+      const uint32_t b1a = smem_u32(sB1), w2a = smem_u32(sW2), w2ta = smem_u32(sW2T), dsa = smem_u32(sDs);
+      const uint32_t tG1 = tmem_base + C::kG1;
       // shared-memory chunk (16 bf16 = 32 B) -> address inside a tile / panel made of 64-column blocks
       auto a_chunk = [&](uint32_t base, int chunk) { return base + (uint32_t)(chunk >> 2) * kBlk + (uint32_t)(chunk & 3) * 32; };
       auto b1_chunk = [&](int chunk) { return b1a + (uint32_t)(chunk >> 2) * (HP * 128) + (uint32_t)(chunk & 3) * 32; };
-      int it = 0;
-      uint32_t ph = 0;   // per-tile barriers complete once per tile
+      uint32_t use[2] = {0, 0};
+      uint32_t phb[2] = {0, 0};   // parity of the per-buffer barriers: they complete once per pair that uses the buffer
       for (int c = 0; c < n_chains; ++c) {
         mbar_wait(w_full, c & 1);
         if (c > 0) mbar_wait(g_free, (c - 1) & 1);     // accumulators of the previous chain have been read out
-        for (int t = 0; t < n_tiles; ++t, ++it, ph ^= 1) {
-          const int s = it % STAGES;
-          const uint32_t xa = smem_u32(sA + s * C::kAStage);
-          mbar_wait(&full_a[s], (it / STAGES) & 1);
-          tc_fence_after();
+        for (int q = 0; q < n_pairs; ++q) {
+          const int nb = (2 * q + 1 < n_tiles) ? 2 : 1;
           // ---- MMA-1: x1w1 x1w2 x2w1 x1w3 x2w2 + bias. x chunks: x1 = [0, DKC), x2 = [DKC, 2 DKC) ----
-          {
+          for (int b = 0; b < nb; ++b) {
+            const uint32_t xa = smem_u32(sA + b * C::kAStage), tD = tmem_base + C::kDS + b * 64;
+            mbar_wait(&full_a[b], use[b] & 1);
+            ++use[b];
+            tc_fence_after();
             constexpr int pa[5] = {0, 0, 1, 0, 1};
             constexpr int pb[5] = {0, 1, 0, 2, 1};
 #pragma unroll
-            for (int q = 0; q < 5; ++q)
+            for (int k = 0; k < 5; ++k)
 #pragma unroll
               for (int j = 0; j < DKC; ++j)
-                tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, pa[q] * DKC + j)), umma_desc_sw128(b1_chunk(pb[q] * DKC + j)), id1, (q | j) ? 1u : 0u);
+                tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, pa[k] * DKC + j)), umma_desc_sw128(b1_chunk(pb[k] * DKC + j)), id1, (k | j) ? 1u : 0u);
             tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, C::BIAS_SLOT_CHUNK)), umma_desc_sw128(b1_chunk(3 * DKC)), id1, 1u);
-            tc_commit(d1_full);
+            tc_commit(&d1_full[b]);
           }
           // ---- MMA-2: D2 = h1.[w1|w2|w3] + h2.[w1|w2], A = Hs read K-major ----
-          mbar_wait(hs_full, ph);
-          tc_fence_after();
+          for (int b = 0; b < nb; ++b) {
+            const uint32_t hsa = smem_u32(sHs + b * C::kHsBytes), tD = tmem_base + C::kDS + b * 64;
+            mbar_wait(&hs_full[b], phb[b]);
+            tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, k)), umma_desc_sw128(w2a + k * 32), id2a, k ? 1u : 0u);
+            for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, k)), umma_desc_sw128(w2a + k * 32), id2a, k ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, HP / 16 + k)), umma_desc_sw128(w2a + k * 32), id2b, 1u);
-          tc_commit(d2_full);
-          // ---- G2 += Hs^T . Ds (K = rows), then MMA-3: D3 = do_hi.w1 + do_hi.w2 + do_lo.w1 ----
-          mbar_wait(ds_full, ph);
-          tc_fence_after();
+            for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, HP / 16 + k)), umma_desc_sw128(w2a + k * 32), id2b, 1u);
+            tc_commit(&d2_full[b]);
+          }
+          // ---- G2[b] += Hs^T . Ds (K = rows; all 64 Ds columns, the 32 of buffer b are meaningful), then
+          //      MMA-3: D3 = do_hi.w1 + do_hi.w2 + do_lo.w1 ----
+          for (int b = 0; b < nb; ++b) {
+            const uint32_t hsa = smem_u32(sHs + b * C::kHsBytes), tD = tmem_base + C::kDS + b * 64, tG2 = tmem_base + C::kG2 + b * 64;
+            mbar_wait(&ds_full[b], phb[b]);
+            tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < kTileM / 16; ++k)
-            tc_mma_bf16(tG2, desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), desc_mn(dsa + k * 2048, 0), idg2, (t | k) ? 1u : 0u);
-          tc_mma_bf16(tD, umma_desc_sw128(dsa), umma_desc_sw128(w2ta), id3, 0u);
-          tc_mma_bf16(tD, umma_desc_sw128(dsa), umma_desc_sw128(w2ta + 32), id3, 1u);
-          tc_mma_bf16(tD, umma_desc_sw128(dsa + 32), umma_desc_sw128(w2ta), id3, 1u);
-          tc_commit(d3_full);
+            for (int k = 0; k < kTileM / 16; ++k)
+              tc_mma_bf16(tG2, desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), desc_mn(dsa + k * 2048, 0), idg2, (q | k) ? 1u : 0u);
+            const uint32_t da = dsa + b * 64;
+            tc_mma_bf16(tD, umma_desc_sw128(da), umma_desc_sw128(w2ta), id3, 0u);
+            tc_mma_bf16(tD, umma_desc_sw128(da), umma_desc_sw128(w2ta + 32), id3, 1u);
+            tc_mma_bf16(tD, umma_desc_sw128(da + 32), umma_desc_sw128(w2ta), id3, 1u);
+            tc_commit(&d3_full[b]);
+          }
           // ---- G1 += X^T . Hs(dh) (K = rows) ----
-          mbar_wait(dh_full, ph);
-          tc_fence_after();
+          for (int b = 0; b < nb; ++b) {
+            const uint32_t xa = smem_u32(sA + b * C::kAStage), hsa = smem_u32(sHs + b * C::kHsBytes);
+            mbar_wait(&dh_full[b], phb[b]);
+            phb[b] ^= 1;
+            tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < kTileM / 16; ++k)
-            tc_mma_bf16(tG1, desc_mn(xa + k * 2048, NSLOT > 1 ? kBlk : 0), desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), idg1, (t | k) ? 1u : 0u);
-          tc_commit(&empty_a[s]);
+            for (int k = 0; k < kTileM / 16; ++k)
+              tc_mma_bf16(tG1, desc_mn(xa + k * 2048, NSLOT > 1 ? kBlk : 0), desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), idg1, (q | b | k) ? 1u : 0u);
+            tc_commit(&empty_a[b]);
+          }
         }
         tc_commit(g_full);
         tc_commit(w_free);
@@ -310,79 +328,93 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int O = p.O, D = p.D, H = p.H;
     float* sGrad = reinterpret_cast<float*>(sHs);        // [P] fp32 at the end of a chain (Hs is idle then)
-    uint32_t ph = 0;
+    uint32_t phb[2] = {0, 0};
     for (int c = 0; c < n_chains; ++c) {
       const int pos = pos0 + c;
       float accB2[ON];
 #pragma unroll
       for (int o = 0; o < ON; ++o) accB2[o] = 0.f;
-      for (int t = 0; t < n_tiles; ++t, ph ^= 1) {
-        const int y = __ldg(p.y + (t_begin + t) * kTileM + row_in_tile);
+      for (int q = 0; q < n_pairs; ++q) {
+        const int nb = (2 * q + 1 < n_tiles) ? 2 : 1;
+        float h[2][HW];
+        int y[2];
         // ---- P1: h = sigmoid(D1), pieces -> Hs ----
-        float h[HW];
-        {
-          mbar_wait(d1_full, ph);
-          tc_fence_after();
-          uint32_t zr[HW];
-          tmem_ldN<HW>(tmem_base + lane_base + (uint32_t)(C::kDS + slice * HW), zr);
-          tmem_ld_wait();
-          float h1[HW], h2[HW];
 #pragma unroll
-          for (int j = 0; j < HW; ++j) {
-            h[j] = rcp_approx(1.0f + ex2_approx(fminf(__uint_as_float(zr[j]), 60.0f)));
-            split2(h[j], h1[j], h2[j]);
+        for (int b = 0; b < 2; ++b) {
+          if (b < nb) {
+            y[b] = __ldg(p.y + (t_begin + 2 * q + b) * kTileM + row_in_tile);
+            uint8_t* hs = sHs + b * C::kHsBytes;
+            mbar_wait(&d1_full[b], phb[b]);
+            tc_fence_after();
+            uint32_t zr[HW];
+            tmem_ldN<HW>(tmem_base + lane_base + (uint32_t)(C::kDS + b * 64 + slice * HW), zr);
+            tmem_ld_wait();
+            float h1[HW], h2[HW];
+#pragma unroll
+            for (int j = 0; j < HW; ++j) {
+              h[b][j] = rcp_approx(1.0f + ex2_approx(fminf(__uint_as_float(zr[j]), 60.0f)));
+              split2(h[b][j], h1[j], h2[j]);
+            }
+            store_row_bf16<HW>(hs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, h1);
+            store_row_bf16<HW>(hs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, h2);
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hs_full[b]);
           }
-          store_row_bf16<HW>(sHs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, h1);
-          store_row_bf16<HW>(sHs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, h2);
-          fence_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(hs_full);
         }
         // ---- P2 (one slice per tile): output layer and its delta -> Ds ----
-        if (slice == (t & 3)) {
-          mbar_wait(d2_full, ph);
-          tc_fence_after();
-          uint32_t d0[ON], d1[ON], d2[ON];
-          const uint32_t ta = tmem_base + lane_base + C::kDS;
-          tmem_ld16(ta, d0); tmem_ld16(ta + ON, d1); tmem_ld16(ta + 2 * ON, d2);
-          tmem_ld_wait();
-          float dhi[ON], dlo[ON];
 #pragma unroll
-          for (int o = 0; o < ON; ++o) {
-            float dv = 0.f;
-            if (o < O && y >= 0) {
-              float tt = (__uint_as_float(d0[o]) + __uint_as_float(d1[o])) + __uint_as_float(d2[o]);
-              if (!p.fold_bias) tt += __ldg(p.bias2 + (int64_t)pos * ON + o);
-              const float out = rcp_approx(1.0f + ex2_approx(fminf(tt, 60.0f)));
-              dv = ((o == y ? 1.0f : 0.0f) - out) * (out * (1.0f - out));     // LG:100
-              accB2[o] += dv;
+        for (int b = 0; b < 2; ++b) {
+          if (b < nb && slice == ((2 * q + b) & 3)) {
+            mbar_wait(&d2_full[b], phb[b]);
+            tc_fence_after();
+            uint32_t d0[ON], d1[ON], d2[ON];
+            const uint32_t ta = tmem_base + lane_base + C::kDS + b * 64;
+            tmem_ld16(ta, d0); tmem_ld16(ta + ON, d1); tmem_ld16(ta + 2 * ON, d2);
+            tmem_ld_wait();
+            float dhi[ON], dlo[ON];
+#pragma unroll
+            for (int o = 0; o < ON; ++o) {
+              float dv = 0.f;
+              if (o < O && y[b] >= 0) {
+                float tt = (__uint_as_float(d0[o]) + __uint_as_float(d1[o])) + __uint_as_float(d2[o]);
+                if (!p.fold_bias) tt += __ldg(p.bias2 + (int64_t)pos * ON + o);
+                const float out = rcp_approx(1.0f + ex2_approx(fminf(tt, 60.0f)));
+                dv = ((o == y[b] ? 1.0f : 0.0f) - out) * (out * (1.0f - out));     // LG:100
+                accB2[o] += dv;
+              }
+              split2(dv, dhi[o], dlo[o]);
             }
-            split2(dv, dhi[o], dlo[o]);
+            store_row_bf16<ON>(sDs, row_in_tile, 32 * b, dhi);
+            store_row_bf16<ON>(sDs, row_in_tile, 32 * b + ON, dlo);
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ds_full[b]);
           }
-          store_row_bf16<ON>(sDs, row_in_tile, 0, dhi);
-          store_row_bf16<ON>(sDs, row_in_tile, ON, dlo);
-          fence_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(ds_full);
         }
         // ---- P3: dh = (do . W2^T) h (1 - h), pieces -> Hs ----
-        {
-          mbar_wait(d3_full, ph);
-          tc_fence_after();
-          uint32_t zr[HW];
-          tmem_ldN<HW>(tmem_base + lane_base + (uint32_t)(C::kDS + slice * HW), zr);
-          tmem_ld_wait();
-          float g1[HW], g2[HW];
 #pragma unroll
-          for (int j = 0; j < HW; ++j) split2(__uint_as_float(zr[j]) * (h[j] * (1.0f - h[j])), g1[j], g2[j]);   // LG:101
-          store_row_bf16<HW>(sHs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, g1);
-          store_row_bf16<HW>(sHs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, g2);
-          fence_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dh_full);
+        for (int b = 0; b < 2; ++b) {
+          if (b < nb) {
+            uint8_t* hs = sHs + b * C::kHsBytes;
+            mbar_wait(&d3_full[b], phb[b]);
+            phb[b] ^= 1;
+            tc_fence_after();
+            uint32_t zr[HW];
+            tmem_ldN<HW>(tmem_base + lane_base + (uint32_t)(C::kDS + b * 64 + slice * HW), zr);
+            tmem_ld_wait();
+            float g1[HW], g2[HW];
+#pragma unroll
+            for (int j = 0; j < HW; ++j) split2(__uint_as_float(zr[j]) * (h[b][j] * (1.0f - h[b][j])), g1[j], g2[j]);   // LG:101
+            store_row_bf16<HW>(hs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, g1);
+            store_row_bf16<HW>(hs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, g2);
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dh_full[b]);
+          }
         }
       }
       // ---- end of the chain: fold the accumulators into one fp32 gradient vector ----
@@ -414,16 +446,21 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
             }
           }
         }
-        // G2: TMEM lane m = [h1 (HP) | h2 (HP)] hidden index; columns [do_hi (16) | do_lo (16)]; slice s reads 8 of the 32
+        // G2[b]: TMEM lane m = [h1 (HP) | h2 (HP)] hidden index; columns 32 b + [do_hi (16) | do_lo (16)]; slice s reads 8 of the 32
         const int hh2 = m < HP ? m : m - HP;
-        uint32_t r2[8];
-        tmem_ld8(tmem_base + lane_base + (uint32_t)(C::kG2 + slice * 8), r2);
-        tmem_ld_wait();
-        if (m < 2 * HP && hh2 < H) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int n = slice * 8 + j, o = n & 15;
-            if (o < O) atomicAdd(&sGrad[D * H + hh2 * O + o], __uint_as_float(r2[j]));   // LG:102: W2 += h^T do
+        for (int b = 0; b < 2; ++b) {
+          if (b == 0 || n_tiles > 1) {
+            uint32_t r2[8];
+            tmem_ld8(tmem_base + lane_base + (uint32_t)(C::kG2 + b * 64 + 32 * b + slice * 8), r2);
+            tmem_ld_wait();
+            if (m < 2 * HP && hh2 < H) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int n = slice * 8 + j, o = n & 15;
+                if (o < O) atomicAdd(&sGrad[D * H + hh2 * O + o], __uint_as_float(r2[j]));   // LG:102: W2 += h^T do
+              }
+            }
           }
         }
 #pragma unroll
