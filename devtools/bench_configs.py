@@ -70,5 +70,22 @@ if "c5" in which:
         print(json.dumps(out), flush=True)
         del eng, prob
         torch.cuda.empty_cache()
+if "c2" in which:
+    # C2: Ionosphere 34-50-2, 245 train / 109 test rows, 10 replicas, Langevin-gradient PT (reference-exact per-row SGD)
+    # with the surrogate interval enabled and the PyTorch surrogate trainer in the loop, through the class surface
+    from sapt_b200.parallel_tempering import ParallelTempering
+    D, H, O, R, S = 34, 50, 2, 10, 400
+    rs = np.random.RandomState(7)
+    mk = lambda n: np.concatenate([rs.standard_normal((n, D)), rs.randint(0, O, n)[:, None].astype(np.float64)], axis=1)
+    tr, te = mk(245), mk(109)
+    for use_sur in (False, True):
+        pt = ParallelTempering(use_sur, True, 0.01, False, tr, te, [D, H, O], R, 4.0, R * S, 100000, 50, 0.5, "", "", 1, variant="lg", seed=3)
+        pt.initialize_chains(0.25)
+        torch.cuda.synchronize(); t0 = time.time()
+        pt.run_chains()
+        torch.cuda.synchronize(); dt = time.time() - t0
+        out[f"C2 ionosphere-shape 34-50-2, 245+109 rows, 10 chains x {S} samples, Langevin (exact SGD) p=0.5, surrogate {'on (interval 50, prob 0.5, torch trainer)' if use_sur else 'off'}"] = dict(
+            wall_s=dt, steps_per_s=(S - 1) / dt, samples_per_s=R * (S - 1) / dt)
+        print(json.dumps(out), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
