@@ -78,6 +78,9 @@ if "c2" in which:
     rs = np.random.RandomState(7)
     mk = lambda n: np.concatenate([rs.standard_normal((n, D)), rs.randint(0, O, n)[:, None].astype(np.float64)], axis=1)
     tr, te = mk(245), mk(109)
+    # one short untimed run first: the first torch matmul of a process loads cuBLAS (~3 s), which is not the workload
+    warm = ParallelTempering(True, True, 0.01, False, tr, te, [D, H, O], R, 4.0, R * 120, 100000, 50, 0.5, "", "", 1, variant="lg", seed=3)
+    warm.initialize_chains(0.25); warm.run_chains(); torch.cuda.synchronize()
     for use_sur in (False, True):
         pt = ParallelTempering(use_sur, True, 0.01, False, tr, te, [D, H, O], R, 4.0, R * S, 100000, 50, 0.5, "", "", 1, variant="lg", seed=3)
         pt.initialize_chains(0.25)

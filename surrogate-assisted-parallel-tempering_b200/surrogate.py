@@ -17,19 +17,24 @@ from .engine import SURROGATE_HIDDEN
 
 
 class SurrogateTrainer:
-    def __init__(self, P: int, topology_id: int, device, seed: int = 0, epochs: int = 20, batch_size: int = 50):
+    """`graph=True` (default on CUDA devices) replays ONE captured CUDA graph per full mini-batch — forward, backward
+    and the Adam update — instead of ~40 eager launches; the arithmetic is the same."""
+
+    def __init__(self, P: int, topology_id: int, device, seed: int = 0, epochs: int = 20, batch_size: int = 50, graph: Optional[bool] = None):
         self.P = P
         self.h1, self.h2 = SURROGATE_HIDDEN[int(topology_id)]
-        self.device = device
+        self.device = torch.device(device)
         self.epochs, self.batch_size = epochs, batch_size
         self.gen = torch.Generator(device="cpu").manual_seed(seed)
         self.params: Optional[Dict[str, torch.Tensor]] = None
         self.train_mse = []
+        self.use_graph = (self.device.type == "cuda") if graph is None else bool(graph)
+        self._opt = None
+        self._graph = None
 
-    def _init_params(self):
-        def uni(*shape):
-            return ((torch.rand(*shape, generator=self.gen) - 0.5) * 0.1).to(self.device).requires_grad_(True)
-        z = lambda n: torch.zeros(n, device=self.device, requires_grad=True)
+    def _init_values(self):
+        uni = lambda *shape: ((torch.rand(*shape, generator=self.gen) - 0.5) * 0.1).to(self.device)
+        z = lambda n: torch.zeros(n, device=self.device)
         return {"W1": uni(self.P, self.h1), "b1": z(self.h1), "W2": uni(self.h1, self.h2), "b2": z(self.h2),
                 "W3": uni(self.h2, 1), "b3": z(1)}
 
@@ -39,6 +44,53 @@ class SurrogateTrainer:
         a = torch.relu(a @ p["W2"] + p["b2"])
         return torch.sigmoid(a @ p["W3"] + p["b3"]).squeeze(-1)
 
+    def _reset(self, fresh: bool):
+        """Parameter tensors and the optimizer are created once (a captured graph holds their addresses); a fresh
+        model re-draws the values in place, and every training starts from zeroed Adam moments like a newly
+        compiled Keras model (_revamp.py:265)."""
+        if self.params is None:
+            self.params = {k: v.requires_grad_(True) for k, v in self._init_values().items()}
+            self._opt = torch.optim.Adam(list(self.params.values()), lr=1e-3, eps=1e-7, capturable=self.use_graph)
+        elif fresh:
+            with torch.no_grad():
+                for k, v in self._init_values().items():
+                    self.params[k].copy_(v)
+        for st in self._opt.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+
+    def _step_eager(self, xb, yb):
+        self._opt.zero_grad(set_to_none=True)
+        loss = torch.mean((self.forward(self.params, xb) - yb) ** 2)
+        loss.backward()
+        self._opt.step()
+
+    def _capture(self):
+        B = self.batch_size
+        self._xb = torch.zeros((B, self.P), dtype=torch.float32, device=self.device)
+        self._yb = torch.zeros(B, dtype=torch.float32, device=self.device)
+        saved = {k: v.detach().clone() for k, v in self.params.items()}
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):                       # warm-up on a side stream (allocator, Adam state, autograd buffers)
+                self._step_eager(self._xb, self._yb)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        self._opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self._graph):
+            loss = torch.mean((self.forward(self.params, self._xb) - self._yb) ** 2)
+            loss.backward()
+            self._opt.step()
+        with torch.no_grad():                        # undo the warm-up steps
+            for k, v in saved.items():
+                self.params[k].copy_(v)
+        for st in self._opt.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+
     def __call__(self, batch: np.ndarray, signature: int):
         """batch = [n, P+1] rows (theta', L_untempered) of one interval (device tensor or numpy). Returns numpy weights."""
         batch = torch.as_tensor(batch, device=self.device)
@@ -46,10 +98,10 @@ class SurrogateTrainer:
         Y = batch[:, self.P].to(torch.float64)
         min_y, max_y = 2.0 * float(Y.min().item()), -1.0            # _revamp.py:989-993 (every call)
         Yn = ((Y - min_y) / (max_y - min_y)).to(torch.float32)       # _revamp.py:1024
-        if signature == 1 or self.params is None:                   # fresh model, else warm start (_revamp.py:247-255)
-            self.params = self._init_params()
+        self._reset(fresh=(signature == 1 or self.params is None))  # fresh model, else warm start (_revamp.py:247-255)
         params = self.params
-        opt = torch.optim.Adam(list(params.values()), lr=1e-3, eps=1e-7)
+        if self.use_graph and self._graph is None:
+            self._capture()
         n = X.shape[0]
         n_val = int(n * 0.1)
         n_tr = n - n_val
@@ -59,10 +111,11 @@ class SurrogateTrainer:
             perm = torch.randperm(n_tr, generator=self.gen).to(self.device)
             for s in range(0, n_tr, self.batch_size):
                 idx = perm[s:s + self.batch_size]
-                opt.zero_grad(set_to_none=True)
-                loss = torch.mean((self.forward(params, Xt[idx]) - Yt[idx]) ** 2)
-                loss.backward()
-                opt.step()
+                if self._graph is not None and idx.numel() == self.batch_size:
+                    self._xb.copy_(Xt[idx]); self._yb.copy_(Yt[idx])
+                    self._graph.replay()
+                else:
+                    self._step_eager(Xt[idx], Yt[idx])
             if n_val > 0:
                 with torch.no_grad():
                     vl = float(torch.mean((self.forward(params, Xv) - Yv) ** 2))
@@ -74,4 +127,4 @@ class SurrogateTrainer:
                         break
         with torch.no_grad():
             self.train_mse.append(float(torch.mean((self.forward(params, X) - Yn) ** 2)))  # _revamp.py:268-285
-        return {k: v.detach().cpu().numpy() for k, v in params.items()}
+        return {k: v.detach().cpu().numpy().copy() for k, v in params.items()}   # copy: on a CPU device .numpy() aliases the parameter

@@ -594,6 +594,37 @@ def test_cli_reference_command_line(lib, tmp_path, monkeypatch):
     assert os.path.isfile(tmp_path / "master_result_file.txt")
 
 
+def test_surrogate_trainer_graph_equals_eager_and_feeds_predict_kernel(lib):
+    """N1 on the device: the CUDA-graph replay of one optimizer step gives the same weights as the eager loop, and the
+    exported weights are what sapt_surrogate_predict consumes."""
+    from sapt_b200.surrogate import SurrogateTrainer
+    rs = np.random.RandomState(1)
+    P, n = 146, 777
+    X = rs.standard_normal((n, P)) * 0.3
+    Y = -300.0 - 40.0 * np.tanh(X[:, 0] - 0.5 * X[:, 1]) - 10.0 * X[:, 2] ** 2
+    batch = torch.as_tensor(np.concatenate([X, Y[:, None]], axis=1)).cuda()
+    # a few optimizer steps: the replayed graph and the eager loop agree to rounding
+    a = SurrogateTrainer(P, 1, "cuda", seed=9, epochs=1, graph=True)
+    b = SurrogateTrainer(P, 1, "cuda", seed=9, epochs=1, graph=False)
+    wa, wb = a(batch, 1), b(batch, 1)
+    for k in wa:
+        np.testing.assert_allclose(wa[k], wb[k], rtol=0, atol=3e-5, err_msg=k)
+    # full trainings (Adam amplifies rounding differences between the capturable and the host-scalar update, so the
+    # weights drift apart; the fit they reach is the same)
+    a = SurrogateTrainer(P, 1, "cuda", seed=9, graph=True)
+    b = SurrogateTrainer(P, 1, "cuda", seed=9, graph=False)
+    for sig in (1, 2):
+        wa, wb = a(batch, sig), b(batch, sig)
+    assert a.train_mse[-1] < a.train_mse[0] and abs(a.train_mse[-1] - b.train_mse[-1]) < 0.2 * b.train_mse[-1] + 1e-5
+    th = torch.as_tensor(X[:64].astype(np.float32)).cuda()
+    w = {k: torch.as_tensor(np.ascontiguousarray(v, dtype=np.float32)).reshape(-1).cuda() for k, v in wa.items()}
+    out = torch.zeros(64, dtype=torch.float32, device="cuda")
+    lib.check(lib.lib().sapt_surrogate_predict(th.data_ptr(), th.stride(0), 64, P, None, None, w["W1"].data_ptr(), w["b1"].data_ptr(), 64,
+                                               w["W2"].data_ptr(), w["b2"].data_ptr(), 16, w["W3"].data_ptr(), w["b3"].data_ptr(), out.data_ptr(), None))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), so.surrogate_forward(X[:64].astype(np.float32), wa).reshape(-1), rtol=2e-5, atol=2e-6)
+
+
 def test_local_surrogate_fork_class_surface(lib):
     """The fork's 15-argument ParallelTempering (LS:894, no surrogate_topology) selects variant 'ls' and runs on Philox
     streams: surrogate steps happen after the first training and their proposals carry prediction * limit."""

@@ -50,3 +50,33 @@ def test_result_row_layout():
     row = result_row(5, 1000, 2, 5, 0.1, 0.5, False, 0.01, acc_tr, acc_te, 12.5, 70.0, 3.0, 1.5, 90)
     assert row.shape == (19,)
     assert row[0] == 5 and row[8] == 91.0 and row[10] == 92.0 and row[11] == 81.0 and row[14] == 12.5 and row[18] == 90
+
+
+def test_surrogate_trainer_learns_and_warm_starts():
+    """N1 (host side, CPU here): the PyTorch restatement of surrogate.train (_revamp.py:235-295). Keras itself is
+    not installed, so this checks behaviour, not bits: shapes, the normalisation of _revamp.py:989-1024, that the
+    fit reduces the error of a smooth target, that signature > 1 warm-starts, and that the exported weights are
+    what oracle.surrogate_forward (the predict path) consumes."""
+    import torch
+    from oracle import sapt_oracle as so
+    from sapt_b200.surrogate import SurrogateTrainer
+    rs = np.random.RandomState(0)
+    P, n = 30, 600
+    X = rs.standard_normal((n, P)) * 0.5
+    Y = -300.0 - 40.0 * np.tanh(X[:, 0] - 0.5 * X[:, 1]) - 10.0 * X[:, 2] ** 2      # a smooth "log-likelihood"
+    batch = np.concatenate([X, Y[:, None]], axis=1)
+    tr = SurrogateTrainer(P, 1, "cpu", seed=3, epochs=20)
+    w1 = tr(batch, 1)
+    assert {k: v.shape for k, v in w1.items()} == {"W1": (P, 64), "b1": (64,), "W2": (64, 16), "b2": (16,), "W3": (16, 1), "b3": (1,)}
+    min_y, max_y = 2.0 * Y.min(), -1.0
+    yn = (Y - min_y) / (max_y - min_y)
+    pred = so.surrogate_forward(X.astype(np.float32), w1).reshape(-1)
+    mse1 = float(np.mean((pred - yn) ** 2))
+    np.testing.assert_allclose(mse1, tr.train_mse[-1], rtol=1e-3)
+    assert mse1 < 0.5 * float(np.var(yn))                                            # better than predicting the mean
+    w2 = tr(batch, 2)                                                                # warm start: keeps improving
+    assert tr.train_mse[-1] < tr.train_mse[0]
+    tr2 = SurrogateTrainer(P, 1, "cpu", seed=3, epochs=20)
+    assert np.array_equal(tr2(batch, 1)["W1"], w1["W1"])                             # deterministic given the seed
+    w3 = tr(batch, 1)                                                                # signature 1 again: fresh model
+    assert not np.array_equal(w3["W1"], w2["W1"])
