@@ -22,7 +22,7 @@
 // fp32-grade accuracy from bf16 operands as in sapt_loglik_tc2.cu: x = x1 + x2 (+ x3 dropped: 2^-17), w = w1 + w2 + w3,
 // h, do, dh = two pieces each; the cross terms kept are listed at each MMA.
 //
-// CTA = (row chunk, chain group); chains of the group run one after the other (the accumulators are per chain).
+// Work item = (chain, row chunk); one CTA per SM takes items round-robin, one after the other (the accumulators are per item).
 // Warp 16 lane 0: TMA producer (X tile ring; per-chain weight panels). Warp 17: TMEM alloc + MMA issue. Warps 0-15:
 // epilogue, warp (quarter q = TMEM lanes 32q.., slice s = HP/4 hidden units); P2 of tile t is done by slice t % 4.
 #include <algorithm>
@@ -81,7 +81,7 @@ struct Params {
   const int32_t* n_rows; int R;
   int D, H, O, fold_bias;
   int tiles_per_chunk; int64_t n_tiles;
-  int chains_per_cta;
+  int n_chunks;                       // work item = (chain, row chunk); item i runs on CTA i % gridDim.x
   float* part;                        // [chunk][R][P]
   int P;
 };
@@ -194,12 +194,19 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nact = p.n_rows ? *p.n_rows : p.R;
-  const int pos0 = blockIdx.y * p.chains_per_cta;
-  if (pos0 >= nact) return;
-  const int n_chains = min(p.chains_per_cta, nact - pos0);
-  const int64_t t_begin = (int64_t)blockIdx.x * p.tiles_per_chunk;
-  const int n_tiles = (int)max((int64_t)0, min(t_begin + (int64_t)p.tiles_per_chunk, p.n_tiles) - t_begin);
-  const int n_pairs = (n_tiles + 1) / 2;      // tile 2 q uses buffer 0, tile 2 q + 1 buffer 1 (absent in a ragged last pair)
+  // work items (chain, row chunk), chain fastest so that CTAs running side by side stream the same rows through L2;
+  // the number of active chains is only known on the device, so the items are dealt round-robin here
+  const int n_items = nact * p.n_chunks;
+  if ((int)blockIdx.x >= n_items) return;
+  struct Item { int pos, chunk, n_tiles, n_pairs; int64_t t_begin; };
+  auto get_item = [&](int item) {
+    Item it;
+    it.pos = item % nact; it.chunk = item / nact;
+    it.t_begin = (int64_t)it.chunk * p.tiles_per_chunk;
+    it.n_tiles = (int)max((int64_t)0, min(it.t_begin + (int64_t)p.tiles_per_chunk, p.n_tiles) - it.t_begin);
+    it.n_pairs = (it.n_tiles + 1) / 2;      // tile 2 q uses buffer 0, tile 2 q + 1 buffer 1 (absent in a ragged last pair)
+    return it;
+  };
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
@@ -224,13 +231,16 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t use[2] = {0, 0};               // how often each X buffer has been filled
-      for (int c = 0; c < n_chains; ++c) {
+      for (int item = blockIdx.x, c = 0; item < n_items; item += gridDim.x, ++c) {
+        const Item w = get_item(item);
+        const int n_tiles = w.n_tiles;
+        const int64_t t_begin = w.t_begin;
         if (c > 0) mbar_wait<500>(w_free, (c - 1) & 1);
         mbar_expect_tx(w_full, C::kB1Bytes + C::kW2Bytes + C::kW2TBytes);
 #pragma unroll
-        for (int kb = 0; kb < KBA; ++kb) tma_load_2d(&map_b1, w_full, sB1 + kb * HP * 128, kb * 64, (pos0 + c) * HP);
-        tma_load_2d(&map_w2, w_full, sW2, 0, (pos0 + c) * N2);
-        tma_load_2d(&map_w2t, w_full, sW2T, 0, (pos0 + c) * HP);
+        for (int kb = 0; kb < KBA; ++kb) tma_load_2d(&map_b1, w_full, sB1 + kb * HP * 128, kb * 64, w.pos * HP);
+        tma_load_2d(&map_w2, w_full, sW2, 0, w.pos * N2);
+        tma_load_2d(&map_w2t, w_full, sW2T, 0, w.pos * HP);
         for (int t = 0; t < n_tiles; ++t) {
           const int b = t & 1;
           mbar_wait<500>(&empty_a[b], (use[b] & 1) ^ 1);
@@ -258,9 +268,11 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
       auto b1_chunk = [&](int chunk) { return b1a + (uint32_t)(chunk >> 2) * (HP * 128) + (uint32_t)(chunk & 3) * 32; };
       uint32_t use[2] = {0, 0};
       uint32_t phb[2] = {0, 0};   // parity of the per-buffer barriers: they complete once per pair that uses the buffer
-      for (int c = 0; c < n_chains; ++c) {
+      for (int item = blockIdx.x, c = 0; item < n_items; item += gridDim.x, ++c) {
+        const Item w = get_item(item);
+        const int n_tiles = w.n_tiles, n_pairs = w.n_pairs;
         mbar_wait(w_full, c & 1);
-        if (c > 0) mbar_wait(g_free, (c - 1) & 1);     // accumulators of the previous chain have been read out
+        if (c > 0) mbar_wait(g_free, (c - 1) & 1);     // accumulators of the previous item have been read out
         for (int q = 0; q < n_pairs; ++q) {
           const int nb = (2 * q + 1 < n_tiles) ? 2 : 1;
           // ---- MMA-1: x1w1 x1w2 x2w1 x1w3 x2w2 + bias. x chunks: x1 = [0, DKC), x2 = [DKC, 2 DKC) ----
@@ -329,8 +341,10 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
     const int O = p.O, D = p.D, H = p.H;
     float* sGrad = reinterpret_cast<float*>(sHs);        // [P] fp32 at the end of a chain (Hs is idle then)
     uint32_t phb[2] = {0, 0};
-    for (int c = 0; c < n_chains; ++c) {
-      const int pos = pos0 + c;
+    for (int item = blockIdx.x, c = 0; item < n_items; item += gridDim.x, ++c) {
+      const Item w = get_item(item);
+      const int pos = w.pos, n_tiles = w.n_tiles, n_pairs = w.n_pairs;
+      const int64_t t_begin = w.t_begin;
       float accB2[ON];
 #pragma unroll
       for (int o = 0; o < ON; ++o) accB2[o] = 0.f;
@@ -471,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
       }
       tc_fence_before();
       epi_sync();
-      float* dst = p.part + ((int64_t)blockIdx.x * p.R + pos) * P;
+      float* dst = p.part + ((int64_t)w.chunk * p.R + pos) * P;
       for (int i = threadIdx.x; i < P; i += 32 * kEpiWarps) dst[i] = sGrad[i];
       epi_sync();
       fence_async_smem();     // Hs goes back to being an MMA operand
@@ -522,11 +536,11 @@ int launch_langevin_tc(sapt_problem* p, const float* theta, float* theta_gd, int
   const int KROW = ((48 * DKC + 16 + 63) / 64) * 64;
   const int P = p->P;
   const int64_t n_tiles = ds.n_pad / kTileM;
-  // CTAs = row chunks x chain groups; a chain group runs its chains one after the other
-  int groups = std::min(R, std::max(1, p->num_sms / 8));
-  int chains_per_cta = (R + groups - 1) / groups;
-  groups = (R + chains_per_cta - 1) / chains_per_cta;
-  int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_tiles / 8, (p->num_sms * 2 + groups - 1) / groups));
+  // Work items = (chain, row chunk), dealt round-robin to one CTA per SM inside the kernel (the number of active
+  // chains is a device-side value). ~16 items per CTA at the host-side bound R keep the load balanced to a few
+  // percent even when only half the chains take a Langevin step; chunks stay >= 32 tiles so that the per-item
+  // cost (weight panels, folding the accumulators) is amortised.
+  int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(1, n_tiles / 32), ((int64_t)16 * p->num_sms + R - 1) / R));
   const int tiles_per_chunk = (int)((n_tiles + n_chunks - 1) / n_chunks);
   n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
 
@@ -551,8 +565,8 @@ int launch_langevin_tc(sapt_problem* p, const float* theta, float* theta_gd, int
   if ((rc = tc_make_map_2d(&mw2t, w2timg, 64, (uint64_t)R * HP, (uint32_t)HP))) return rc;
   Params a{};
   a.y = ds.y; a.bias2 = bias2; a.n_rows = n_rows; a.R = R; a.D = p->D; a.H = p->H; a.O = p->O; a.fold_bias = (p->H < HP) ? 1 : 0;
-  a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.chains_per_cta = chains_per_cta; a.part = part; a.P = P;
-  dim3 grid((unsigned)n_chunks, (unsigned)groups);
+  a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.n_chunks = (int)n_chunks; a.part = part; a.P = P;
+  dim3 grid((unsigned)std::min<int64_t>(p->num_sms, (int64_t)R * n_chunks));
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(ds.tmap);
 #define SAPT_LT(H_, K_) if (HP == H_ && DKC == K_) rc = launch_variant<H_, K_>(ma, mb1, mw2, mw2t, a, grid, st); else
   SAPT_LT(16, 1) SAPT_LT(16, 2) SAPT_LT(16, 3) SAPT_LT(16, 4) SAPT_LT(32, 1) SAPT_LT(32, 2) SAPT_LT(32, 3) SAPT_LT(32, 4)
