@@ -182,6 +182,7 @@ class PTEngine:
             self.train_theta = torch.zeros((self.Rg, self.train_cap, self.P), dtype=torch.float32, device=dev)
             self.train_L = torch.zeros((self.Rg, self.train_cap), **f64)
             self.train_count = torch.zeros(self.Rg, **i32)
+        self._train_synced = False
         self.surr_batches: List[torch.Tensor] = []   # device tensors; keep_batches=False drops them after training
         # injected streams (parity tests): numpy arrays indexed [step, chain(, P)]
         self.inj = None
@@ -275,6 +276,7 @@ class PTEngine:
         if self._graph_mode:
             i = 0  # the device counter is advanced after every captured step: the absolute step is *step_dev
         use_sur = bool(cfg.use_surrogate)
+        self._train_synced = False     # this step may append training rows on the hosting rank
         self.counters[:3].zero_()
         gate = cfg.swap_interval if sp.gate_on_swap_interval else cfg.surrogate_interval
         a = _lib.ProposeArgs()
@@ -394,6 +396,7 @@ class PTEngine:
         if self.Rg < 2:
             return
         self.sync_slots()
+        self._sync_training_buffers()
         if self.cfg.world > 1 and self.hist is not None and "pos_w" in self.hist:
             # a rejected step copies pos_w history row i (RV:608): the row must follow the slot across ranks
             import torch.distributed as dist
@@ -416,18 +419,27 @@ class PTEngine:
         self.sweep_count += 1
         self.total_swap_proposals += self.Rg - 1
 
+    def _sync_training_buffers(self):
+        """Multi-rank: a chain's training rows are appended on whichever rank hosts the chain. Taking every chain's
+        buffer from its CURRENT host (masked all-reduce, in place) makes the buffers complete and identical on all
+        ranks; it must run before an exchange re-binds the chains (the rows of the interval were written under the
+        old binding) and before the rows are handed to the trainer."""
+        if self.cfg.world == 1 or self.train_theta is None or self._train_synced:
+            return
+        import torch.distributed as dist
+        mask = self._hosted_mask()
+        cnt = self.train_count.double() * mask
+        self.train_theta.mul_(mask[:, None, None].to(self.train_theta.dtype)); self.train_L.mul_(mask[:, None])
+        dist.all_reduce(cnt, group=self.pg); dist.all_reduce(self.train_theta, group=self.pg); dist.all_reduce(self.train_L, group=self.pg)
+        self.train_count.copy_(cnt.round().to(torch.int32))
+        self._train_synced = True
+
     def gather_training_rows(self) -> torch.Tensor:
         """(theta', L_untempered) rows of the interval's true steps, chain by chain (RW:1105-1116), as ONE device
         tensor [n, P+1] (fp64): the training set never visits the host (the reference pickles it through queues)."""
+        self._sync_training_buffers()
         cnt = self.train_count
         th, tl = self.train_theta, self.train_L
-        if self.cfg.world > 1:
-            import torch.distributed as dist
-            mask = self._hosted_mask()
-            cnt = (cnt.double() * mask)
-            th = th * mask[:, None, None].float(); tl = tl * mask[:, None]
-            dist.all_reduce(cnt, group=self.pg); dist.all_reduce(th, group=self.pg); dist.all_reduce(tl, group=self.pg)
-            cnt = cnt.round().to(torch.int32)
         cap = self.train_cap
         j = torch.arange(cap, device=self.dev)[None, :]
         valid = j < cnt.long()[:, None]                       # [Rg, cap]
@@ -504,6 +516,7 @@ class PTEngine:
     def fused_steps(self, i0: int, n: int):
         """Steps i0 .. i0+n-1 of every local chain in ONE launch (sapt_fused_steps)."""
         cfg, sp = self.cfg, self.spec
+        self._train_synced = False
         f = _lib.FusedArgs()
         f.theta = self.theta.data_ptr(); f.ld = self.ld; f.R = self.R; f.P = self.P
         f.step_w = cfg.step_w; f.sigma_squared = cfg.sigma_squared; f.seed = cfg.seed & 0xFFFFFFFF

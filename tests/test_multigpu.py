@@ -22,6 +22,9 @@ def _cfg(world, rank, variant="rw"):
     if variant == "ls":   # local-surrogate fork: Philox streams, networks and history windows follow the chains across ranks
         return EngineConfig(variant="ls", samples=40, swap_interval=4, surrogate_interval=10, surrogate_prob=0.5,
                             use_surrogate=True, seed=22, record_history=True, record_pos=False, rank=rank, world=world)
+    if variant == "rw_sur":   # global surrogate: the interval's training rows of all chains are assembled on every rank
+        return EngineConfig(variant="rw", samples=40, swap_interval=4, surrogate_interval=4, surrogate_prob=0.5, use_surrogate=True,
+                            surrogate_topology=1, seed=23, record_history=True, record_pos=True, rank=rank, world=world)
     return EngineConfig(variant="rw", samples=30, swap_interval=3, surrogate_interval=3, surrogate_prob=0.0,
                         use_surrogate=False, seed=21, record_history=True, record_pos=True, rank=rank, world=world)
 
@@ -38,7 +41,12 @@ def _run(rank, world, port, q, variant="rw"):
     g = gu.load("unit_cancer")
     topo = [int(v) for v in g["topology"]]
     prob = Problem(topo, g["train"], g["test"], device=rank)
-    eng = PTEngine(prob, assign_temperatures(8, 4.0), _cfg(world, rank, variant))
+    trainer = None
+    if variant == "rw_sur":
+        from oracle import sapt_oracle as so      # fixed MLPs stand in for the trained surrogate (one per signature)
+        ws = [so.make_surrogate_weights(prob.P, 1, 50 + s) for s in range(12)]
+        trainer = lambda batch, sig: ws[sig - 1]
+    eng = PTEngine(prob, assign_temperatures(8, 4.0), _cfg(world, rank, variant), surrogate_trainer=trainer)
     eng.initialize(g["W"][0])
     eng.run()
     torch.cuda.synchronize()
@@ -47,7 +55,11 @@ def _run(rank, world, port, q, variant="rw"):
     if variant == "ls":
         keys = ("accepted", "accept_list", "lhood_list", "acc_train", "naccept", "row_of_slot", "surg_likeh_list", "is_surrogate_step",
                 "ls_weights", "ls_limit")
+    if variant == "rw_sur":
+        keys = keys + ("is_surrogate_step", "surg_likeh_list")
     out = {k: res[k] for k in keys}
+    if variant == "rw_sur":
+        out["surr_batches"] = res["surr_batches"]
     out["swaps"] = np.array([s for s in res["swap_decisions"]])
     out["num_swap"] = res["num_swap"]
     if world > 1:
@@ -97,3 +109,24 @@ def test_two_gpu_local_surrogate_equals_one_gpu():
     np.testing.assert_allclose(b[~np.isnan(a)], a[~np.isnan(a)], rtol=1e-12)
     np.testing.assert_allclose(two["lhood_list"][np.isfinite(one["lhood_list"])], one["lhood_list"][np.isfinite(one["lhood_list"])], rtol=1e-12)
     np.testing.assert_allclose(two["ls_limit"], one["ls_limit"], rtol=1e-12)
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_global_surrogate_equals_one_gpu():
+    """Random-walk PT with the global surrogate over two ranks: the training rows every rank assembles at the
+    rendezvous (RW:1105-1116) and every decision that follows must equal the single-GPU run."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_run, args=(0, 1, 0, q, "rw_sur")); p.start(); one = q.get(timeout=300); p.join()
+    port = _free_port()
+    procs = [ctx.Process(target=_run, args=(r, 2, port, q, "rw_sur")) for r in range(2)]
+    for p in procs: p.start()
+    two = q.get(timeout=300)
+    for p in procs: p.join()
+    assert one["is_surrogate_step"].sum() > 0 and one["swaps"].sum() > 0
+    for k in ("accepted", "is_surrogate_step", "swaps", "row_of_slot", "naccept", "pos_w"):
+        assert np.array_equal(one[k], two[k]), k
+    assert len(one["surr_batches"]) == len(two["surr_batches"]) > 0
+    for a, b in zip(one["surr_batches"], two["surr_batches"]):
+        assert np.array_equal(a, b)
