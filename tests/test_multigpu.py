@@ -25,6 +25,10 @@ def _cfg(world, rank, variant="rw"):
     if variant == "rw_sur":   # global surrogate: the interval's training rows of all chains are assembled on every rank
         return EngineConfig(variant="rw", samples=40, swap_interval=4, surrogate_interval=4, surrogate_prob=0.5, use_surrogate=True,
                             surrogate_topology=1, seed=23, record_history=True, record_pos=True, rank=rank, world=world)
+    if variant == "lg_sur":   # Langevin fork: exchanges fall INSIDE a surrogate interval, training rows are captured by lg_first_eval
+        return EngineConfig(variant="lg", samples=36, swap_interval=3, surrogate_interval=5, surrogate_prob=0.4, use_surrogate=True,
+                            use_langevin=True, learn_rate=0.05, surrogate_topology=1, seed=24, record_history=True, record_pos=True,
+                            rank=rank, world=world)
     return EngineConfig(variant="rw", samples=30, swap_interval=3, surrogate_interval=3, surrogate_prob=0.0,
                         use_surrogate=False, seed=21, record_history=True, record_pos=True, rank=rank, world=world)
 
@@ -42,7 +46,7 @@ def _run(rank, world, port, q, variant="rw"):
     topo = [int(v) for v in g["topology"]]
     prob = Problem(topo, g["train"], g["test"], device=rank)
     trainer = None
-    if variant == "rw_sur":
+    if variant in ("rw_sur", "lg_sur"):
         from oracle import sapt_oracle as so      # fixed MLPs stand in for the trained surrogate (one per signature)
         ws = [so.make_surrogate_weights(prob.P, 1, 50 + s) for s in range(12)]
         trainer = lambda batch, sig: ws[sig - 1]
@@ -55,10 +59,10 @@ def _run(rank, world, port, q, variant="rw"):
     if variant == "ls":
         keys = ("accepted", "accept_list", "lhood_list", "acc_train", "naccept", "row_of_slot", "surg_likeh_list", "is_surrogate_step",
                 "ls_weights", "ls_limit")
-    if variant == "rw_sur":
+    if variant in ("rw_sur", "lg_sur"):
         keys = keys + ("is_surrogate_step", "surg_likeh_list")
     out = {k: res[k] for k in keys}
-    if variant == "rw_sur":
+    if variant in ("rw_sur", "lg_sur"):
         out["surr_batches"] = res["surr_batches"]
     out["swaps"] = np.array([s for s in res["swap_decisions"]])
     out["num_swap"] = res["num_swap"]
@@ -112,15 +116,17 @@ def test_two_gpu_local_surrogate_equals_one_gpu():
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_global_surrogate_equals_one_gpu():
-    """Random-walk PT with the global surrogate over two ranks: the training rows every rank assembles at the
+@pytest.mark.parametrize("variant", ["rw_sur", "lg_sur"])
+def test_two_gpu_global_surrogate_equals_one_gpu(variant):
+    """PT with the global surrogate over two ranks (random-walk fork: exchange and training share the rendezvous;
+    Langevin fork: exchanges inside a surrogate interval): the training rows every rank assembles at the
     rendezvous (RW:1105-1116) and every decision that follows must equal the single-GPU run."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    p = ctx.Process(target=_run, args=(0, 1, 0, q, "rw_sur")); p.start(); one = q.get(timeout=300); p.join()
+    p = ctx.Process(target=_run, args=(0, 1, 0, q, variant)); p.start(); one = q.get(timeout=300); p.join()
     port = _free_port()
-    procs = [ctx.Process(target=_run, args=(r, 2, port, q, "rw_sur")) for r in range(2)]
+    procs = [ctx.Process(target=_run, args=(r, 2, port, q, variant)) for r in range(2)]
     for p in procs: p.start()
     two = q.get(timeout=300)
     for p in procs: p.join()
