@@ -159,58 +159,100 @@ __global__ void advance_kernel(int32_t* counter, int delta) { *counter += delta;
 // the earlier pairs) competes with the message chain k+1 posted; the loser of the comparison stays at k, the
 // other is carried on. Chains are staged through shared memory in chunks so any R fits; thread 0 walks a chunk,
 // the CTA loads / scatters around it.
+// The walk itself must stay sequential, so everything that does not depend on the carried message is done by the
+// whole CTA beforehand: u < min(1, 0.5 exp(min(709, p - c)))  <=>  u < 1 and c < p - ln(2u), i.e. the exponential
+// of the reference's rule becomes one logarithm per pair computed in parallel (t = p - ln(2u)) and the serial
+// step is a compare + select (~25 cycles instead of ~280; the sweep over 65 536 chains went from 9.3 ms to <1 ms).
+// The two forms can differ only when u is within an ulp of the acceptance probability (a stated near-threshold
+// tie); u <= 0 keeps the literal formula, NaNs behave like Python's min(1, nan) == 1. The compare runs on
+// order-preserving int64 keys of the doubles (integer compare + selects; fp64 compares sit on the slow pipe).
 constexpr int kSweepChunk = 2048;
+
+// monotone map double -> int64 (non-NaN); the callers give NaN the key they need
+__device__ __forceinline__ long long order_key(double x) {
+  const long long b = __double_as_longlong(x);
+  return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
 
 __global__ void swap_sweep_kernel(int R, double* lik_post, const double* temperature, int32_t* row_of_slot, uint32_t flags,
                                   uint32_t seed, int sweep_base, const int32_t* sweep_dev, const double* u_inject,
                                   uint8_t* swapped, int32_t* num_swap, int32_t* src_slot, int row0, int R_local,
                                   int32_t* slot_of_row_local, int32_t* scratch_src /*[R]*/, double* scratch_post /*[R]*/) {
-  __shared__ double s_post[kSweepChunk];   // posted likelihood of chain k+1 (input) / of the message left at k (output)
-  __shared__ double s_u[kSweepChunk];
+  __shared__ long long s_kp[kSweepChunk];  // key of the likelihood chain k+1 posted; NaN -> smallest key (always swaps onward)
+  __shared__ long long s_kt[kSweepChunk];  // key of t = p - ln(2u); NaN -> largest key (swap); literal pairs: bits of u
   __shared__ int32_t s_src[kSweepChunk];   // output: which chain's message stays at position k
-  __shared__ uint8_t s_sw[kSweepChunk];
-  __shared__ double c_post;                // carried message
+  __shared__ uint8_t s_f[kSweepChunk];     // bit 0 = (u < 1), bit 1 = literal formula
+  __shared__ uint8_t s_sw[kSweepChunk];    // output: swapped
+  __shared__ long long c_key;              // carried message: key and chain
   __shared__ int c_src, c_ns;
   const int sweep = sweep_base + (sweep_dev ? *sweep_dev : 0);
   auto posted = [&](int k) {  // RW:623 posts likelihood*adapttemp ; LG:805 posts the tempered value
     return (flags & SAPT_F_POST_TEMPERED) ? lik_post[k] : lik_post[k] * temperature[k];
   };
-  if (threadIdx.x == 0) { c_post = posted(0); c_src = 0; c_ns = 0; }
+  auto pkey = [&](double v) { return (v != v) ? (long long)0x8000000000000000ULL : order_key(v); };
+  if (threadIdx.x == 0) { c_key = pkey(posted(0)); c_src = 0; c_ns = 0; }
   for (int k0 = 0; k0 < R - 1; k0 += kSweepChunk) {
     const int n = min(kSweepChunk, R - 1 - k0);
     __syncthreads();
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
       const int k = k0 + j;
-      s_post[j] = posted(k + 1);
-      s_u[j] = u_inject ? u_inject[k] : (double)philox_uniform(seed, SAPT_STREAM_SWAP, sweep, 0u, (uint32_t)k);
+      const double pk = posted(k + 1);
+      const double u = u_inject ? u_inject[k] : (double)philox_uniform(seed, SAPT_STREAM_SWAP, sweep, 0u, (uint32_t)k);
+      const bool literal = !(u > 0.0);
+      const double t = pk - log(2.0 * u);
+      s_kp[j] = pkey(pk);
+      s_kt[j] = literal ? __double_as_longlong(u) : ((t != t) ? 0x7fffffffffffffffLL : order_key(t));
+      s_f[j] = (uint8_t)((u < 1.0 ? 1 : 0) | (literal ? 2 : 0));
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      double cp = c_post; int cs = c_src; int ns = c_ns;
-      for (int j = 0; j < n; ++j) {
-        const double np_ = s_post[j];
-        const double d = fmin(709.0, np_ - cp);
-        double pr = 0.5 * exp(d);
-        if (d != d) pr = 1.0;  // min(1, nan) == 1 in Python
-        pr = fmin(1.0, pr);
-        const bool sw = s_u[j] < pr;
-        if (sw) { s_src[j] = k0 + j + 1; s_post[j] = np_; ++ns; }       // chain k+1's message drops to position k
-        else { s_src[j] = cs; s_post[j] = cp; cp = np_; cs = k0 + j + 1; } // carried message stays, k+1's is carried on
-        s_sw[j] = sw ? 1 : 0;
+      long long ck = c_key; int cs = c_src; int ns = c_ns;
+      constexpr int kB = 8;                    // operands of kB pairs are fetched before the dependent chain starts
+      for (int j0 = 0; j0 < n; j0 += kB) {
+        long long kp[kB], kt[kB]; int f[kB]; int src[kB]; uint8_t swv[kB];
+#pragma unroll
+        for (int e = 0; e < kB; ++e) {
+          const int j = min(j0 + e, n - 1);
+          kp[e] = s_kp[j]; kt[e] = s_kt[j]; f[e] = s_f[j];
+        }
+#pragma unroll
+        for (int e = 0; e < kB; ++e) {
+          const int k1 = k0 + j0 + e + 1;
+          bool sw;
+          if (f[e] & 2) {   // RW:886-888 literally (u <= 0)
+            const double cp = posted(cs), np_ = posted(min(k1, R - 1));
+            const double d = fmin(709.0, np_ - cp);
+            double pr = 0.5 * exp(d);
+            if (d != d) pr = 1.0;  // min(1, nan) == 1 in Python
+            pr = fmin(1.0, pr);
+            sw = __longlong_as_double(kt[e]) < pr;
+          } else {
+            sw = (f[e] & 1) && (ck < kt[e]);   // c < t; a NaN on either side swaps, like min(1, nan) == 1
+          }
+          if (j0 + e >= n) sw = true;          // padding of the last batch: leaves the carried message alone
+          src[e] = sw ? k1 : cs;               // swap: chain k+1's message drops to position k; else the carried one stays
+          ns += (sw && j0 + e < n) ? 1 : 0;
+          ck = sw ? ck : kp[e];                // no swap: k+1's message is carried on
+          cs = sw ? cs : k1;
+          swv[e] = sw ? 1 : 0;
+        }
+#pragma unroll
+        for (int e = 0; e < kB; ++e)
+          if (j0 + e < n) { s_src[j0 + e] = src[e]; s_sw[j0 + e] = swv[e]; }
       }
-      c_post = cp; c_src = cs; c_ns = ns;
+      c_key = ck; c_src = cs; c_ns = ns;
     }
     __syncthreads();
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
       const int k = k0 + j;
       scratch_src[k] = s_src[j];
-      scratch_post[k] = s_post[j];
+      scratch_post[k] = posted(s_src[j]);      // lik_post is not modified before the re-binding loop below
       if (swapped) swapped[k] = s_sw[j];
     }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    scratch_src[R - 1] = c_src; scratch_post[R - 1] = c_post;
+    scratch_src[R - 1] = c_src; scratch_post[R - 1] = posted(c_src);
     if (num_swap) *num_swap += c_ns;
   }
   __syncthreads();
@@ -219,6 +261,135 @@ __global__ void swap_sweep_kernel(int R, double* lik_post, const double* tempera
   for (int k = threadIdx.x; k < R; k += blockDim.x) old_rows[k] = row_of_slot[k];
   __syncthreads();
   for (int k = threadIdx.x; k < R; k += blockDim.x) {
+    const int newrow = old_rows[scratch_src[k]];
+    row_of_slot[k] = newrow;
+    if (src_slot) src_slot[k] = scratch_src[k];
+    if (flags & SAPT_F_TAKE_POST_LIK) lik_post[k] = scratch_post[k];  // LG:813-815
+    if (slot_of_row_local && newrow >= row0 && newrow < row0 + R_local) slot_of_row_local[newrow - row0] = k;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// The same sweep without a serial walk (large ladders: 65 536 chains took 3.4 ms in the walk above).
+// After a pair does NOT swap, the carried message is simply chain k+1's: the state "reset at m" (about to
+// process pair m carrying chain m's own message) does not depend on the past. From such a state every pair swaps
+// until the first j >= m whose threshold is not above chain m's likelihood, i.e. the first j >= m with
+// kt[j] <= kp[m] — a next-smaller-or-equal query, answered for ALL m at once with a range-minimum sparse table.
+// nxt[m] = that j + 1 is the next reset state, so the states the real sweep visits are the list 0 -> nxt[0] -> ...;
+// it is marked by pointer doubling (S <- S u J(S), J <- J o J). Then: pair j did not swap  <=>  state j+1 is on
+// the list; the message left at position k is chain k+1's if pair k swapped, else the message carried at that
+// time = the last list state <= k (a prefix maximum). Same decision rule as the serial walk (integer keys), so
+// the two kernels agree bit for bit; pairs that need the literal formula (u <= 0) make the kernel fall back to it.
+// One CTA of 1024 threads; all phases are O(R log R / 1024) with R-sized global scratch.
+constexpr int kParThreads = 1024;
+constexpr long long kKeyMin = (long long)0x8000000000000000ULL, kKeyMax = 0x7fffffffffffffffLL;
+
+__global__ void __launch_bounds__(kParThreads) swap_sweep_parallel_kernel(
+    int R, double* lik_post, const double* temperature, int32_t* row_of_slot, uint32_t flags, uint32_t seed, int sweep_base,
+    const int32_t* sweep_dev, const double* u_inject, uint8_t* swapped, int32_t* num_swap, int32_t* src_slot, int row0, int R_local,
+    int32_t* slot_of_row_local, int32_t* scratch_src /*[2R]*/, double* scratch_post /*[R]*/, long long* st /*[levels][R]*/,
+    long long* kp /*[R]*/, int32_t* jmp /*[2][R+1]*/, uint8_t* mark /*[2][R+1]*/, int32_t* literal_flag) {
+  const int sweep = sweep_base + (sweep_dev ? *sweep_dev : 0);
+  const int tid = threadIdx.x;
+  const int NP = R - 1;   // pairs
+  auto posted = [&](int k) { return (flags & SAPT_F_POST_TEMPERED) ? lik_post[k] : lik_post[k] * temperature[k]; };
+  __shared__ int s_any_literal, s_ns;
+  __shared__ int s_scan[kParThreads];
+  if (tid == 0) { s_any_literal = 0; s_ns = 0; }
+  __syncthreads();
+  // ---- keys: kp[k] of every chain; level 0 of the table = threshold keys (kKeyMin forces "no swap" when u >= 1) ----
+  for (int k = tid; k < R; k += kParThreads) {
+    const double pk = posted(k);
+    kp[k] = (pk != pk) ? kKeyMin : order_key(pk);
+  }
+  for (int j = tid; j < NP; j += kParThreads) {
+    const double pk = posted(j + 1);
+    const double u = u_inject ? u_inject[j] : (double)philox_uniform(seed, SAPT_STREAM_SWAP, sweep, 0u, (uint32_t)j);
+    if (!(u > 0.0)) s_any_literal = 1;
+    const double t = pk - log(2.0 * u);
+    long long kt = (t != t) ? kKeyMax : order_key(t);
+    if (!(u < 1.0)) kt = kKeyMin;
+    st[j] = kt;
+  }
+  __syncthreads();
+  if (s_any_literal) { if (tid == 0) *literal_flag = 1; return; }   // the host re-runs the serial kernel (never with Philox: u > 0)
+  int levels = 1;
+  while ((1 << levels) <= NP) ++levels;
+  for (int l = 1; l < levels; ++l) {
+    const long long* a = st + (int64_t)(l - 1) * R;
+    long long* b = st + (int64_t)l * R;
+    const int half = 1 << (l - 1), span = 1 << l;
+    for (int j = tid; j + span <= NP; j += kParThreads) b[j] = min(a[j], a[j + half]);
+    __syncthreads();
+  }
+  // ---- nxt[m] = 1 + first j >= m with kt[j] <= kp[m]  (a swap needs kp[m] < kt[j]); R = no such pair ----
+  int32_t* J0 = jmp; int32_t* J1 = jmp + (R + 1);
+  uint8_t* M0 = mark; uint8_t* M1 = mark + (R + 1);
+  for (int m = tid; m <= R; m += kParThreads) {
+    int nx = R;
+    if (m < NP) {
+      const long long c = kp[m];
+      int j = m;
+      for (int l = levels - 1; l >= 0; --l)
+        if (j + (1 << l) <= NP && st[(int64_t)l * R + j] > c) j += (1 << l);
+      nx = (j < NP) ? j + 1 : R;
+    }
+    J0[m] = nx;
+    M0[m] = (m == 0) ? 1 : 0;
+  }
+  __syncthreads();
+  // ---- states on the list from 0: pointer doubling ----
+  for (int l = 0; l < levels + 1; ++l) {
+    for (int m = tid; m <= R; m += kParThreads) M1[m] = M0[m];
+    __syncthreads();
+    for (int m = tid; m < R; m += kParThreads) {
+      const int t = J0[m];
+      if (M0[m] && t < R) M1[t] = 1;
+      J1[m] = (t < R) ? J0[t] : R;
+    }
+    if (tid == 0) J1[R] = R;
+    __syncthreads();
+    int32_t* tj = J0; J0 = J1; J1 = tj;
+    uint8_t* tm = M0; M0 = M1; M1 = tm;
+  }
+  // ---- decisions, and the carried chain at every position: prefix maximum of the list states ----
+  // scratch_src[k] temporarily holds (state k on the list ? k : -1); chunked inclusive max-scan
+  int carry = -1;
+  for (int base = 0; base < R; base += kParThreads) {
+    const int k = base + tid;
+    int v = (k < R && M0[k]) ? k : -1;
+    s_scan[tid] = v;
+    __syncthreads();
+    for (int off = 1; off < kParThreads; off <<= 1) {
+      const int o = (tid >= off) ? s_scan[tid - off] : -1;
+      __syncthreads();
+      s_scan[tid] = max(s_scan[tid], o);
+      __syncthreads();
+    }
+    const int last = max(carry, s_scan[tid]);
+    const int chunk_max = s_scan[kParThreads - 1];
+    if (k < R) {
+      int src;
+      if (k < NP) {
+        const bool sw = !M0[k + 1];                    // pair k swapped <=> no reset at k+1
+        src = sw ? k + 1 : last;
+        if (swapped) swapped[k] = sw ? 1 : 0;
+        if (sw) atomicAdd(&s_ns, 1);
+      } else {
+        src = last;                                    // the message carried out of the last pair
+      }
+      scratch_src[k] = src;
+      scratch_post[k] = posted(src);
+    }
+    carry = max(carry, chunk_max);
+    __syncthreads();
+  }
+  if (tid == 0 && num_swap) *num_swap += s_ns;
+  // ---- new binding (as in the serial kernel) ----
+  int32_t* old_rows = scratch_src + R;
+  for (int k = tid; k < R; k += kParThreads) old_rows[k] = row_of_slot[k];
+  __syncthreads();
+  for (int k = tid; k < R; k += kParThreads) {
     const int newrow = old_rows[scratch_src[k]];
     row_of_slot[k] = newrow;
     if (src_slot) src_slot[k] = scratch_src[k];
@@ -317,6 +488,37 @@ extern "C" int sapt_swap_sweep_dev(int R_global, double* lik_post, const double*
     sc_cap = cap;
   }
   // NOTE: old_rows lives at sc_i + R_global (the kernel derives it from scratch_src + R)
+  const bool parallel = (flags & SAPT_F_SWEEP_PARALLEL) || R_global >= 4096;
+  if (parallel && R_global >= 3) {
+    static long long* sp_st[kMaxDev] = {nullptr}; static int32_t* sp_i[kMaxDev] = {nullptr}; static uint8_t* sp_m[kMaxDev] = {nullptr};
+    static int sp_cap[kMaxDev] = {0};
+    int levels = 1;
+    while ((1 << levels) <= R_global - 1) ++levels;
+    if (R_global > sp_cap[dev]) {
+      SAPT_CUDA(cudaDeviceSynchronize());
+      if (sp_st[dev]) { SAPT_CUDA(cudaFree(sp_st[dev])); SAPT_CUDA(cudaFree(sp_i[dev])); SAPT_CUDA(cudaFree(sp_m[dev])); }
+      const int cap = R_global + R_global / 4 + 64;
+      int lv = 1;
+      while ((1 << lv) <= cap) ++lv;
+      SAPT_CUDA(cudaMalloc(&sp_st[dev], sizeof(long long) * (size_t)(lv + 1) * cap));       // table levels + kp
+      SAPT_CUDA(cudaMalloc(&sp_i[dev], sizeof(int32_t) * (2 * (size_t)(cap + 1) + 4)));      // jump arrays + the literal flag
+      SAPT_CUDA(cudaMalloc(&sp_m[dev], 2 * (size_t)(cap + 1)));
+      SAPT_CUDA(cudaMemset(sp_i[dev], 0, sizeof(int32_t) * (2 * (size_t)(cap + 1) + 4)));
+      sp_cap[dev] = cap;
+    }
+    long long* kp = sp_st[dev] + (size_t)levels * R_global;
+    int32_t* lit = sp_i[dev];                    // fixed slot; the jump arrays follow it
+    swap_sweep_parallel_kernel<<<1, kParThreads, 0, (cudaStream_t)stream>>>(R_global, lik_post, temperature, row_of_slot, flags, seed, sweep,
+                                                                            sweep_dev, u_inject, swapped, num_swap, src_slot, row0, R_local,
+                                                                            slot_of_row_local, sc_i, sc_d, sp_st[dev], kp, sp_i[dev] + 4, sp_m[dev], lit);
+    SAPT_CHECK_LAUNCH();
+    if (!u_inject) return SAPT_OK;              // Philox uniforms lie in (0, 1]: the literal formula is never needed
+    int32_t h_lit = 0;                          // injected streams (parity tests): u <= 0 is possible, check and redo serially
+    SAPT_CUDA(cudaMemcpyAsync(&h_lit, lit, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    SAPT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (!h_lit) return SAPT_OK;
+    SAPT_CUDA(cudaMemsetAsync(lit, 0, sizeof(int32_t), (cudaStream_t)stream));
+  }
   swap_sweep_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(R_global, lik_post, temperature, row_of_slot, flags, seed, sweep, sweep_dev,
                                                          u_inject, swapped, num_swap, src_slot, row0, R_local, slot_of_row_local,
                                                          sc_i, sc_d);

@@ -209,13 +209,13 @@ def test_langevin_batch_gradient(lib):
 def test_swap_sweep_matches_reference(lib):
     g = gu.load("swap_ladder")
     L = lib.lib()
-    for n in range(int(g["n_swap_cases"])):
+    for n, fl in [(n, fl) for n in range(int(g["n_swap_cases"])) for fl in (0, lib.F_SWEEP_PARALLEL)]:
         lik = g[f"swap{n}_lik"]; u = g[f"swap{n}_u"]; R = len(lik)
         lik_d = torch.as_tensor(lik.copy()).cuda(); T = torch.ones(R, dtype=torch.float64).cuda()
         ros = torch.arange(R, dtype=torch.int32).cuda(); u_d = torch.as_tensor(u.copy()).cuda()
         sw = torch.zeros(R - 1, dtype=torch.uint8).cuda(); ns = torch.zeros(1, dtype=torch.int32).cuda()
         src = torch.zeros(R, dtype=torch.int32).cuda(); sor = torch.zeros(R, dtype=torch.int32).cuda()
-        lib.check(L.sapt_swap_sweep(R, lik_d.data_ptr(), T.data_ptr(), ros.data_ptr(), 0, 1, 0, u_d.data_ptr(), sw.data_ptr(),
+        lib.check(L.sapt_swap_sweep(R, lik_d.data_ptr(), T.data_ptr(), ros.data_ptr(), fl, 1, 0, u_d.data_ptr(), sw.data_ptr(),
                                     ns.data_ptr(), src.data_ptr(), 0, R, sor.data_ptr(), None))
         torch.cuda.synchronize()
         assert np.array_equal(src.cpu().numpy(), g[f"swap{n}_src"])
@@ -224,6 +224,46 @@ def test_swap_sweep_matches_reference(lib):
         assert np.array_equal(ros.cpu().numpy(), g[f"swap{n}_src"])          # identity binding before -> rows follow src
         inv = np.empty(R, dtype=np.int64); inv[g[f"swap{n}_src"]] = np.arange(R)
         assert np.array_equal(sor.cpu().numpy(), inv)
+
+
+@pytest.mark.parametrize("R", [3, 4, 17, 1000, 5001, 70000])
+def test_swap_sweep_parallel_kernel_equals_serial_walk_and_oracle(lib, R):
+    """The parallel sweep (range-minimum table + pointer doubling, the default for >= 4096 chains) against the serial walk
+    and, for moderate R, the oracle's swap_sweep: tempered and untempered posts, ties, u >= 1, NaN likelihoods, a
+    shuffled binding, a rank-local window, injected and Philox uniforms."""
+    L = lib.lib()
+    rs = np.random.RandomState(R)
+    lik = -np.abs(rs.standard_normal(R)) * 30.0 - 300.0
+    lik[rs.randint(0, R, max(1, R // 50))] = lik[0]                   # exact ties
+    if R > 10:
+        lik[rs.randint(1, R, 3)] = np.nan
+    T = np.linspace(1.0, 4.0, R)
+    u = rs.uniform(size=R - 1)
+    u[rs.randint(0, R - 1, max(1, R // 100))] = 1.0                    # never swaps
+    perm = rs.permutation(R).astype(np.int32)
+    row0, Rl = R // 3, max(1, R // 2)
+    for flags0 in (0, lib.F_POST_TEMPERED | lib.F_TAKE_POST_LIK):
+        for inj in (True, False):
+            outs = []
+            for par in (0, lib.F_SWEEP_PARALLEL):
+                lik_d = torch.as_tensor(lik.copy()).cuda(); T_d = torch.as_tensor(T.copy()).cuda()
+                ros = torch.as_tensor(perm.copy()).cuda(); u_d = torch.as_tensor(u.copy()).cuda()
+                sw = torch.zeros(R - 1, dtype=torch.uint8).cuda(); ns = torch.zeros(1, dtype=torch.int32).cuda()
+                src = torch.zeros(R, dtype=torch.int32).cuda(); sor = torch.full((Rl,), -7, dtype=torch.int32).cuda()
+                lib.check(L.sapt_swap_sweep(R, lik_d.data_ptr(), T_d.data_ptr(), ros.data_ptr(), flags0 | par, 11, 5,
+                                            u_d.data_ptr() if inj else None, sw.data_ptr(), ns.data_ptr(), src.data_ptr(), row0, Rl,
+                                            sor.data_ptr(), None))
+                torch.cuda.synchronize()
+                outs.append((sw.cpu().numpy(), int(ns.item()), src.cpu().numpy(), ros.cpu().numpy(), sor.cpu().numpy(), lik_d.cpu().numpy()))
+            a, b = outs
+            assert np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[2], b[2])
+            assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+            assert np.array_equal(np.isnan(a[5]), np.isnan(b[5])) and np.array_equal(a[5][~np.isnan(a[5])], b[5][~np.isnan(b[5])])
+            assert a[1] == int(a[0].sum()) and (R < 1000 or 0 < a[1] < R - 1)
+            if inj and R <= 5001 and not np.isnan(lik).any():
+                post = lik.copy() if (flags0 & lib.F_POST_TEMPERED) else lik * T
+                osrc, osw = so.swap_sweep(post, u)
+                assert np.array_equal(a[0].astype(bool), osw) and np.array_equal(a[2], osrc)
 
 
 def test_philox_device_matches_oracle(lib):
