@@ -423,12 +423,17 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
         const bool mine = (HALVES == 1) || ((u & 1) == hf);   // which of the chain's warps runs phase 2 of this unit
         if (has_next) phase1(u + 1);
         // ---- D2 of unit u: wait for MMA-2 (this also frees the HV buffer), pull it into registers ----
-        uint32_t dr0[ON], dr1[ON], dr2[ON];  // the partial sums of D2 (dr2 unused when PARTS == 2)
+        // the partial sums of D2 (dr2 unused when PARTS == 2). ON = 32 serves O = 17..20: only 20 columns are read
+        constexpr int NR = (ON == 32) ? 20 : ON;
+        uint32_t dr0[NR], dr1[NR], dr2[ON == 32 ? 1 : ON];
         mbar_wait(&d2_full[(u & 1) * UC + c], (u >> 1) & 1);
         tc_fence_after();
         if (mine) {
           const uint32_t taddr = tmem_base + lane_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (UC * N2) + c * N2);
-          if constexpr (ON == 32) { tmem_ld32(taddr, dr0); tmem_ld32(taddr + ON, dr1); }
+          if constexpr (ON == 32) {
+            tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&dr0[0])); tmem_ld4(taddr + 16, *reinterpret_cast<uint32_t(*)[4]>(&dr0[16]));
+            tmem_ld16(taddr + ON, *reinterpret_cast<uint32_t(*)[16]>(&dr1[0])); tmem_ld4(taddr + ON + 16, *reinterpret_cast<uint32_t(*)[4]>(&dr1[16]));
+          }
           else { tmem_ld16(taddr, dr0); tmem_ld16(taddr + ON, dr1); tmem_ld16(taddr + 2 * ON, dr2); }
           tmem_ld_wait();
         }
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
             emit(o, t, kLog2e * rcp_approx(1.0f + ex2_approx(fminf(t, 30.0f))));
           };
 #pragma unroll
-          for (int g = 0; g < ON / 4; ++g) {
+          for (int g = 0; g < NR / 4; ++g) {
             const int rem = O - 4 * g;   // warp-uniform
             if (rem >= 4) {
               const float t0 = tval(4 * g), t1 = tval(4 * g + 1), t2 = tval(4 * g + 2), t3 = tval(4 * g + 3);
