@@ -162,7 +162,10 @@ int sapt_propose(const sapt_propose_args* a, void* stream);
 /* ---- Langevin "gradient": replaces Network.langevin_gradient LG:138-156 + BackwardPass
  * LG:96-106 (one epoch of per-row online SGD, sequential over the train rows) for the listed
  * rows. mode 0 = "sgd_exact" (reference semantics); mode 1 = "batch": theta + lr * scale *
- * sum_i g_i(theta) with g_i the LG:100-106 increments at FIXED theta. */
+ * sum_i g_i(theta) with g_i the LG:100-106 increments at FIXED theta — on the tensor cores
+ * (tcgen05: forward, back-propagation and the X^T.delta / h^T.delta row contractions) where the topology allows
+ * (O <= 16, H <= 64, D <= 64), else on CUDA cores; mode 2 = "batch" on CUDA cores always (cross-check).
+ * SAPT_ERR_UNSUPPORTED when the topology exceeds the kernels' shared-memory envelope (H beyond ~150). */
 int sapt_langevin(sapt_problem_t* p, const float* theta, float* theta_gd, int64_t ld, int R,
                   const int32_t* rows, const int32_t* n_rows, double lrate, int mode,
                   double batch_scale, void* stream);
