@@ -840,3 +840,71 @@ def run_pt_local(traindata, testdata, topology, temperatures, w0, samples: int, 
                 is_surrogate_step=is_surrogate_step, accepted=accepted, swap_decisions=swap_decisions, num_swap=num_swap,
                 total_swap_proposals=total_swap_proposals, likelihood=likelihood, likelihood_copy=likelihood_copy,
                 prior_current=prior_current, limit=limit, nets=nets, train_rmse=train_rmse)
+
+
+# --------------------------------------------------------------------------------------
+# a14 (device algorithm): the exchange sweep WITHOUT a serial walk, restated in numpy so the algorithm behind
+# swap_sweep_parallel_kernel (csrc/sapt_mcmc.cu) can be checked on the CPU against swap_sweep above.
+# --------------------------------------------------------------------------------------
+
+def _order_key(x: np.ndarray) -> np.ndarray:
+    """Order-preserving int64 image of float64 (non-NaN)."""
+    b = np.asarray(x, dtype=np.float64).view(np.int64)
+    return b ^ ((b >> 63) & np.int64(0x7FFFFFFFFFFFFFFF))
+
+
+def swap_sweep_parallel(post_lik: np.ndarray, u: np.ndarray):
+    """Same result as swap_sweep, computed with data-parallel steps only:
+    (1) u < min(1, 0.5 exp(min(709, p - c)))  <=>  u < 1 and c < p - ln(2u): thresholds t[j] = p[j+1] - ln(2 u[j]);
+    (2) from the state "reset at m" (pair m next, carrying chain m's own message) every pair swaps until the first
+        j >= m with t[j] <= p[m]: nxt[m] = that j + 1, found for all m with a range-minimum sparse table;
+    (3) the states the sweep visits are the list 0 -> nxt[0] -> ..., marked by pointer doubling;
+    (4) pair j did not swap <=> state j+1 is on the list; position k keeps chain k+1's message if pair k swapped,
+        else the message carried then = the last list state <= k (a prefix maximum).
+    Requires u > 0 (the device falls back to the serial walk otherwise). NaN: like Python's min(1, nan) == 1."""
+    p = np.asarray(post_lik, dtype=np.float64)
+    u = np.asarray(u, dtype=np.float64)
+    R = len(p)
+    NP = R - 1
+    if NP <= 0:
+        return np.arange(R), np.zeros(0, dtype=bool)
+    assert np.all(u > 0)
+    KMIN, KMAX = np.iinfo(np.int64).min, np.iinfo(np.int64).max
+    kp = np.where(np.isnan(p), KMIN, _order_key(np.nan_to_num(p, nan=0.0)))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        t = p[1:] - np.log(2.0 * u)
+    kt = np.where(np.isnan(t), KMAX, _order_key(np.nan_to_num(t, nan=0.0)))
+    kt = np.where(u < 1.0, kt, KMIN)
+    levels = 1
+    while (1 << levels) <= NP:
+        levels += 1
+    st = [kt]
+    for l in range(1, levels):
+        a = st[-1]
+        half, span = 1 << (l - 1), 1 << l
+        b = np.full(NP, KMAX, dtype=np.int64)
+        n = NP - span + 1
+        if n > 0:
+            b[:n] = np.minimum(a[:n], a[half:half + n])
+        st.append(b)
+    j = np.arange(NP)
+    c = kp[:NP]
+    for l in range(levels - 1, -1, -1):
+        ok = (j + (1 << l) <= NP)
+        go = ok & (st[l][np.minimum(j, NP - 1)] > c)
+        j = np.where(go, j + (1 << l), j)
+    nxt = np.full(R + 1, R, dtype=np.int64)
+    nxt[:NP] = np.where(j < NP, j + 1, R)
+    mark = np.zeros(R + 1, dtype=bool)
+    mark[0] = True
+    J = nxt.copy()
+    for _ in range(levels + 1):
+        tgt = J[:R][mark[:R]]
+        mark[tgt[tgt < R]] = True
+        J = np.where(J < R, J[np.minimum(J, R)], R)
+    swapped = ~mark[1:R]
+    last = np.maximum.accumulate(np.where(mark[:R], np.arange(R), -1))
+    src = np.empty(R, dtype=np.int64)
+    src[:NP] = np.where(swapped, np.arange(1, R), last[:NP])
+    src[NP] = last[NP]
+    return src, swapped

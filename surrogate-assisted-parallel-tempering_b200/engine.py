@@ -426,12 +426,7 @@ class PTEngine:
         old binding) and before the rows are handed to the trainer."""
         if self.cfg.world == 1 or self.train_theta is None or self._train_synced:
             return
-        import torch.distributed as dist
-        mask = self._hosted_mask()
-        cnt = self.train_count.double() * mask
-        self.train_theta.mul_(mask[:, None, None].to(self.train_theta.dtype)); self.train_L.mul_(mask[:, None])
-        dist.all_reduce(cnt, group=self.pg); dist.all_reduce(self.train_theta, group=self.pg); dist.all_reduce(self.train_L, group=self.pg)
-        self.train_count.copy_(cnt.round().to(torch.int32))
+        parallel.sync_training_buffers(self.train_theta, self.train_L, self.train_count, self._hosted_mask(), self.pg)
         self._train_synced = True
 
     def gather_training_rows(self) -> torch.Tensor:
@@ -466,10 +461,9 @@ class PTEngine:
         written. Between two exchanges the binding is fixed, so in the rows written since the last sync every
         (row, chain) entry is non-zero on exactly one rank: a plain sum makes them complete everywhere (NaN
         markers survive the sum), and the new host of a chain can feed its network."""
-        import torch.distributed as dist
         lo = self.ls_synced_row
         if upto > lo:
-            dist.all_reduce(self.hist["surg"][lo:upto], group=self.pg)
+            parallel.sync_history_rows(self.hist["surg"][lo:upto], self.pg)
             self.ls_synced_row = upto
 
     def local_surrogate_train(self, i: int):

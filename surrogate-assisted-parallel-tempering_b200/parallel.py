@@ -66,3 +66,26 @@ def merge_history(hist: torch.Tensor, group=None) -> torch.Tensor:
     t = hist.clone() if hist.dtype != torch.uint8 else hist.to(torch.int32)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+def sync_training_buffers(train_theta: torch.Tensor, train_L: torch.Tensor, train_count: torch.Tensor, mask: torch.Tensor, group=None) -> None:
+    """Surrogate training rows are appended on whichever rank hosts a chain. In place: every chain's buffer
+    ([R_global, cap, P] rows, [R_global, cap] likelihoods, [R_global] counts) is taken from its CURRENT host, so
+    afterwards the buffers are complete and identical on all ranks. Must run before an exchange re-binds the chains
+    (the rows of the interval were written under the old binding) and before the rows go to the trainer."""
+    import torch.distributed as dist
+    cnt = train_count.to(torch.float64) * mask
+    train_theta.mul_(mask[:, None, None].to(train_theta.dtype))
+    train_L.mul_(mask[:, None].to(train_L.dtype))
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(train_theta, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(train_L, op=dist.ReduceOp.SUM, group=group)
+    train_count.copy_(cnt.round().to(train_count.dtype))
+
+
+def sync_history_rows(hist_rows: torch.Tensor, group=None) -> None:
+    """Rows of a per-chain history written since the last synchronisation: between two exchanges the binding is
+    fixed, so every (row, chain) entry is non-zero on exactly one rank and a plain sum completes the rows everywhere
+    (NaN markers survive: NaN + 0 = NaN)."""
+    import torch.distributed as dist
+    dist.all_reduce(hist_rows, op=dist.ReduceOp.SUM, group=group)

@@ -64,6 +64,29 @@ def _worker(rank, world, port, q):
         assert torch.equal(merged, want)
         h8 = torch.zeros((2, Rg), dtype=torch.uint8); h8[:, slot_of_row.long()] = 1
         assert parallel.merge_history(h8).sum().item() == 2 * Rg
+        # surrogate training rows follow the chains: each rank holds the rows of the slots it hosts (stale garbage elsewhere)
+        cap, P = 3, 5
+        full_cnt = torch.tensor([3, 0, 2, 1, 3, 3, 0, 2], dtype=torch.int32)
+        full_th = torch.arange(Rg * cap * P, dtype=torch.float32).reshape(Rg, cap, P) + 1.0
+        full_L = -torch.arange(Rg * cap, dtype=torch.float64).reshape(Rg, cap) - 0.25
+        hosted = mask > 0
+        th = torch.where(hosted[:, None, None], full_th, torch.full_like(full_th, -777.0))
+        tl = torch.where(hosted[:, None], full_L, torch.full_like(full_L, 555.0))
+        cnt = torch.where(hosted, full_cnt, torch.full_like(full_cnt, 9))
+        parallel.sync_training_buffers(th, tl, cnt, mask)
+        assert torch.equal(th, full_th) and torch.equal(tl, full_L) and torch.equal(cnt, full_cnt)
+        # history rows written since the last exchange: non-zero on the writing rank only, NaN markers included
+        rows = torch.zeros((4, Rg, 3), dtype=torch.float64)
+        rows[:, slot_of_row.long(), :] = float(rank + 1)
+        rows[1, slot_of_row.long()[0], 1] = float("nan")
+        parallel.sync_history_rows(rows)
+        want_rows = torch.zeros((4, Rg, 3), dtype=torch.float64)
+        want_rows[:, [2, 0, 4, 6], :] = 1.0; want_rows[:, [1, 7, 3, 5], :] = 2.0
+        nan_at = [(1, 2, 1), (1, 1, 1)]                      # first hosted slot of rank 0 / rank 1
+        for (a_, b_, c_) in nan_at:
+            assert torch.isnan(rows[a_, b_, c_])
+            rows[a_, b_, c_] = want_rows[a_, b_, c_]
+        assert torch.equal(rows, want_rows)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, f"FAIL {type(e).__name__}: {e}"))

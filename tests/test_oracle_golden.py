@@ -137,3 +137,29 @@ def test_local_surrogate_units():
     np.testing.assert_allclose(rm, float(g[f"ls_train0_rmse_{k}"]), rtol=1e-10)
     w = np.concatenate([net["W1"].ravel(), net["W2"].ravel(), net["B1"].ravel(), net["B2"].ravel()])
     np.testing.assert_allclose(w, g[f"ls_train0_weights_{k}"], rtol=1e-10, atol=1e-12)
+
+
+def test_parallel_sweep_algorithm_equals_sequential_sweep():
+    """The algorithm of the device's parallel exchange sweep (sparse table + pointer doubling), restated in numpy,
+    against the reference's sequential rule on random ladders: ties, u >= 1, all-swap and no-swap runs."""
+    rs = np.random.RandomState(4)
+    for case in range(300):
+        R = int(rs.choice([2, 3, 4, 5, 9, 33, 200, 1025]))
+        scale = float(rs.choice([0.1, 1.0, 30.0]))
+        lik = -np.abs(rs.standard_normal(R)) * scale - 100.0
+        if case % 5 == 0:
+            lik = np.sort(lik)                       # every pair wants to swap
+        if case % 7 == 0:
+            lik[rs.randint(0, R, 2)] = lik[0]        # ties
+        u = rs.uniform(size=R - 1)
+        u[u == 0] = 0.5
+        if case % 3 == 0 and R > 2:
+            u[rs.randint(0, R - 1)] = 1.0            # never swaps
+        s1, w1 = so.swap_sweep(lik, u)
+        s2, w2 = so.swap_sweep_parallel(lik, u)
+        assert np.array_equal(w1, w2), (case, R)
+        assert np.array_equal(s1, s2), (case, R)
+    g = gu.load("swap_ladder")
+    for n in range(int(g["n_swap_cases"])):
+        s2, w2 = so.swap_sweep_parallel(g[f"swap{n}_lik"], g[f"swap{n}_u"])
+        assert np.array_equal(s2, g[f"swap{n}_src"]) and np.array_equal(w2, g[f"swap{n}_swapped"])
