@@ -82,8 +82,8 @@ const char* sapt_last_error(void);
 long long sapt_launch_count(void);
 void sapt_launch_count_reset(void);
 /* sizeof() of sapt_propose_args, sapt_chain_state, sapt_history, sapt_accept_args, sapt_lg_first_args,
- * sapt_fused_args, sapt_local_surrogate — lets an FFI binding verify its struct mirrors at load time */
-int sapt_struct_sizes(int32_t out[7]);
+ * sapt_fused_args, sapt_local_surrogate, sapt_step_args — lets an FFI binding verify its struct mirrors at load time */
+int sapt_struct_sizes(int32_t out[8]);
 
 /* ---- data + topology: replaces Network.__init__(Topo, Train, Test, lr) RV:49-60 -------
  * train_host/test_host: row-major float64 [n][D+1], features then the class index as a
@@ -299,6 +299,29 @@ int sapt_advance(int32_t* counter, int delta, void* stream);
 int sapt_philox_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* fills u[n] (kind uniform) or z[n] (normals) on the device exactly as the kernels draw them */
 int sapt_philox_fill(uint32_t seed, int kind, int step, int chain, int n, int normal, float* out, void* stream);
+
+/* ---- n whole MCMC steps of the random-walk forks chained inside the library (no host code between the kernels):
+ * the loop body RV:514-642 / RW:492-640 for all R chains, i.e. per step
+ *   sapt_propose -> [sapt_surrogate_predict on the surrogate rows] -> sapt_loglik(train: all rows when the surrogate is
+ *   compared or absent, RV:543, else the true rows) -> sapt_loglik(test, true rows) -> sapt_mh_accept.
+ * `prop` and `acc` are the argument blocks of sapt_propose / sapt_mh_accept filled by the caller as for a single
+ * step; their `step` fields give the FIRST step, the driver advances them. No exchange happens inside: call
+ * sapt_swap_sweep (and the surrogate rendezvous) between calls. The Langevin fork's extra stages
+ * (sapt_lg_first_eval, sapt_langevin, second proposal) are driven by the host mirror (engine.py). */
+typedef struct {
+  sapt_propose_args prop;
+  sapt_accept_args acc;
+  int use_surrogate;          /* surrogate coin thrown at all (prop.decide) */
+  int compare_surrogate;      /* SAPT_F_COMPARE_SURROGATE: train likelihood on every row */
+  const float* W1; const float* b1; int h1; const float* W2; const float* b2; int h2; const float* W3; const float* b3;
+  float* sur_s;               /* [R] surrogate outputs (same buffer acc.sur_s reads) */
+  double* L_train; int32_t* nc_train; double* sq_train;   /* [R] outputs of the train evaluation (acc reads them) */
+  double* L_test; int32_t* nc_test; double* sq_test;      /* [R] */
+  int32_t* counters;          /* [3] n_true, n_sur, spare: zeroed before every proposal (prop.n_true / prop.n_sur point here) */
+  int path;                   /* SAPT_PATH_* */
+  int n_steps;
+} sapt_step_args;
+int sapt_step(sapt_problem_t* p, const sapt_step_args* a, void* stream);
 
 /* ---- N4: per-chain "local" surrogate of the fork localsurrogates/surrogate_pt_classifier_rw_localsurrogate.py (LS).
  * Every chain owns a 4 -> 10 -> 1 sigmoid network (LS:57-101) that predicts its next tempered likelihood from

@@ -75,6 +75,13 @@ class LocalSurrogate(C.Structure):
 LS_WEIGHTS = 61
 
 
+class StepArgs(C.Structure):
+    _fields_ = [("prop", ProposeArgs), ("acc", AcceptArgs), ("use_surrogate", C.c_int), ("compare_surrogate", C.c_int),
+                ("W1", vp), ("b1", vp), ("h1", C.c_int), ("W2", vp), ("b2", vp), ("h2", C.c_int), ("W3", vp), ("b3", vp),
+                ("sur_s", vp), ("L_train", vp), ("nc_train", vp), ("sq_train", vp), ("L_test", vp), ("nc_test", vp), ("sq_test", vp),
+                ("counters", vp), ("path", C.c_int), ("n_steps", C.c_int)]
+
+
 class SaptError(RuntimeError):
     pass
 
@@ -118,10 +125,11 @@ def lib():
     L.sapt_fused_steps.argtypes = [vp, C.POINTER(FusedArgs), vp]
     L.sapt_local_surrogate_train.argtypes = [C.POINTER(LocalSurrogate), C.c_int, C.c_int, C.c_int, vp, u32, f64, C.c_int, vp, vp]
     L.sapt_local_surrogate_predict.argtypes = [C.POINTER(LocalSurrogate), C.c_int, vp, vp, vp, vp, vp, vp]
+    L.sapt_step.argtypes = [vp, C.POINTER(StepArgs), vp]
     L.sapt_struct_sizes.argtypes = [C.POINTER(i32)]
-    sizes = (i32 * 7)()
+    sizes = (i32 * 8)()
     L.sapt_struct_sizes(sizes)
-    mine = [C.sizeof(t) for t in (ProposeArgs, ChainState, History, AcceptArgs, LgFirstArgs, FusedArgs, LocalSurrogate)]
+    mine = [C.sizeof(t) for t in (ProposeArgs, ChainState, History, AcceptArgs, LgFirstArgs, FusedArgs, LocalSurrogate, StepArgs)]
     if list(sizes) != mine:
         raise ImportError(f"struct layout mismatch between include/sapt.h and _lib.py: C={list(sizes)} ctypes={mine}")
     if L.sapt_abi_version() != 1:
@@ -143,5 +151,5 @@ EXPORTS = [
     "sapt_problem_rows", "sapt_problem_tc_supported", "sapt_loglik", "sapt_loglik_host", "sapt_evaluate_proposal",
     "sapt_prior", "sapt_propose", "sapt_fused_steps", "sapt_langevin", "sapt_surrogate_predict", "sapt_mh_accept", "sapt_lg_first_eval",
     "sapt_swap_sweep", "sapt_swap_sweep_dev", "sapt_advance", "sapt_philox_host", "sapt_philox_fill",
-    "sapt_local_surrogate_train", "sapt_local_surrogate_predict",
+    "sapt_local_surrogate_train", "sapt_local_surrogate_predict", "sapt_step",
 ]

@@ -184,7 +184,7 @@ extern "C" int sapt_evaluate_proposal(sapt_problem_t* p, int which, const float*
 }
 
 // layout self-check for FFI bindings: sizes of the argument structs, in header order
-extern "C" int sapt_struct_sizes(int32_t out[7]) {
+extern "C" int sapt_struct_sizes(int32_t out[8]) {
   out[0] = (int32_t)sizeof(sapt_propose_args);
   out[1] = (int32_t)sizeof(sapt_chain_state);
   out[2] = (int32_t)sizeof(sapt_history);
@@ -192,5 +192,46 @@ extern "C" int sapt_struct_sizes(int32_t out[7]) {
   out[4] = (int32_t)sizeof(sapt_lg_first_args);
   out[5] = (int32_t)sizeof(sapt_fused_args);
   out[6] = (int32_t)sizeof(sapt_local_surrogate);
+  out[7] = (int32_t)sizeof(sapt_step_args);
+  return SAPT_OK;
+}
+
+// n MCMC steps of the random-walk forks without host code between the kernels (the order is PTEngine.step's)
+extern "C" int sapt_step(sapt_problem_t* p, const sapt_step_args* a, void* stream) {
+  SAPT_REQUIRE(p && a && a->n_steps >= 0 && a->counters && a->L_train && a->nc_train && a->sq_train, "sapt_step");
+  SAPT_REQUIRE(!a->prop.step_dev && !a->acc.step_dev, "sapt_step advances the step index itself: step_dev must be NULL");
+  sapt_propose_args prop = a->prop;
+  sapt_accept_args acc = a->acc;
+  const int R = prop.R;
+  const int64_t ntest = p->set[1].n;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int s = 0; s < a->n_steps; ++s) {
+    const int step = a->prop.step + s;
+    SAPT_CUDA(cudaMemsetAsync(a->counters, 0, 3 * sizeof(int32_t), st));
+    prop.step = step;
+    int rc = sapt_propose(&prop, stream);
+    if (rc) return rc;
+    const bool use_sur = a->use_surrogate != 0;
+    const bool sur_possible = use_sur && prop.surrogate_ready && prop.surrogate_prob > 0 && step >= prop.gate + 1;
+    if (sur_possible) {
+      SAPT_REQUIRE(a->W1 && a->sur_s, "sapt_step: surrogate weights");
+      rc = sapt_surrogate_predict(prop.proposal, prop.ld, R, prop.P, prop.sur_rows, prop.n_sur, a->W1, a->b1, a->h1, a->W2, a->b2, a->h2,
+                                  a->W3, a->b3, a->sur_s, stream);
+      if (rc) return rc;
+    }
+    const int32_t* true_rows = use_sur ? prop.true_rows : nullptr;
+    const int32_t* n_true = use_sur ? prop.n_true : nullptr;
+    const bool all_rows = a->compare_surrogate || !use_sur;                         // RV:543-544
+    rc = sapt_loglik(p, 0, prop.proposal, prop.ld, R, all_rows ? nullptr : true_rows, all_rows ? nullptr : n_true, a->L_train,
+                     a->nc_train, a->sq_train, a->path, stream);
+    if (rc) return rc;
+    if (ntest > 0) {
+      rc = sapt_loglik(p, 1, prop.proposal, prop.ld, R, true_rows, n_true, a->L_test, a->nc_test, a->sq_test, a->path, stream);
+      if (rc) return rc;
+    }
+    acc.step = step;
+    rc = sapt_mh_accept(&acc, stream);
+    if (rc) return rc;
+  }
   return SAPT_OK;
 }

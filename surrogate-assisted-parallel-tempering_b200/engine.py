@@ -267,6 +267,47 @@ class PTEngine:
                 self.hist["pos_w"][0].fill_(1.0)  # pos_w = np.ones (RW:431)
 
     # ------------------------------------------------------------------------------------
+    def _propose_args(self, i, sdev, gate, use_sur, sur_ready) -> _lib.ProposeArgs:
+        cfg, sp = self.cfg, self.spec
+        a = _lib.ProposeArgs()
+        a.base = self.theta.data_ptr(); a.proposal = self.prop.data_ptr(); a.ld = self.ld; a.R = self.R; a.P = self.P
+        a.slot_of_row = self.slot_of_row.data_ptr(); a.slot_offset = 0
+        a.step_w = cfg.step_w; a.sigma_squared = cfg.sigma_squared; a.prior_prop = self.prior_prop.data_ptr()
+        a.seed = cfg.seed & 0xFFFFFFFF; a.kind = _lib.STREAM_Z1; a.step = i; a.step_dev = sdev
+        z1 = self._inj("z1", i); a.z_inject = z1.data_ptr() if z1 is not None else None
+        a.decide = 1 if use_sur else 0
+        a.redraw = 1 if sp.lg_flow else 0
+        a.surrogate_ready = 1 if sur_ready else 0
+        a.surrogate_prob = cfg.surrogate_prob; a.gate = gate
+        z2 = self._inj("z2", i); a.z2_inject = z2.data_ptr() if z2 is not None else None
+        ku = self._inj("ku", i); a.ku_inject = ku.data_ptr() if ku is not None else None
+        a.is_sur = self.is_sur.data_ptr(); a.true_rows = self.true_rows.data_ptr(); a.n_true = self.counters[0:1].data_ptr()
+        a.sur_rows = self.sur_rows.data_ptr(); a.n_sur = self.counters[1:2].data_ptr()
+        return a
+
+    def _accept_args(self, i, sdev, use_sur) -> _lib.AcceptArgs:
+        cfg, sp = self.cfg, self.spec
+        ntr, nte = self.p.n
+        m = _lib.AcceptArgs()
+        m.theta = self.theta.data_ptr(); m.proposal = self.prop.data_ptr(); m.ld = self.ld; m.R = self.R; m.P = self.P
+        m.st = self._chain_state(); m.hist = self._history(); m.step = i; m.step_dev = sdev; m.flags = self.flags
+        m.is_sur = self.is_sur.data_ptr() if use_sur else None
+        m.L_train = self.L_train.data_ptr(); m.nc_train = self.nc_train.data_ptr(); m.sq_train = self.sq_train.data_ptr()
+        m.L_test = self.L_test.data_ptr(); m.nc_test = self.nc_test.data_ptr(); m.sq_test = self.sq_test.data_ptr()
+        m.n_train = ntr; m.n_test = nte
+        m.prior_prop = self.prior_prop.data_ptr(); m.sur_s = self.sur_s.data_ptr()
+        m.min_y = self.surrogate.min_y; m.max_y = self.surrogate.max_y
+        m.seed = cfg.seed & 0xFFFFFFFF
+        u = self._inj("u", i); m.u_inject = u.data_ptr() if u is not None else None
+        if self.train_theta is not None:
+            m.train_theta = self.train_theta.data_ptr(); m.train_L = self.train_L.data_ptr()
+            m.train_count = self.train_count.data_ptr(); m.train_cap = self.train_cap
+        m.capture = 0 if sp.lg_flow else 1
+        m.surg_first = self.surg_first.data_ptr() if sp.lg_flow else None
+        if self.ls is not None:
+            m.ls_pred = self.ls_pred.data_ptr(); m.ls_avg = self.ls_avg.data_ptr()
+        return m
+
     def step(self, i: int):
         """Enqueue one MCMC step of every local chain (no host synchronisation). In graph mode `i` is the
         offset inside the captured segment and the absolute step lives in self.step_dev[0]."""
@@ -279,21 +320,9 @@ class PTEngine:
         self._train_synced = False     # this step may append training rows on the hosting rank
         self.counters[:3].zero_()
         gate = cfg.swap_interval if sp.gate_on_swap_interval else cfg.surrogate_interval
-        a = _lib.ProposeArgs()
-        a.base = self.theta.data_ptr(); a.proposal = self.prop.data_ptr(); a.ld = self.ld; a.R = self.R; a.P = self.P
-        a.slot_of_row = self.slot_of_row.data_ptr(); a.slot_offset = 0
-        a.step_w = cfg.step_w; a.sigma_squared = cfg.sigma_squared; a.prior_prop = self.prior_prop.data_ptr()
-        a.seed = cfg.seed & 0xFFFFFFFF; a.kind = _lib.STREAM_Z1; a.step = i; a.step_dev = sdev
-        z1 = self._inj("z1", i); a.z_inject = z1.data_ptr() if z1 is not None else None
-        a.decide = 1 if use_sur else 0
-        a.redraw = 1 if sp.lg_flow else 0
         sur_ready = self.ls_ready if self.ls is not None else self.surrogate.ready
-        a.surrogate_ready = 1 if sur_ready else 0
-        a.surrogate_prob = cfg.surrogate_prob; a.gate = gate
-        z2 = self._inj("z2", i); a.z2_inject = z2.data_ptr() if z2 is not None else None
-        ku = self._inj("ku", i); a.ku_inject = ku.data_ptr() if ku is not None else None
-        a.is_sur = self.is_sur.data_ptr(); a.true_rows = self.true_rows.data_ptr(); a.n_true = self.counters[0:1].data_ptr()
-        a.sur_rows = self.sur_rows.data_ptr(); a.n_sur = self.counters[1:2].data_ptr()
+        a = self._propose_args(i, sdev, gate, use_sur, sur_ready)
+        z2 = self._inj("z2", i)
         _lib.check(L.sapt_propose(C.byref(a), st), "sapt_propose")
 
         sur_possible = use_sur and sur_ready and cfg.surrogate_prob > 0 and (self._graph_mode or i >= gate + 1)
@@ -356,24 +385,7 @@ class PTEngine:
                 self.p.loglik(self.prop, 1, rows=true_rows, n_rows=n_true, out=out_te, path=cfg.path)
                 self.evals += self.R * nte
 
-        m = _lib.AcceptArgs()
-        m.theta = self.theta.data_ptr(); m.proposal = self.prop.data_ptr(); m.ld = self.ld; m.R = self.R; m.P = self.P
-        m.st = self._chain_state(); m.hist = self._history(); m.step = i; m.step_dev = sdev; m.flags = self.flags
-        m.is_sur = self.is_sur.data_ptr() if use_sur else None
-        m.L_train = self.L_train.data_ptr(); m.nc_train = self.nc_train.data_ptr(); m.sq_train = self.sq_train.data_ptr()
-        m.L_test = self.L_test.data_ptr(); m.nc_test = self.nc_test.data_ptr(); m.sq_test = self.sq_test.data_ptr()
-        m.n_train = ntr; m.n_test = nte
-        m.prior_prop = self.prior_prop.data_ptr(); m.sur_s = self.sur_s.data_ptr()
-        m.min_y = self.surrogate.min_y; m.max_y = self.surrogate.max_y
-        m.seed = cfg.seed & 0xFFFFFFFF
-        u = self._inj("u", i); m.u_inject = u.data_ptr() if u is not None else None
-        if self.train_theta is not None:
-            m.train_theta = self.train_theta.data_ptr(); m.train_L = self.train_L.data_ptr()
-            m.train_count = self.train_count.data_ptr(); m.train_cap = self.train_cap
-        m.capture = 0 if sp.lg_flow else 1
-        m.surg_first = self.surg_first.data_ptr() if sp.lg_flow else None
-        if self.ls is not None:
-            m.ls_pred = self.ls_pred.data_ptr(); m.ls_avg = self.ls_avg.data_ptr()
+        m = self._accept_args(i, sdev, use_sur)
         _lib.check(L.sapt_mh_accept(C.byref(m), st), "sapt_mh_accept")
 
     # ------------------------------------------------------------------------------------
@@ -543,6 +555,45 @@ class PTEngine:
         ntr, nte = self.p.n
         self.evals += n * self.R * (ntr + nte)
 
+    def native_supported(self) -> bool:
+        """sapt_step drives whole steps of the random-walk forks inside the library (no Python between the kernels)."""
+        return not self.spec.lg_flow and self.ls is None and self.inj is None
+
+    def native_steps(self, i0: int, n: int):
+        """Steps i0 .. i0+n-1 of every local chain through ONE C call (sapt_step): same kernels, same order as step()."""
+        cfg, sp = self.cfg, self.spec
+        use_sur = bool(cfg.use_surrogate)
+        self._train_synced = False
+        gate = cfg.swap_interval if sp.gate_on_swap_interval else cfg.surrogate_interval
+        sa = _lib.StepArgs()
+        sa.prop = self._propose_args(i0, None, gate, use_sur, self.surrogate.ready)
+        sa.acc = self._accept_args(i0, None, use_sur)
+        sa.use_surrogate = 1 if use_sur else 0
+        sa.compare_surrogate = 1 if sp.compare_surrogate else 0
+        sa.h1 = self.surrogate.h1; sa.h2 = self.surrogate.h2
+        if self.surrogate.ready:
+            w = self.surrogate.weights
+            sa.W1 = w["W1"].data_ptr(); sa.b1 = w["b1"].data_ptr(); sa.W2 = w["W2"].data_ptr(); sa.b2 = w["b2"].data_ptr()
+            sa.W3 = w["W3"].data_ptr(); sa.b3 = w["b3"].data_ptr()
+        sa.sur_s = self.sur_s.data_ptr()
+        sa.L_train = self.L_train.data_ptr(); sa.nc_train = self.nc_train.data_ptr(); sa.sq_train = self.sq_train.data_ptr()
+        sa.L_test = self.L_test.data_ptr(); sa.nc_test = self.nc_test.data_ptr(); sa.sq_test = self.sq_test.data_ptr()
+        sa.counters = self.counters.data_ptr(); sa.path = cfg.path; sa.n_steps = n
+        _lib.check(self.L.sapt_step(self.p.handle, C.byref(sa), current_stream_ptr()), "sapt_step")
+        ntr, nte = self.p.n
+        self.evals += n * self.R * (ntr + nte)
+
+    def _run_native(self, n):
+        pts = self._rendezvous_steps(n)
+        i = 0
+        while i < n:
+            j = i
+            while j not in pts and j < n - 1:
+                j += 1
+            self.native_steps(i, j - i + 1)
+            self.rendezvous(j)
+            i = j + 1
+
     def _run_fused(self, n):
         pts = self._rendezvous_steps(n)
         i = 0
@@ -554,12 +605,14 @@ class PTEngine:
             self.rendezvous(j)
             i = j + 1
 
-    def run(self, steps: Optional[int] = None, graph: Optional[bool] = None, fused: Optional[bool] = None):
+    def run(self, steps: Optional[int] = None, graph: Optional[bool] = None, fused: Optional[bool] = None, native: Optional[bool] = None):
         """Run the chain loop. `graph=True` captures the launches of one interval between rendezvous points in a
         CUDA graph and replays it (the step index is read from device memory), removing the per-launch host cost.
         Measured at C1 (8 chains x 699 rows) the eager loop is already GPU-latency bound (~67 us per step for ~10
         dependent small kernels) and capture + instantiation only pays off for runs of >~10^4 steps, so the
-        default is off; the mode is kept for host-bound deployments (slow CPUs, many short kernels)."""
+        default is off; the mode is kept for host-bound deployments (slow CPUs, many short kernels).
+        `native` (default: on where it applies) runs every stretch between two rendezvous through ONE sapt_step call —
+        the C driver of the random-walk forks' loop body — instead of ~6 ctypes calls per step."""
         n = self.cfg.samples - 1 if steps is None else steps
         if fused is None:
             fused = self.fused_supported()
@@ -570,6 +623,12 @@ class PTEngine:
         if graph is None:
             graph = False
         if not graph or self.inj is not None or self.cfg.world != 1:
+            if native is None:
+                native = self.native_supported()
+            if native:
+                if not self.native_supported():
+                    raise NotImplementedError("sapt_step drives the random-walk forks with Philox streams only")
+                return self._run_native(n)
             for i in range(n):
                 self.step(i)
                 self.rendezvous(i)

@@ -642,7 +642,7 @@ def test_cuda_graph_replay_equals_eager(lib, variant, use_sur, use_lg):
                            use_surrogate=use_sur, use_langevin=use_lg, learn_rate=0.05, seed=5)
         eng = PTEngine(prob, assign_temperatures(6, 4.0), cfg, surrogate_trainer=lambda batch, sig: sw[sig - 1])
         eng.initialize(g["W"][1])
-        eng.run(graph=graph, fused=False); torch.cuda.synchronize()
+        eng.run(graph=graph, fused=False, native=False); torch.cuda.synchronize()
         return eng.results(), eng
 
     (a, ea), (b, eb) = run(False), run(True)
@@ -652,6 +652,39 @@ def test_cuda_graph_replay_equals_eager(lib, variant, use_sur, use_lg):
     for k in ("lhood_list", "surg_likeh_list", "acc_train", "rmse_test"):
         assert np.array_equal(np.nan_to_num(a[k], nan=-1.0, posinf=-2.0), np.nan_to_num(b[k], nan=-1.0, posinf=-2.0)), k
     assert a["num_swap"] == b["num_swap"] and len(a["swap_decisions"]) == len(b["swap_decisions"])
+    if use_sur:
+        assert a["is_surrogate_step"].sum() > 0
+
+
+@pytest.mark.parametrize("variant,use_sur", [("rw", False), ("rw", True), ("rv", True)])
+def test_native_step_driver_equals_python_chained_steps(lib, variant, use_sur):
+    """sapt_step (the C driver of the random-walk forks' loop body: n steps per call, no host code between the
+    kernels) must reproduce the step-by-step path of PTEngine.step bit for bit."""
+    from sapt_b200.engine import EngineConfig, PTEngine
+    from sapt_b200.ladder import assign_temperatures
+    from sapt_b200.problem import Problem
+    g = gu.load("unit_cancer")
+    topo = [int(v) for v in g["topology"]]
+    prob = Problem(topo, g["train"][:200], g["test"][:80])
+    sw = [so.make_surrogate_weights(prob.P, 1, 70 + s) for s in range(12)]
+
+    def run(native):
+        cfg = EngineConfig(variant=variant, samples=64, swap_interval=9, surrogate_interval=11, surrogate_prob=0.4, use_surrogate=use_sur, seed=5)
+        eng = PTEngine(prob, assign_temperatures(6, 4.0), cfg, surrogate_trainer=lambda batch, sig: sw[sig - 1])
+        eng.initialize(g["W"][1])
+        assert eng.native_supported()
+        eng.run(fused=False, native=native); torch.cuda.synchronize()
+        return eng.results(), eng
+
+    (a, ea), (b, eb) = run(False), run(True)
+    assert ea.evals == eb.evals
+    for k in ("accepted", "is_surrogate_step", "pos_w", "accept_list", "naccept", "row_of_slot"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("lhood_list", "surg_likeh_list", "acc_train", "rmse_test", "likeh_list"):
+        assert np.array_equal(np.nan_to_num(a[k], nan=-1.0, posinf=-2.0), np.nan_to_num(b[k], nan=-1.0, posinf=-2.0)), k
+    assert a["num_swap"] == b["num_swap"] and len(a["surr_batches"]) == len(b["surr_batches"])
+    for x, y in zip(a["surr_batches"], b["surr_batches"]):
+        assert np.array_equal(x, y)
     if use_sur:
         assert a["is_surrogate_step"].sum() > 0
 
