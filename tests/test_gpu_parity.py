@@ -689,6 +689,38 @@ def test_native_step_driver_equals_python_chained_steps(lib, variant, use_sur):
         assert a["is_surrogate_step"].sum() > 0
 
 
+def test_plain_c_host_over_the_c_abi_equals_engine(lib):
+    """examples/c_host/run_pt.c drives a whole parallel-tempering run through include/sapt.h from plain C (gcc, CUDA
+    runtime, no Python, no PyTorch): sapt_problem_create_f32, sapt_loglik, sapt_prior, sapt_step, sapt_swap_sweep.
+    PTEngine on the same data, temperatures and seed must end in the same state."""
+    import json, math, os, subprocess
+    from sapt_b200.engine import EngineConfig, PTEngine
+    from sapt_b200.problem import Problem
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "c_host", "run_pt")
+    if not os.path.isfile(exe):
+        pytest.skip("examples/c_host/run_pt not built (python -c 'import __graft_entry__ as g; g.build()')")
+    R, S, SI, seed = 8, 40, 5, 7
+    out = subprocess.run([exe, str(R), str(S), str(SI), str(seed)], check=True, capture_output=True, text=True, timeout=120).stdout
+    c = json.loads(out.strip().splitlines()[-1])
+    D, H, O, NTR, NTE = 9, 12, 2, 300, 120
+    i = np.arange(NTR)[:, None]; d = np.arange(D)[None, :]
+    xtr = ((((i * 37 + d * 11) % 23) - 11) / 8.0).astype(np.float32); ytr = ((np.arange(NTR) * 7 + 3) % O).astype(np.int32)
+    i = np.arange(NTE)[:, None]
+    xte = ((((i * 29 + d * 13) % 19) - 9) / 6.0).astype(np.float32); yte = ((np.arange(NTE) * 5 + 1) % O).astype(np.int32)
+    prob = Problem.from_f32([D, H, O], xtr, ytr, xte, yte)
+    w0 = ((((np.arange(prob.P) * 17 + 5) % 41) - 20) / 40.0).astype(np.float32)
+    temps = np.array([math.pow(4.0, r / (R - 1)) for r in range(R)])
+    cfg = EngineConfig(variant="rw", samples=S, swap_interval=SI, surrogate_interval=SI, use_surrogate=False, seed=seed, record_history=False)
+    eng = PTEngine(prob, temps, cfg)
+    eng.initialize(w0); eng.run(fused=False); torch.cuda.synchronize()
+    res = eng.results()
+    assert c["naccept"] == res["naccept"].tolist() and sum(c["naccept"]) > 0
+    assert c["row_of_slot"] == res["row_of_slot"].tolist()
+    assert c["num_swap"] == res["num_swap"] and c["num_swap"] > 0
+    np.testing.assert_allclose(c["lik_cur"], res["likelihood_copy"], rtol=1e-13)
+    assert c["launches"] > 0
+
+
 def test_c1_posterior_accuracy_envelope(lib):
     """C1 end to end through the reference-facing class: Cancer 9-12-2, 8 chains, random-walk PT, no surrogate.
     The reference's committed runs give train 95.6 +- 0.6 / test 98.8 +- 0.5 % for this problem
