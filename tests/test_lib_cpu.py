@@ -72,3 +72,18 @@ def test_no_cpu_fallback():
     from sapt_b200.problem import Problem
     with pytest.raises(RuntimeError):
         Problem([2, 2, 2], np.zeros((4, 3)))
+
+
+def test_header_is_plain_c_and_c_host_builds(tmp_path):
+    """include/sapt.h is the drop-in boundary: it must compile as C (C11) without any C++/CUDA/torch type, and the
+    plain-C host example must link against libsapt.so."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text('#include "sapt.h"\nint main(void) { return sapt_abi_version == 0; }\n')
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)], check=True)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples", "c_host"), "-B", "run_pt"], check=True, capture_output=True)
+    assert os.path.isfile(os.path.join(ROOT, "examples", "c_host", "run_pt"))
