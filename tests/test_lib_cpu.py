@@ -83,7 +83,7 @@ def test_header_is_plain_c_and_c_host_builds(tmp_path):
     if gcc is None:
         pytest.skip("gcc not available")
     src = tmp_path / "t.c"
-    src.write_text('#include "sapt.h"\nint main(void) { return sapt_abi_version == 0; }\n')
+    src.write_text('#include "sapt.h"\nint main(void) { sapt_step_args a; (void)a; return (int)sizeof(sapt_accept_args) == 0; }\n')
     subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)], check=True)
     subprocess.run(["make", "-C", os.path.join(ROOT, "examples", "c_host"), "-B", "run_pt"], check=True, capture_output=True)
     assert os.path.isfile(os.path.join(ROOT, "examples", "c_host", "run_pt"))
