@@ -3,30 +3,35 @@
 // Replaces, for all chains a GPU hosts: ptReplica.likelihood_func (_revamp.py:391-402) ->
 // Network.evaluate_proposal (:155-174) -> ForwardPass (:70-76) + softmax (:129-131).
 //
-//   MMA-1  D1[128 rows, 4 chains x HP] = X . W1'      smem x smem -> TMEM     (kind::f16, bf16 in, fp32 acc)
+//   MMA-1  D1[128 rows, UC chains x HP] = X . W1'     smem x smem -> TMEM     (kind::f16, bf16 in, fp32 acc)
 //   phase 1 (thread = data row):  tcgen05.ld D1 -> h = sigmoid -> h = h1 + h2 (bf16 pieces) ->
 //           tcgen05.st HV[chain] = [h1 | h2]          (the A operand of MMA-2, never leaves TMEM)
-//   MMA-2  D2[128 rows, ON] = H . W2'                 TMEM x smem -> TMEM, one per chain; D2 overwrites the
-//                                                      chain's dead D1 columns
-//   phase 2: tcgen05.ld D2 (+ bias) -> sigmoid -> softmax / argmax -> fp64 log-likelihood sums
+//   MMA-2  D2[128 rows, N2] = H . W2'                 TMEM x smem -> TMEM, per chain, into its own D2 columns
+//   phase 2: tcgen05.ld D2 -> sigmoid -> softmax / argmax over exactly O outputs -> fp64 log-likelihood sums
 //
 // fp32-grade accuracy from bf16 tensor cores: every fp32 operand is split into bf16 pieces that sum to it
 // (x = x1+x2+x3, w = w1+w2+w3 exactly; h = h1+h2 to 2^-16, unbiased) and the significant cross terms are
 // accumulated by pointing successive MMA K-steps at different (A chunk, B chunk) pairs — each piece is
-// stored once. MMA-1 (K = 7 x 16): (x1,w1) (x1,w2) (x2,w1) (x1,w3) (x2,w2) (x3,w1) (1,b): dropped terms
-// O(2^-24). MMA-2: h1.[w1|w2|w3] and h2.[w1|w2] with the weight pieces side by side along N (three partial
-// sums per output, added by the epilogue), so each activation piece is read from TMEM once. Weights are pre-scaled by -log2(e) (biases +log2(e)),
-// so an accumulator is t = -log2(e) z and sigmoid(z) = 1 / (1 + 2^t).
+// stored once. MMA-1 (K = (6 DKC + 1) x 16, DKC = 16-feature chunks per piece): (x1,w1) (x1,w2) (x2,w1) (x1,w3)
+// (x2,w2) (x3,w1) (1,b): dropped terms O(2^-24). MMA-2: h1.[w1|w2|w3] and h2.[w1|w2] with the weight pieces side by
+// side along N (partial sums per output, added by the epilogue), so each activation piece is read from TMEM once.
+// Weights are pre-scaled by -log2(e) (biases +log2(e)), so an accumulator is t = -log2(e) z and
+// sigmoid(z) = 1 / (1 + 2^t). When H < HP the output bias rides in MMA-2: the spare hidden slot's activation is
+// sigmoid(0) = 1/2 and its W2 row holds twice the bias.
 //
-// The SIMT side is bound by the SFU (MUFU) pipe, so reciprocals are batched four at a time
-// (1/a = (1/(abcd)) * bcd: one MUFU.RCP + 9 FMUL per four sigmoids) and the bf16 split uses integer
-// ops (truncate / add-half + PRMT) instead of F2FP conversions, which also issue on the SFU pipe.
+// The SIMT side is bound by the SFU (MUFU) pipe and by instruction issue, so reciprocals are batched four at a
+// time (1/a = (1/(abcd)) * bcd: one MUFU.RCP + 9 FMUL per four sigmoids), the bf16 split uses integer ops
+// (truncate / add-half + PRMT) instead of F2FP conversions, which also issue on the SFU pipe, and the sigmoid
+// groups of phase 1 are kept in order (see phase 1) so that SFU and FP32/integer work alternate finely.
 //
-// CTA = (row chunk, CH = 256/HP chains). Warp 16 lane 0: TMA producer (A ring; B1, W2 panels once).
-// Warp 17: TMEM alloc + single-thread MMA issue. Warps 0-15: epilogue; warp (quarter q, index e) owns TMEM
-// lanes 32q.. and one chain of every unit (16 epilogue warps). TMEM (512 columns): D1 (4 HP columns), two HV
-// buffers of 4 HP columns, two D2 buffers of 4 ON columns. The epilogue is software pipelined (phase 1 of unit
-// u+1 before phase 2 of unit u) so that every MMA has a full unit of slack before its result is awaited.
+// Geometry = TcCfg<HP, ON, DKC> (HP = 16/32/64 padded hidden width, ON = 16/32 padded outputs, DKC = ceil(D/16)):
+// CTA = (row chunk, CH chains), CH and the A-ring depth from the 224 KB shared-memory budget; a unit = UC chains
+// (4, or 2 for HP = 64). Warp 16 lane 0: TMA producer (A ring, KBA boxes per tile; B1, W2 panels once). Warp 17:
+// TMEM alloc + single-thread MMA issue. Warps 0-15: epilogue; warp (quarter q, index e) owns TMEM lanes 32q.. and
+// one chain of every unit (for HP = 64: half the hidden units of a chain; the two halves alternate on phase 2).
+// TMEM (512 columns): D1 (UC x HP) | HV (UC x HP) | D2 (UC x N2, doubled when it fits). The epilogue is software
+// pipelined (phase 1 of unit u+1 before phase 2 of unit u) so that every MMA has a full unit of slack before its
+// result is awaited.
 #include <algorithm>
 #include <type_traits>
 #include <vector>
