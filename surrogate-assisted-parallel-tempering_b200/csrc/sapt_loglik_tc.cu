@@ -85,9 +85,10 @@ int tc_prepare_dataset(sapt_problem* p, int which, const float* x_host, int64_t 
       }
     }
     row[3 * dw] = one; row[3 * dw + 1] = one; row[3 * dw + 2] = one;
-    // batch-Langevin gradient (sapt_langevin_tc.cu): for D > 32 the bias chunk lies outside the 128 image columns its
-    // X^T.dh contraction covers, so the first spare column of the x1 piece carries the ones (its weights are zero)
-    if (dw >= 48 && p->D < dw) row[p->D] = one;
+    // when D is not a multiple of 16 the first spare column of the x1 piece carries a 1.0 as well: the likelihood kernel
+    // then takes its bias from there (TcCfg BIASX, sapt_loglik_tc2.cu), and for D > 32, where the bias chunk lies outside
+    // the 128 image columns of the batch-Langevin contraction X^T.dh, so does that kernel (sapt_langevin_tc.cu)
+    if (p->D < dw) row[p->D] = one;
   }
   SAPT_CUDA(cudaMalloc(&ds.a_bf16, img.size() * 2));
   SAPT_CUDA(cudaMemcpy(ds.a_bf16, img.data(), img.size() * 2, cudaMemcpyHostToDevice));

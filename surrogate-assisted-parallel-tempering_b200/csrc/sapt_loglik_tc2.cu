@@ -56,13 +56,20 @@ constexpr int kSmemLimit = 224 * 1024;
 
 // Compile-time geometry of one kernel variant. HP = padded hidden width (16/32/64), ON = padded output width
 // (16/32), DKC = 16-feature chunks per x piece (D <= 16 DKC).
-template <int HP, int ON, int DKC>
+// The third parameter DK packs two things: DK & 7 = DKC, and DK >= 8 = "bias in x1": when D is not a multiple of 16 the
+// first spare column of the x1 piece of the operand image holds 1.0 (tc_prepare_dataset) and the bias pieces b1, b2, b3
+// sit in that column of the w1, w2, w3 pieces of B1, so MMA-1 needs no bias K-step and no bias chunk: one MMA less per
+// unit, and for D > 48 one 128-byte K block less per row (A stage 64 -> 48 KB, B1 panel 3/4), which doubles the
+// chains a CTA can keep at HP = 64.
+template <int HP, int ON, int DK>
 struct TcCfg {
+  static constexpr bool BIASX = DK >= 8;
+  static constexpr int DKC = DK & 7;
   static constexpr int HALVES = (HP == 64) ? 2 : 1;       // epilogue warps sharing one chain's hidden units
   static constexpr int UC = 4 / HALVES;                   // chains per unit (one MMA-1)
   static constexpr int HW = HP / HALVES;                  // hidden units per epilogue warp
   static constexpr int N1 = UC * HP;                      // MMA-1 N (<= 128)
-  static constexpr int KA = 48 * DKC + 16;                // used bf16 per A / B1 row: [x1|x2|x3|bias chunk]
+  static constexpr int KA = 48 * DKC + (BIASX ? 0 : 16);  // used bf16 per A / B1 row: [x1|x2|x3|bias chunk]
   static constexpr int KBA = (KA + 63) / 64;              // 128-byte K blocks per row
   static constexpr int N2 = (ON == 16) ? 48 : 64;         // D2 columns per chain
   static constexpr int PARTS = N2 / ON;
@@ -103,7 +110,7 @@ struct Tc2Params {
 // W2: [group][CH][3 ON rows][64]  : row (p, o) = piece p of -log2(e) W2[:, o] over the HP hidden units (rest 0).
 //     MMA-2 reads rows [0, N2) as one operand against h1 and rows [0, 2 ON) again against h2.
 __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O,
-                                int HP, int ON, int CH, int DKC, int KROW, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2) {
+                                int HP, int ON, int CH, int DKC, int KROW, int biasx, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2) {
   constexpr int KW = 64;
   const int nact = n_rows ? *n_rows : R;
   const int pos = blockIdx.x;
@@ -130,11 +137,20 @@ __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* r
     __nv_bfloat16* dst = brow0 + (int64_t)h * KROW;
     dst[d] = p[0]; dst[DW + d] = p[1]; dst[2 * DW + d] = p[2];
   }
+  __syncthreads();
   for (int i = threadIdx.x; i < HP * (KROW - 3 * DW); i += blockDim.x) {   // bias chunk + tail padding
     const int h = i / (KROW - 3 * DW), q = i - h * (KROW - 3 * DW);
     __nv_bfloat16 v = zero;
-    if (h < H && q < 3) { __nv_bfloat16 b[3]; split3(kLog2e * src[D * H + H * O + h], b[0], b[1], b[2]); v = b[q]; }
+    if (!biasx && h < H && q < 3) { __nv_bfloat16 b[3]; split3(kLog2e * src[D * H + H * O + h], b[0], b[1], b[2]); v = b[q]; }
     brow0[(int64_t)h * KROW + 3 * DW + q] = v;
+  }
+  if (biasx) {   // bias pieces in column D of the w1 / w2 / w3 pieces: they meet the 1.0 in column D of the x1 piece
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+      __nv_bfloat16 b[3];
+      split3(kLog2e * src[D * H + H * O + h], b[0], b[1], b[2]);
+      __nv_bfloat16* dst = brow0 + (int64_t)h * KROW;
+      dst[D] = b[0]; dst[DW + D] = b[1]; dst[2 * DW + D] = b[2];
+    }
   }
   for (int i = threadIdx.x; i < ON * KW; i += blockDim.x) {
     const int o = i / KW, h = i - o * KW;
@@ -150,7 +166,7 @@ __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* r
 
 int launch_tc2_pack(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O, int HP, int ON, int CH,
                     int DKC, int KROW, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2, int n_blocks, cudaStream_t st) {
-  tc2_pack_kernel<<<n_blocks, 256, 0, st>>>(theta, ld, rows, n_rows, R, D, H, O, HP, ON, CH, DKC, KROW, b1img, w2img, bias2);
+  tc2_pack_kernel<<<n_blocks, 256, 0, st>>>(theta, ld, rows, n_rows, R, D, H, O, HP, ON, CH, DKC, KROW, 0, b1img, w2img, bias2);
   SAPT_CHECK_LAUNCH();
   return SAPT_OK;
 }
@@ -197,12 +213,13 @@ __device__ __forceinline__ void sigmoid4_scaled(float t0, float t1, float t2, fl
   s0 = rab * a1; s1 = rab * a0; s2 = rcd * a3; s3 = rcd * a2;
 }
 
-template <int HP, int ON, int DKC>
+template <int HP, int ON, int DK>
 __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b1,
                                                                      const __grid_constant__ CUtensorMap map_w2, Tc2Params p) {
   using namespace v2;
-  using C = TcCfg<HP, ON, DKC>;
+  using C = TcCfg<HP, ON, DK>;
+  constexpr int DKC = C::DKC;
   constexpr int HALVES = C::HALVES, UC = C::UC, HW = C::HW, N1 = C::N1, KBA = C::KBA, N2 = C::N2, PARTS = C::PARTS;
   constexpr int UPT = C::UPT, CH = C::CH, STAGES = C::STAGES, kD2Bufs = C::kD2Bufs;
   static_assert(UPT >= 1, "variant does not fit in shared memory");
@@ -315,7 +332,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
 #pragma unroll
           for (int j = 0; j < DKC; ++j)
             tc_mma_bf16(tmem_base, a_at(pa[q] * DKC + j), b_at(pb[q] * DKC + j), idesc1, (q | j) ? 1u : 0u);
-        tc_mma_bf16(tmem_base, a_at(3 * DKC), b_at(3 * DKC), idesc1, 1u);
+        if constexpr (!C::BIASX) tc_mma_bf16(tmem_base, a_at(3 * DKC), b_at(3 * DKC), idesc1, 1u);
         if (uu == UPT - 1) tc_commit(&empty_a[s]);
         tc_commit(d1_full);
       };
@@ -563,6 +580,12 @@ static int tc2_dispatch(int HP, int ON, int DKC, F&& fn) {
   SAPT_V(32, 32, 1) SAPT_V(32, 32, 2) SAPT_V(32, 32, 3) SAPT_V(32, 32, 4)
   SAPT_V(64, 16, 1) SAPT_V(64, 16, 2) SAPT_V(64, 16, 3) SAPT_V(64, 16, 4)
   SAPT_V(64, 32, 1) SAPT_V(64, 32, 2) SAPT_V(64, 32, 3) SAPT_V(64, 32, 4)
+  // bias in the spare x1 column (D not a multiple of 16)
+  SAPT_V(16, 16, 9) SAPT_V(16, 16, 10) SAPT_V(16, 16, 11) SAPT_V(16, 16, 12)
+  SAPT_V(32, 16, 9) SAPT_V(32, 16, 10) SAPT_V(32, 16, 11) SAPT_V(32, 16, 12)
+  SAPT_V(32, 32, 9) SAPT_V(32, 32, 10) SAPT_V(32, 32, 11) SAPT_V(32, 32, 12)
+  SAPT_V(64, 16, 9) SAPT_V(64, 16, 10) SAPT_V(64, 16, 11) SAPT_V(64, 16, 12)
+  SAPT_V(64, 32, 9) SAPT_V(64, 32, 10) SAPT_V(64, 32, 11) SAPT_V(64, 32, 12)
 #undef SAPT_V
   set_error("tcgen05 path: no variant for HP=%d ON=%d DKC=%d", HP, ON, DKC);
   return SAPT_ERR_UNSUPPORTED;
@@ -574,6 +597,7 @@ static void tc2_shape(const sapt_problem* p, int& HP, int& ON, int& DKC) {
   HP = p->H <= 16 ? 16 : (p->H <= 32 ? 32 : 64);
   ON = p->O <= 16 ? 16 : 32;
   DKC = tc2_dkc(p->D);
+  if (p->D < 16 * DKC) DKC += 8;   // see TcCfg: bias in the spare x1 column
 }
 
 bool tc2_supported(int D, int H, int O) {
@@ -626,7 +650,8 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   int32_t* partNc = reinterpret_cast<int32_t*>(partL + (size_t)n_chunks * R);
   int32_t* partSq = partNc + (size_t)n_chunks * R;
 
-  tc2_pack_kernel<<<n_groups * CH, 256, 0, st>>>(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, ON, CH, DKC, g.KROW, b1img, w2img, bias2);
+  tc2_pack_kernel<<<n_groups * CH, 256, 0, st>>>(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, ON, CH, DKC & 7, g.KROW, DKC >= 8 ? 1 : 0, b1img,
+                                                 w2img, bias2);
   SAPT_CHECK_LAUNCH();
   CUtensorMap mb1, mw2;
   rc = tc_make_map_2d(&mb1, b1img, (uint64_t)g.KROW, (uint64_t)n_groups * CH * HP, (uint32_t)(CH * HP));
