@@ -61,8 +61,14 @@ constexpr int kSmemLimit = 224 * 1024;
 // sit in that column of the w1, w2, w3 pieces of B1, so MMA-1 needs no bias K-step and no bias chunk: one MMA less per
 // unit, and for D > 48 one 128-byte K block less per row (A stage 64 -> 48 KB, B1 panel 3/4), which doubles the
 // chains a CTA can keep at HP = 64.
-template <int HP, int ON, int DK>
+// The second parameter ONX is the padded output width ON (16 / 32), or 8 / 12 = "ON = 16 geometry, O <= 8 / 12": phase 2 then
+// reads 8 / 12 instead of 16 accumulator columns per partial sum (24 / 36 instead of 48 registers). Instantiated for HP = 64, where the
+// spills of the wide variant cost most: with 225 KB of shared memory in use the L1 that backs local memory is a few KB
+// (ncu: local loads hit 4 %).
+template <int HP, int ONX, int DK>
 struct TcCfg {
+  static constexpr int ON = (ONX == 8 || ONX == 12) ? 16 : ONX;
+  static constexpr int NR = (ONX == 32) ? 20 : ONX;      // accumulator columns phase 2 reads per partial sum
   static constexpr bool BIASX = DK >= 8;
   static constexpr int DKC = DK & 7;
   static constexpr int HALVES = (HP == 64) ? 2 : 1;       // epilogue warps sharing one chain's hidden units
@@ -213,13 +219,13 @@ __device__ __forceinline__ void sigmoid4_scaled(float t0, float t1, float t2, fl
   s0 = rab * a1; s1 = rab * a0; s2 = rcd * a3; s3 = rcd * a2;
 }
 
-template <int HP, int ON, int DK>
+template <int HP, int ONX, int DK>
 __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b1,
                                                                      const __grid_constant__ CUtensorMap map_w2, Tc2Params p) {
   using namespace v2;
-  using C = TcCfg<HP, ON, DK>;
-  constexpr int DKC = C::DKC;
+  using C = TcCfg<HP, ONX, DK>;
+  constexpr int DKC = C::DKC, ON = C::ON;
   constexpr int HALVES = C::HALVES, UC = C::UC, HW = C::HW, N1 = C::N1, KBA = C::KBA, N2 = C::N2, PARTS = C::PARTS;
   constexpr int UPT = C::UPT, CH = C::CH, STAGES = C::STAGES, kD2Bufs = C::kD2Bufs;
   static_assert(UPT >= 1, "variant does not fit in shared memory");
@@ -446,8 +452,8 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
         if (has_next) phase1(u + 1);
         // ---- D2 of unit u: wait for MMA-2 (this also frees the HV buffer), pull it into registers ----
         // the partial sums of D2 (dr2 unused when PARTS == 2). ON = 32 serves O = 17..20: only 20 columns are read
-        constexpr int NR = (ON == 32) ? 20 : ON;
-        uint32_t dr0[NR], dr1[NR], dr2[ON == 32 ? 1 : ON];
+        constexpr int NR = C::NR;
+        uint32_t dr0[NR], dr1[NR], dr2[ON == 32 ? 1 : NR];
         mbar_wait(&d2_full[(u & 1) * UC + c], (u >> 1) & 1);
         tc_fence_after();
         if (mine) {
@@ -456,7 +462,12 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
             tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&dr0[0])); tmem_ld4(taddr + 16, *reinterpret_cast<uint32_t(*)[4]>(&dr0[16]));
             tmem_ld16(taddr + ON, *reinterpret_cast<uint32_t(*)[16]>(&dr1[0])); tmem_ld4(taddr + ON + 16, *reinterpret_cast<uint32_t(*)[4]>(&dr1[16]));
           }
-          else { tmem_ld16(taddr, dr0); tmem_ld16(taddr + ON, dr1); tmem_ld16(taddr + 2 * ON, dr2); }
+          else if constexpr (NR == 16) { tmem_ld16(taddr, dr0); tmem_ld16(taddr + ON, dr1); tmem_ld16(taddr + 2 * ON, dr2); }
+          else if constexpr (NR == 8) { tmem_ld8(taddr, dr0); tmem_ld8(taddr + ON, dr1); tmem_ld8(taddr + 2 * ON, dr2); }
+          else {
+            auto ld12 = [&](uint32_t ta, uint32_t* d) { tmem_ld8(ta, *reinterpret_cast<uint32_t(*)[8]>(d)); tmem_ld4(ta + 8, *reinterpret_cast<uint32_t(*)[4]>(d + 8)); };
+            ld12(taddr, dr0); ld12(taddr + ON, dr1); ld12(taddr + 2 * ON, dr2);
+          }
           tmem_ld_wait();
         }
         if (has_next) publish_hv(u + 1);
@@ -586,6 +597,9 @@ static int tc2_dispatch(int HP, int ON, int DKC, F&& fn) {
   SAPT_V(32, 32, 9) SAPT_V(32, 32, 10) SAPT_V(32, 32, 11) SAPT_V(32, 32, 12)
   SAPT_V(64, 16, 9) SAPT_V(64, 16, 10) SAPT_V(64, 16, 11) SAPT_V(64, 16, 12)
   SAPT_V(64, 32, 9) SAPT_V(64, 32, 10) SAPT_V(64, 32, 11) SAPT_V(64, 32, 12)
+  // O <= 8 at HP = 64 (see TcCfg)
+  SAPT_V(64, 8, 1) SAPT_V(64, 8, 2) SAPT_V(64, 8, 3) SAPT_V(64, 8, 4) SAPT_V(64, 8, 9) SAPT_V(64, 8, 10) SAPT_V(64, 8, 11) SAPT_V(64, 8, 12)
+  SAPT_V(64, 12, 1) SAPT_V(64, 12, 2) SAPT_V(64, 12, 3) SAPT_V(64, 12, 4) SAPT_V(64, 12, 9) SAPT_V(64, 12, 10) SAPT_V(64, 12, 11) SAPT_V(64, 12, 12)
 #undef SAPT_V
   set_error("tcgen05 path: no variant for HP=%d ON=%d DKC=%d", HP, ON, DKC);
   return SAPT_ERR_UNSUPPORTED;
@@ -622,7 +636,8 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   int HP, ON, DKC; tc2_shape(p, HP, ON, DKC);
   if (ON > HP) { set_error("tcgen05 path: O=%d needs H > 16", p->O); return SAPT_ERR_UNSUPPORTED; }
   Tc2Geom g{};
-  int rc = tc2_dispatch(HP, ON, DKC, [&](auto h, auto o, auto k) { g = geom_of<h(), o(), k()>(); return 0; });
+  const int ONX = (HP == 64 && ON == 16 && p->O <= 12) ? (p->O <= 8 ? 8 : 12) : ON;   // narrow accumulator read-out, see TcCfg
+  int rc = tc2_dispatch(HP, ONX, DKC, [&](auto h, auto o, auto k) { g = geom_of<h(), o(), k()>(); return 0; });
   if (rc) return rc;
   if (g.UPT < 1) { set_error("tcgen05 path: topology %d-%d-%d does not fit", p->D, p->H, p->O); return SAPT_ERR_UNSUPPORTED; }
   const int CH = g.CH;
@@ -663,7 +678,7 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.partL = partL; a.partNc = partNc; a.partSq = partSq;
   dim3 grid((unsigned)n_chunks, (unsigned)n_groups);
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(ds.tmap);
-  rc = tc2_dispatch(HP, ON, DKC, [&](auto h, auto o, auto k) { return launch_tc2<h(), o(), k()>(ma, mb1, mw2, a, grid, st); });
+  rc = tc2_dispatch(HP, ONX, DKC, [&](auto h, auto o, auto k) { return launch_tc2<h(), o(), k()>(ma, mb1, mw2, a, grid, st); });
   if (rc) return rc;
   return launch_loglik_finalize(partL, partNc, partSq, (int)n_chunks, R, rows, n_rows, L, nc, sq, st);
 }
