@@ -50,8 +50,13 @@ constexpr int ON = 16;                    // outputs padded (O <= 16)
 constexpr int N2 = 3 * ON;
 constexpr uint32_t kBlk = 128 * 128;      // one 64-column block of a 128-row tile
 
-template <int HP, int DKC>
+// DK packs DKC (DK & 7) and "O <= 8" (DK >= 8): the output phase then keeps 8 instead of 16 accumulator columns per
+// partial sum in registers. With 228 KB of shared memory in use the L1 behind local memory is tiny, so spills are
+// served from L2 (see the same finding for the likelihood kernel, profiles/r1_c4_loglik_summary.json).
+template <int HP, int DK>
 struct Cfg {
+  static constexpr int DKC = DK & 7;
+  static constexpr int NRL = (DK >= 8) ? 8 : 16;              // output columns read / accumulated per partial sum
   static constexpr int DW = 16 * DKC;                         // features per x piece (padded)
   static constexpr int KBA = (3 * DKC + 1 + 3) / 4;           // 128-byte K blocks of an image row
   static constexpr int NSLOT = (DKC == 4) ? 3 : KBA;          // X blocks kept in shared memory: x1, x2, bias (x3 skipped)
@@ -154,11 +159,12 @@ __global__ void lt_pack_w2t_kernel(const float* theta, int64_t ld, const int32_t
   }
 }
 
-template <int HP, int DKC>
+template <int HP, int DK>
 __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b1,
                                                                   const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2t,
                                                                   Params p) {
-  using C = Cfg<HP, DKC>;
+  using C = Cfg<HP, DK>;
+  constexpr int DKC = C::DKC, NRL = C::NRL;
   constexpr int DW = C::DW, KBA = C::KBA, NSLOT = C::NSLOT, NBH = C::NBH, HW = C::HW, NG1 = C::NG1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -337,9 +343,9 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
       const Item w = get_item(item);
       const int pos = w.pos, n_tiles = w.n_tiles, n_pairs = w.n_pairs;
       const int64_t t_begin = w.t_begin;
-      float accB2[ON];
+      float accB2[NRL];
 #pragma unroll
-      for (int o = 0; o < ON; ++o) accB2[o] = 0.f;
+      for (int o = 0; o < NRL; ++o) accB2[o] = 0.f;
       for (int q = 0; q < n_pairs; ++q) {
         const int nb = (2 * q + 1 < n_tiles) ? 2 : 1;
         float h[2][HW];
@@ -375,13 +381,15 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
           if (b < nb && slice == ((2 * q + b) & 3)) {
             mbar_wait(&d2_full[b], phb[b]);
             tc_fence_after();
-            uint32_t d0[ON], d1[ON], d2[ON];
+            uint32_t d0[NRL], d1[NRL], d2[NRL];
             const uint32_t ta = tmem_base + lane_base + C::kDS + b * 64;
-            tmem_ld16(ta, d0); tmem_ld16(ta + ON, d1); tmem_ld16(ta + 2 * ON, d2);
+            tmem_ldN<NRL>(ta, d0); tmem_ldN<NRL>(ta + ON, d1); tmem_ldN<NRL>(ta + 2 * ON, d2);
             tmem_ld_wait();
             float dhi[ON], dlo[ON];
 #pragma unroll
-            for (int o = 0; o < ON; ++o) {
+            for (int o = NRL; o < ON; ++o) { dhi[o] = 0.f; dlo[o] = 0.f; }
+#pragma unroll
+            for (int o = 0; o < NRL; ++o) {
               float dv = 0.f;
               if (o < O && y[b] >= 0) {
                 float tt = (__uint_as_float(d0[o]) + __uint_as_float(d1[o])) + __uint_as_float(d2[o]);
@@ -470,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
           }
         }
 #pragma unroll
-        for (int o = 0; o < ON; ++o) {
+        for (int o = 0; o < NRL; ++o) {
           const float sres = warp_sum(accB2[o]);
           if (lane == 0 && o < O) atomicAdd(&sGrad[D * H + H * O + H + o], -sres);       // LG:103: B2 += -do
         }
@@ -560,9 +568,10 @@ int launch_langevin_tc(sapt_problem* p, const float* theta, float* theta_gd, int
   a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.n_chunks = (int)n_chunks; a.part = part; a.P = P;
   dim3 grid((unsigned)std::min<int64_t>(p->num_sms, (int64_t)R * n_chunks));
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(ds.tmap);
-#define SAPT_LT(H_, K_) if (HP == H_ && DKC == K_) rc = launch_variant<H_, K_>(ma, mb1, mw2, mw2t, a, grid, st); else
+  const int DKX = (HP == 64 && p->O <= 8) ? DKC + 8 : DKC;   // narrow output phase, see Cfg
+#define SAPT_LT(H_, K_) if (HP == H_ && DKX == K_) rc = launch_variant<H_, K_>(ma, mb1, mw2, mw2t, a, grid, st); else
   SAPT_LT(16, 1) SAPT_LT(16, 2) SAPT_LT(16, 3) SAPT_LT(16, 4) SAPT_LT(32, 1) SAPT_LT(32, 2) SAPT_LT(32, 3) SAPT_LT(32, 4)
-  SAPT_LT(64, 1) SAPT_LT(64, 2) SAPT_LT(64, 3) SAPT_LT(64, 4) { set_error("tcgen05 Langevin: no variant for HP=%d DKC=%d", HP, DKC); rc = SAPT_ERR_UNSUPPORTED; }
+  SAPT_LT(64, 1) SAPT_LT(64, 2) SAPT_LT(64, 3) SAPT_LT(64, 4) SAPT_LT(64, 9) SAPT_LT(64, 10) SAPT_LT(64, 11) SAPT_LT(64, 12) { set_error("tcgen05 Langevin: no variant for HP=%d DKC=%d", HP, DKC); rc = SAPT_ERR_UNSUPPORTED; }
 #undef SAPT_LT
   if (rc) return rc;
   return launch_langevin_batch_finalize(part, (int)n_chunks, R, P, theta, theta_gd, ld, rows, n_rows, lr_scale, st);
