@@ -497,9 +497,6 @@ def main():
                    surrogate_prob=0.4, maxtemp=3.0, seed=36, n_train=80, n_test=30)
 
 
-if __name__ == "__main__":
-    main()
-
 
 # ----------------------------------------------------------------------------------------
 # N4: local-surrogate fork (LS). Same thread/stream harness; the fork's own coordinator is racy in the same
@@ -621,3 +618,7 @@ def make_run_local(tag: str, problem: str, R: int, samples_per_chain: int, swap_
     sur_steps = int(np.sum(~np.isnan(np.array(traces["surg_likeh_list"])[:, 1:, 1])))
     print(f"run_ls_{tag}: R={R} S={S} swaps={pt.num_swap}/{pt.total_swap_proposals} train_calls={n_calls} "
           f"surrogate_steps={sur_steps} accept%={np.round(acc, 1)}")
+
+
+if __name__ == "__main__":
+    main()
