@@ -8,7 +8,7 @@
 #include <cuda_runtime.h>
 #include <vector>
 
-#include "../surrogate-assisted-parallel-tempering_b200/csrc/sapt_tc_ptx.cuh"
+#include "../sapt_b200/csrc/sapt_tc_ptx.cuh"
 using namespace sapt;
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {

@@ -4,7 +4,7 @@
  * final state as one JSON line. tests/test_gpu_parity.py runs this binary and checks that PTEngine, given the
  * same data, temperatures and seed, ends in the same state (same kernels, same Philox streams).
  *
- *   build: make -C examples/c_host        (gcc, links ../../surrogate-assisted-parallel-tempering_b200/libsapt.so)
+ *   build: make -C examples/c_host        (gcc, links ../../sapt_b200/libsapt.so)
  *   usage: run_pt R samples swap_interval seed
  */
 #include <cuda_runtime_api.h>

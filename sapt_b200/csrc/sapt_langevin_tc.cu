@@ -37,7 +37,7 @@ namespace sapt {
 
 int launch_tc2_pack(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O, int HP, int ON, int CH,
                     int DKC, int KROW, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2, int n_blocks, cudaStream_t st);   // sapt_loglik_tc2.cu
-int tc_make_map_2d(CUtensorMap* map, void* base, uint64_t inner_elems, uint64_t rows, uint32_t box_rows);                       // sapt_loglik_tc.cu
+int tc_make_map_2d(CUtensorMap* map, void* base, uint64_t inner_elems, uint64_t rows, uint32_t box_rows);                       // sapt_tc_host.cu
 int launch_langevin_batch_finalize(const float* part, int n_chunks, int R, int P, const float* theta, float* theta_gd, int64_t ld,
                                    const int32_t* rows, const int32_t* n_rows, double lr_scale, cudaStream_t st);                // sapt_langevin.cu
 

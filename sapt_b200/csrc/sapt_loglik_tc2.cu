@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
 }
 
 // ---- host ------------------------------------------------------------------------------------------
-int tc_make_map_2d(CUtensorMap* map, void* base, uint64_t inner_elems, uint64_t rows, uint32_t box_rows);  // sapt_loglik_tc.cu
+int tc_make_map_2d(CUtensorMap* map, void* base, uint64_t inner_elems, uint64_t rows, uint32_t box_rows);  // sapt_tc_host.cu
 
 struct Tc2Geom { int CH, KROW, W2BOX, UPT; size_t smem; };
 
