@@ -355,6 +355,16 @@ int sapt_local_surrogate_train(const sapt_local_surrogate* m, int row_lo, int ro
 int sapt_local_surrogate_predict(const sapt_local_surrogate* m, int step, const int32_t* step_dev, const int32_t* rows,
                                  const int32_t* n_rows, double* pred, double* avg, void* stream);
 
+/* ---- measurement: SM pipe micro-benchmarks (the denominators of bench.py's "governing" roofline; SURVEY.md 8d:
+ * "pipe peaks must be re-measured by microbenchmark"). Fills out[SAPT_PIPE_COUNT]: lane-operations per second of
+ * MUFU.EX2, MUFU.RCP, FFMA, FMUL, fma.rn.f32x2 (instructions x 32 lanes; one f32x2 counts once), LOP3, a 1:3
+ * MUFU:FFMA mix, and the SM clock seen by clock64 during the FFMA / MUFU loops. Takes ~30 ms; synchronises. */
+enum {
+  SAPT_PIPE_SMS = 0, SAPT_PIPE_SM_HZ = 1, SAPT_PIPE_EX2 = 2, SAPT_PIPE_RCP = 3, SAPT_PIPE_FFMA = 4, SAPT_PIPE_FMUL = 5,
+  SAPT_PIPE_FFMA2 = 6, SAPT_PIPE_LOP3 = 7, SAPT_PIPE_MIX = 8, SAPT_PIPE_SM_HZ_MUFU = 9, SAPT_PIPE_COUNT = 10
+};
+int sapt_measure_pipes(int device, double* out_host, int n_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

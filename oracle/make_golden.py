@@ -114,6 +114,11 @@ def make_swap_and_ladder(seed: int):
         duck.default_beta_ladder = lambda ndim, ntemps, Tmax: ref.ParallelTempering.default_beta_ladder(duck, ndim, ntemps, Tmax)
         ref.ParallelTempering.assign_temperatures(duck)
         out[f"ladder_R{R}_T{mt}"] = np.array(duck.temperatures, dtype=np.float64)
+    # the ptemcee step table (RV:854-881): Tmax derived from ntemps for every tabulated dimension and beyond
+    duck = types.SimpleNamespace()
+    out["ladder_ndim"] = np.arange(1, 111)
+    out["ladder_betas_ntemps5"] = np.array([ref.ParallelTempering.default_beta_ladder(duck, int(nd), 5, None) for nd in range(1, 111)])
+    out["ladder_ntemps_Tmax50"] = np.array([len(ref.ParallelTempering.default_beta_ladder(duck, int(nd), None, 50.0)) for nd in range(1, 111)])
     # swap sweeps: drive the reference's swap_procedure through queues exactly like RW:1095-1099
     rs = np.random.RandomState(seed)
     P = 5
@@ -344,6 +349,7 @@ def make_run(variant: str, tag: str, problem: str, R: int, samples_per_chain: in
         return orig_trainer(self, params)
 
     mod.ParallelTempering.surrogate_trainer = logged_trainer
+    ref_show_results = mod.ParallelTempering.show_results    # run below on the files the chains leave behind
     pt.show_results = lambda: tuple([None] * 12)
 
     with contextlib.redirect_stdout(io.StringIO()):
@@ -351,6 +357,23 @@ def make_run(variant: str, tag: str, problem: str, R: int, samples_per_chain: in
             _run_lg_barrier(mod, pt)
         else:
             pt.run_chains()
+
+    # the reference's own aggregation (RV:1231-1392 and the forks' copies): burn-in slicing, reshape order, rmse_surr —
+    # fed by the per-chain files the chains have just written (with the reference's own text formats)
+    show = {}
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            shown = ref_show_results(pt)
+    except ValueError:
+        shown = None   # a run without a single surrogate step: the reference's plot code dies on np.amax([]) (RW:1280)
+    if shown is not None:
+        show_names = ("posterior", "fx_train", "fx_test", "rmse_train", "rmse_test", "acc_train", "acc_test", "likelihood_vec",
+                      "accept_list", "rmse_surr", "surr_list", "accept")
+        show = {f"show_{n}": np.array(v, dtype=np.float64) for n, v in zip(show_names, shown) if not n.startswith("fx_")}
+        show["show_fx_shapes"] = np.array([np.shape(shown[1]), np.shape(shown[2])])
+        show["show_burn_in"] = np.array(pt.burn_in)
+        for fn in ("pos_param.txt", "likelihood.txt", "acc_train.txt", "acc_test.txt"):
+            show["showfile_" + fn.replace(".txt", "")] = np.loadtxt(os.path.join(tmp, fn))
 
     # ---- assemble streams [step, chain, ...] from the per-thread logs ----
     S = samples_per_chain
@@ -396,7 +419,7 @@ def make_run(variant: str, tag: str, problem: str, R: int, samples_per_chain: in
                swap_u=swap_u, swap_log=np.array([(-1 if s is None else int(s)) for s in swap_log]),
                num_swap=np.array(pt.num_swap), total_swap_proposals=np.array(pt.total_swap_proposals),
                n_trainer_calls=np.array(len(trainer_batches)), min_y=np.array(minmax[0]),
-               max_y=np.array(minmax[1]), n_signatures=np.array(min(n_sig, len(trainer_batches))), **meta)
+               max_y=np.array(minmax[1]), n_signatures=np.array(min(n_sig, len(trainer_batches))), **meta, **show)
     for s, b in enumerate(trainer_batches):
         out[f"trainer_batch_{s}"] = b
     for s in range(min(n_sig, len(trainer_batches))):  # only the signatures the run reached

@@ -127,6 +127,7 @@ def lib():
     L.sapt_local_surrogate_predict.argtypes = [C.POINTER(LocalSurrogate), C.c_int, vp, vp, vp, vp, vp, vp]
     L.sapt_step.argtypes = [vp, C.POINTER(StepArgs), vp]
     L.sapt_struct_sizes.argtypes = [C.POINTER(i32)]
+    L.sapt_measure_pipes.argtypes = [C.c_int, C.POINTER(f64), C.c_int, vp]
     sizes = (i32 * 8)()
     L.sapt_struct_sizes(sizes)
     mine = [C.sizeof(t) for t in (ProposeArgs, ChainState, History, AcceptArgs, LgFirstArgs, FusedArgs, LocalSurrogate, StepArgs)]
@@ -151,5 +152,19 @@ EXPORTS = [
     "sapt_problem_rows", "sapt_problem_tc_supported", "sapt_loglik", "sapt_loglik_host", "sapt_evaluate_proposal",
     "sapt_prior", "sapt_propose", "sapt_fused_steps", "sapt_langevin", "sapt_surrogate_predict", "sapt_mh_accept", "sapt_lg_first_eval",
     "sapt_swap_sweep", "sapt_swap_sweep_dev", "sapt_advance", "sapt_philox_host", "sapt_philox_fill",
-    "sapt_local_surrogate_train", "sapt_local_surrogate_predict", "sapt_step",
+    "sapt_local_surrogate_train", "sapt_local_surrogate_predict", "sapt_step", "sapt_measure_pipes",
 ]
+
+
+PIPE_NAMES = ("sms", "sm_hz", "ex2", "rcp", "ffma", "fmul", "ffma2", "lop3", "mix", "sm_hz_mufu")
+
+
+def measure_pipes(device: int = 0) -> dict:
+    """SM pipe micro-benchmarks (sapt_measure_pipes): lane-operations per second and per clock per SM."""
+    out = (f64 * len(PIPE_NAMES))()
+    check(lib().sapt_measure_pipes(device, out, len(PIPE_NAMES), None), "sapt_measure_pipes")
+    d = dict(zip(PIPE_NAMES, [float(v) for v in out]))
+    for k in ("ex2", "rcp", "ffma", "fmul", "ffma2", "lop3", "mix"):
+        hz = d["sm_hz_mufu"] if k in ("ex2", "rcp") else d["sm_hz"]
+        d[k + "_per_clk_sm"] = d[k] / (d["sms"] * hz)
+    return d

@@ -613,7 +613,10 @@ class PTEngine:
         default is off; the mode is kept for host-bound deployments (slow CPUs, many short kernels).
         `native` (default: on where it applies) runs every stretch between two rendezvous through ONE sapt_step call —
         the C driver of the random-walk forks' loop body — instead of ~6 ctypes calls per step."""
-        n = self.cfg.samples - 1 if steps is None else steps
+        n = self.cfg.samples - 1 if steps is None else int(steps)
+        if self.hist is not None and n > self.cfg.samples - 1:
+            # the kernels write history row step+1 with no bound check: the buffers hold cfg.samples rows
+            raise ValueError(f"run(steps={n}) with record_history needs samples >= steps + 1 (samples = {self.cfg.samples})")
         if fused is None:
             fused = self.fused_supported()
         if fused:
@@ -657,7 +660,11 @@ class PTEngine:
             while j not in pts and j < n - 1:
                 j += 1
             length = j - i + 1
-            key = (length, self.surrogate.signature, self.surrogate.ready)
+            # everything a captured step bakes in: the segment length, the global surrogate's weights (signature) and
+            # whether surrogate steps exist at all — for the local-surrogate fork that is ls_ready, which the
+            # rendezvous flips without touching the signature
+            ready = self.ls_ready if self.ls is not None else self.surrogate.ready
+            key = (length, self.surrogate.signature, bool(ready))
             g = self._graphs.get(key)
             self.step_dev[0] = i
             if g is None and length >= 4:
@@ -733,6 +740,32 @@ class PTEngine:
             owner[r0:r1] = mask[None, :].to(owned.dtype)
         owned.mul_(owner[:, :, None])
         return owned
+
+    def export_streams(self, steps: Optional[int] = None) -> dict:
+        """The engine's in-kernel Philox streams as arrays indexed [step, chain(, P)] (and swap_u [sweep, R-1]): exactly
+        the numbers the kernels draw for this seed (sapt_philox_fill runs the same device functions). Feeding them to
+        another implementation of the chain loop (the oracle's run_pt, or `inject=` of a second engine) gives a
+        same-seed run: the posterior-parity tests are built on this."""
+        n = self.cfg.samples - 1 if steps is None else int(steps)
+        R, P, seed = self.Rg, self.P, self.cfg.seed & 0xFFFFFFFF
+        z1 = torch.zeros((n, R, P), dtype=torch.float32, device=self.dev); z2 = torch.zeros_like(z1)
+        sc = {k: torch.zeros((n, R), dtype=torch.float32, device=self.dev) for k in ("ku", "lx2", "u")}
+        n_sweeps = n // max(1, self.cfg.swap_interval) + 2
+        swap_u = torch.zeros((n_sweeps, max(1, R - 1)), dtype=torch.float32, device=self.dev)
+        fill, st = self.L.sapt_philox_fill, current_stream_ptr()
+        for i in range(n):
+            for k in range(R):
+                _lib.check(fill(seed, _lib.STREAM_Z1, i, k, P, 1, z1[i, k].data_ptr(), st))
+                _lib.check(fill(seed, _lib.STREAM_Z2, i, k, P, 1, z2[i, k].data_ptr(), st))
+                for name, kind in (("ku", _lib.STREAM_KU), ("lx2", _lib.STREAM_LX2), ("u", _lib.STREAM_U)):
+                    _lib.check(fill(seed, kind, i, k, 1, 0, sc[name][i, k:k + 1].data_ptr(), st))
+        if R > 1:
+            for s in range(n_sweeps):
+                _lib.check(fill(seed, _lib.STREAM_SWAP, s, 0, R - 1, 0, swap_u[s].data_ptr(), st))
+        out = dict(z1=z1.cpu().numpy().astype(np.float64), z2=z2.cpu().numpy().astype(np.float64),
+                   swap_u=swap_u.cpu().numpy().astype(np.float64))
+        out.update({k: v.cpu().numpy().astype(np.float64) for k, v in sc.items()})
+        return out
 
     def current_w(self) -> np.ndarray:
         """[chain, P] parameter vector each chain currently holds (single rank)."""

@@ -3,10 +3,14 @@
 Same names, arguments and return conventions as _revamp.py:47-174 (`Network`) and
 _revamp.py:380-410 (`ptReplica.rmse/accuracy/likelihood_func/prior_likelihood`); the arithmetic
 runs in the CUDA kernels behind include/sapt.h. `data` arrays keep the reference layout
-(float [n, D+1], label in column D). Data sets are uploaded once and cached per array identity;
-passing an array that is neither TrainData nor TestData uploads it on first use.
+(float [n, D+1], label in column D). Data sets are uploaded once and cached by CONTENT (shape + a
+digest of the bytes), so a temporary slice, a recycled `id()` or an in-place edit can never be
+evaluated against a stale device copy; the cache is a small LRU whose evicted entries free their HBM.
 """
 from __future__ import annotations
+
+import hashlib
+from collections import OrderedDict
 
 import numpy as np
 import torch
@@ -23,11 +27,13 @@ class Network:
         self.lrate = learn_rate
         self._path = path
         self._device = device
-        self._problems = {}  # id(data) -> (Problem, which)
+        self._problems = OrderedDict()  # content key -> (Problem, which); LRU, the constructor's two sets are pinned
         self._main = Problem(self.Top, Train, Test, device=device, path=path)
-        self._problems[id(Train)] = (self._main, 0)
+        self._pinned = {self._key(Train)}
+        self._problems[self._key(Train)] = (self._main, 0)
         if Test is not None and len(Test):
-            self._problems[id(Test)] = (self._main, 1)
+            self._pinned.add(self._key(Test))
+            self._problems.setdefault(self._key(Test), (self._main, 1))
         d, h, o = self.Top
         # same draw sequence as the reference constructor (_revamp.py:54-57)
         self.W1 = np.random.randn(d, h) / np.sqrt(d)
@@ -49,17 +55,40 @@ class Network:
         return np.concatenate([self.W1.ravel(), self.W2.ravel(), self.B1.ravel(), self.B2.ravel()])
 
     # -- data-set cache -------------------------------------------------------------------
+    MAX_CACHED = 8          # extra data sets kept on the device besides TrainData / TestData
+    _FULL_DIGEST = 64 << 20  # arrays up to this size are digested in full, larger ones by a strided row sample + both ends
+
+    @classmethod
+    def _key(cls, data):
+        a = np.asarray(data)
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        h = hashlib.blake2b(digest_size=16)
+        h.update(repr((a.shape, a.dtype.str)).encode())
+        if a.nbytes <= cls._FULL_DIGEST or a.ndim < 1 or a.shape[0] < 4096:
+            h.update(memoryview(a).cast("B"))
+        else:
+            step = max(1, a.shape[0] // 4096)
+            h.update(np.ascontiguousarray(a[::step]).tobytes())
+            h.update(np.ascontiguousarray(a[:64]).tobytes()); h.update(np.ascontiguousarray(a[-64:]).tobytes())
+            h.update(np.asarray(a.sum(axis=0, dtype=np.float64)).tobytes())
+        return h.digest()
+
     def _resolve(self, data):
-        key = id(data)
-        if key not in self._problems:
-            for k, (pr, which) in list(self._problems.items()):
-                ref = self.TrainData if (pr is self._main and which == 0) else (self.TestData if pr is self._main else None)
-                if ref is not None and ref.shape == np.shape(data) and np.array_equal(ref, data):
-                    self._problems[key] = (pr, which)
-                    break
-            else:
-                self._problems[key] = (Problem(self.Top, data, None, device=self._device, path=self._path), 0)
-        return self._problems[key]
+        key = self._key(data)
+        hit = self._problems.get(key)
+        if hit is not None:
+            self._problems.move_to_end(key)
+            return hit
+        entry = (Problem(self.Top, data, None, device=self._device, path=self._path), 0)
+        self._problems[key] = entry
+        extra = [k for k in self._problems if k not in self._pinned]
+        while len(extra) > self.MAX_CACHED:
+            old = extra.pop(0)
+            pr, _ = self._problems.pop(old)
+            if pr is not self._main:
+                pr.close()
+        return entry
 
     def _theta(self, w, pr):
         w = np.asarray(w, dtype=np.float32)
@@ -87,9 +116,12 @@ class Network:
     def langevin_gradient(self, data, w, depth, mode="sgd_exact", batch_scale=1.0):
         """One epoch (per unit of depth) of per-row online SGD, LG:138-156. w may be [P] or [R, P]."""
         pr, which = self._resolve(data)
-        if which != 0:
-            pr = Problem(self.Top, data, None, device=self._device, path=self._path)
-            self._problems[id(data)] = (pr, 0)
+        if which != 0:   # the Langevin kernels walk the TRAIN slot of a problem: give this array its own
+            key = b"train:" + self._key(data)
+            if key not in self._problems:
+                self._problems[key] = (Problem(self.Top, data, None, device=self._device, path=self._path), 0)
+                self._pinned.add(key)
+            pr = self._problems[key][0]
         t, single = self._theta(w, pr)
         for _ in range(int(depth)):
             t = pr.langevin(t, self.lrate, 0 if mode == "sgd_exact" else 1, batch_scale)

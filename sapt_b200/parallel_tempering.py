@@ -15,6 +15,7 @@ from . import _lib
 from .engine import EngineConfig, PTEngine
 from .ladder import assign_temperatures, default_beta_ladder
 from .problem import Problem
+from .results import aggregate
 from .surrogate import SurrogateTrainer
 
 
@@ -108,31 +109,11 @@ class ParallelTempering:
         torch.cuda.synchronize()
         res = eng.results()
         self.results = res
-        S, R, P = self.NumSamples, self.num_chains, self.num_param
-        burnin = int(S * self.burn_in)
-        keep = S - burnin
-        pos_w = res["pos_w"][:, burnin:, :] if "pos_w" in res else np.zeros((R, keep, P))
-        posterior = pos_w.transpose(2, 0, 1).reshape(P, -1)
         ntr, nte = self.traindata.shape[0], (self.testdata.shape[0] if self.testdata is not None else 0)
-        # the reference returns all-zero fx arrays (their loading code is commented out, _revamp.py:1270-1275)
-        fx_train_all = np.zeros((R, keep, ntr)) if R * keep * ntr <= (1 << 26) else None
-        fx_test_all = np.zeros((R, keep, nte)) if R * keep * nte <= (1 << 26) else None
-        col = lambda k: res[k][:, burnin:].reshape(R * keep, 1)
-        rmse_train, rmse_test, acc_train, acc_test = col("rmse_train"), col("rmse_test"), col("acc_train"), col("acc_test")
-        likelihood_rep = res["likeh_list"][:, 1:, :]
-        likelihood_vec = likelihood_rep.transpose(2, 0, 1).reshape(2, -1)
-        surg = res["surg_likeh_list"][:, 1:, 0:2]
-        surg_vec = surg.transpose(2, 0, 1).reshape(2, -1)
-        accept_list = res["accept_list"]
-        rmse_surr, surr_list = 0, []
-        if self.use_surrogate:
-            surr_list = surg_vec.T
-            sl = surr_list[~np.isnan(surr_list).any(axis=1)]
-            rmse_surr = float(np.sqrt(((sl[:, 1] - sl[:, 0]) ** 2).mean())) if len(sl) else 0.0
-        accept_percent = res["naccept"] / (S * 1.0) * 100
-        accept = float(np.sum(accept_percent) / R)
+        (posterior, fx_train_all, fx_test_all, rmse_train, rmse_test, acc_train, acc_test, likelihood_vec_t, accept_list, rmse_surr,
+         surr_list, accept) = aggregate(res, self.NumSamples, self.num_chains, self.num_param, self.burn_in, self.use_surrogate, ntr, nte)
         self.num_swap = res["num_swap"]
         self.total_swap_proposals = res["total_swap_proposals"]
         swap_perc = self.num_swap * 100 / self.total_swap_proposals if self.total_swap_proposals else 0
         return (posterior, fx_train_all, fx_test_all, rmse_train, rmse_test, acc_train, acc_test, accept_list, swap_perc,
-                likelihood_vec.T, rmse_surr, surr_list, accept)
+                likelihood_vec_t, rmse_surr, surr_list, accept)

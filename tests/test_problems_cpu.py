@@ -80,3 +80,61 @@ def test_surrogate_trainer_learns_and_warm_starts():
     assert np.array_equal(tr2(batch, 1)["W1"], w1["W1"])                             # deterministic given the seed
     w3 = tr(batch, 1)                                                                # signature 1 again: fresh model
     assert not np.array_equal(w3["W1"], w2["W1"])
+
+
+def _res_from_traces(g):
+    S = int(g["samples"])
+    res = {k: g["trace_" + k] for k in ("pos_w", "rmse_train", "rmse_test", "acc_train", "acc_test", "surg_likeh_list", "likeh_list", "accept_list")}
+    res["naccept"] = np.asarray(g["trace_accept_ratio"]).reshape(-1) * S / 100.0
+    return res
+
+
+@pytest.mark.parametrize("name", ["run_rv_cancer", "run_rw_cancer", "run_lg_cancer", "run_lg_ions"])
+def test_show_results_values_match_reference(name, tmp_path):
+    """N2: the VALUES of the reference's own ParallelTempering.show_results (_revamp.py:1231-1392 and the forks'
+    copies; recorded by oracle/make_golden.py from the unmodified reference fed with the per-chain files its chains
+    wrote): burn-in slicing, the reshape order of pos_w / likelihood_vec / surr_list, rmse_surr, mean acceptance and
+    the aggregated files. Same per-chain traces in -> identical 12-tuple out, through the file round trip
+    (dump_chains -> show_results, the reference's text formats) and, up to those formats, in memory (aggregate)."""
+    from sapt_b200 import results as R
+    g = gu.load(name)
+    S = int(g["samples"]); P = g["trace_pos_w"].shape[2]; burn = float(g["show_burn_in"])
+    temps = list(g["temperatures"])
+    ntr, nte = g["train"].shape[0], g["test"].shape[0]
+    res = _res_from_traces(g)
+    R.dump_chains(str(tmp_path), temps, res, S)
+    out = R.show_results(str(tmp_path), temps, S, P, burn, True, ntr, nte)
+    names = ("posterior", "fx_train", "fx_test", "rmse_train", "rmse_test", "acc_train", "acc_test", "likelihood_vec", "accept_list",
+             "rmse_surr", "surr_list", "accept")
+    for n, v in zip(names, out):
+        if n.startswith("fx_"):
+            continue
+        ref = g["show_" + n]
+        assert np.shape(v) == ref.shape, (n, np.shape(v), ref.shape)
+        np.testing.assert_array_equal(np.asarray(v, dtype=np.float64), ref, err_msg=n)   # NaN == NaN here
+    assert [tuple(s) for s in g["show_fx_shapes"]] == [out[1].shape, out[2].shape]
+    for fn in ("pos_param", "likelihood", "acc_train", "acc_test"):
+        np.testing.assert_array_equal(np.loadtxt(os.path.join(str(tmp_path), fn + ".txt")), g["showfile_" + fn], err_msg=fn)
+    # in memory (no text round trip): equal up to the formats of the per-chain files (%1.2f, %1.4f)
+    mem = R.aggregate(res, S, len(temps), P, burn, True, ntr, nte)
+    np.testing.assert_array_equal(mem[0], g["show_posterior"])
+    for idx, n, tol in ((3, "rmse_train", 0.0051), (4, "rmse_test", 0.0051), (5, "acc_train", 0.0051), (6, "acc_test", 0.0051),
+                        (7, "likelihood_vec", 5.1e-5), (10, "surr_list", 5.1e-5), (8, "accept_list", 5.1e-5)):
+        a, b = np.asarray(mem[idx], dtype=np.float64), g["show_" + n]
+        assert a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.isinf(a), np.isinf(b)), n
+        m = np.isfinite(b)
+        np.testing.assert_allclose(a[m], b[m], rtol=0, atol=tol, err_msg=n)
+    np.testing.assert_allclose(mem[9], float(g["show_rmse_surr"]), rtol=0, atol=2e-4)
+    np.testing.assert_allclose(mem[11], float(g["show_accept"]), rtol=0, atol=1e-4)
+
+
+def test_ladder_step_table_matches_reference():
+    """default_beta_ladder with Tmax / ntemps derived from ptemcee's step table (RV:854-881): all 100 tabulated
+    dimensions and the large-dimension formula beyond, against the reference's own output; product and oracle."""
+    from oracle import sapt_oracle as so
+    from sapt_b200 import default_beta_ladder
+    g = gu.load("swap_ladder")
+    for fn in (default_beta_ladder, so.default_beta_ladder):
+        for nd, betas, nt in zip(g["ladder_ndim"], g["ladder_betas_ntemps5"], g["ladder_ntemps_Tmax50"]):
+            np.testing.assert_allclose(fn(int(nd), 5, None), betas, rtol=1e-14)
+            assert len(fn(int(nd), None, 50.0)) == int(nt)
