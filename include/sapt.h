@@ -355,6 +355,19 @@ int sapt_local_surrogate_train(const sapt_local_surrogate* m, int row_lo, int ro
 int sapt_local_surrogate_predict(const sapt_local_surrogate* m, int step, const int32_t* step_dev, const int32_t* rows,
                                  const int32_t* n_rows, double* pred, double* avg, void* stream);
 
+/* ---- measurement: what ONE replica x row evaluation executes on the likelihood kernel `path` selects for this topology
+ * (padding, split products and shared reciprocals included) — derived from the same compile-time geometry the kernels use,
+ * so bench.py's roofline is computed from the instruction mix the kernel runs, not from a model of an ideal kernel. */
+enum {
+  SAPT_WORK_PATH = 0,             /* SAPT_PATH_F32 or SAPT_PATH_TC: what SAPT_PATH_AUTO resolves to */
+  SAPT_WORK_MUFU = 1,             /* MUFU (ex2 / rcp / lg2) operations per evaluation */
+  SAPT_WORK_MMA_FLOPS = 2,        /* tensor-pipe FLOPs issued per evaluation (0 on the fp32 path) */
+  SAPT_WORK_FFMA = 3,             /* FP32 FMAs of the two layers per evaluation (0 on the tcgen05 path) */
+  SAPT_WORK_FLOPS_ALGORITHMIC = 4, /* 2 D H + 2 H O */
+  SAPT_WORK_COUNT = 5
+};
+int sapt_loglik_work_model(const sapt_problem_t* p, int path, double* out_host, int n_out);
+
 /* ---- measurement: SM pipe micro-benchmarks (the denominators of bench.py's "governing" roofline; SURVEY.md 8d:
  * "pipe peaks must be re-measured by microbenchmark"). Fills out[SAPT_PIPE_COUNT]: lane-operations per second of
  * MUFU.EX2, MUFU.RCP, FFMA, FMUL, fma.rn.f32x2 (instructions x 32 lanes; one f32x2 counts once), LOP3, a 1:3

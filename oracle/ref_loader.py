@@ -1,9 +1,14 @@
 """TEST INFRASTRUCTURE ONLY — loads the *unmodified* reference scripts for oracle pinning.
 
-Only usable where ``/root/reference`` exists (the build container). Nothing in the
-``-m gpu`` tests, ``smoke()`` or ``bench.py`` may import this module at run time; it is
-used by ``oracle/make_golden.py`` (fixture generation) and by the ``not gpu`` tests that
-re-validate the numpy restatement against the live reference when it is present.
+Two sources, in this order:
+  1. ``/root/reference`` (the build container): used by ``oracle/make_golden.py`` (fixture generation) and by the
+     ``not gpu`` tests that re-validate the numpy restatement against the live reference;
+  2. ``oracle/_ref/reference_scripts.zip``: a byte-for-byte archive of the four reference scripts that
+     ``oracle/build_ref.py`` (run by ``__graft_entry__.build()`` wherever /root/reference exists) writes. The archive is
+     git-ignored (no reference source enters the history) but travels with the ``gpurun`` snapshot like the built
+     ``.so`` files, so that ``bench.py --impl reference`` / ``cpu_baseline`` can time the UNMODIFIED reference
+     (``ptReplica.likelihood_func`` -> ``Network.evaluate_proposal``) on the GPU box's host cores. It is unpacked into
+     a per-process temporary directory; /root/reference itself is never read on the GPU box.
 
 The reference scripts import keras / matplotlib / nn_mcmc_plots at module top
 (/root/reference/_revamp.py:13-37); none is installed here and none is needed by the hot
@@ -17,6 +22,7 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("SAPT_REFERENCE_ROOT", "/root/reference")
+ARCHIVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_scripts.zip")
 
 VARIANTS = {
     # abbreviations follow SURVEY.md
@@ -70,7 +76,38 @@ _STUBS = [
 
 
 def reference_available() -> bool:
+    """The live reference tree (scripts AND its DATA directory) is present."""
     return os.path.isfile(os.path.join(REFERENCE_ROOT, VARIANTS["RV"]))
+
+
+def archive_available() -> bool:
+    return os.path.isfile(ARCHIVE)
+
+
+_unpacked = None
+
+
+def scripts_root():
+    """Directory holding the reference scripts: the live tree, else the unpacked archive; None if neither exists."""
+    global _unpacked
+    if reference_available():
+        return REFERENCE_ROOT
+    if archive_available():
+        if _unpacked is None:
+            import atexit
+            import shutil
+            import tempfile
+            import zipfile
+            _unpacked = tempfile.mkdtemp(prefix="sapt_ref_")
+            with zipfile.ZipFile(ARCHIVE) as z:
+                z.extractall(_unpacked)
+            atexit.register(shutil.rmtree, _unpacked, True)
+        return _unpacked
+    return None
+
+
+def source_kind() -> str:
+    return "live tree" if reference_available() else ("archive oracle/_ref/reference_scripts.zip" if archive_available() else "absent")
 
 
 def _install_stubs():
@@ -89,10 +126,11 @@ def load_reference(variant: str = "LG"):
     ParallelTempering, surrogate). ``main()`` is never executed (guarded by __name__)."""
     if variant in _cache:
         return _cache[variant]
-    if not reference_available():
-        raise FileNotFoundError(f"reference not present under {REFERENCE_ROOT}")
+    root = scripts_root()
+    if root is None:
+        raise FileNotFoundError(f"reference not present under {REFERENCE_ROOT} and no archive at {ARCHIVE}")
     _install_stubs()
-    path = os.path.join(REFERENCE_ROOT, VARIANTS[variant])
+    path = os.path.join(root, VARIANTS[variant])
     spec = importlib.util.spec_from_file_location(f"_sapt_reference_{variant}", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

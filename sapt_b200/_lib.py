@@ -128,6 +128,7 @@ def lib():
     L.sapt_step.argtypes = [vp, C.POINTER(StepArgs), vp]
     L.sapt_struct_sizes.argtypes = [C.POINTER(i32)]
     L.sapt_measure_pipes.argtypes = [C.c_int, C.POINTER(f64), C.c_int, vp]
+    L.sapt_loglik_work_model.argtypes = [vp, C.c_int, C.POINTER(f64), C.c_int]
     sizes = (i32 * 8)()
     L.sapt_struct_sizes(sizes)
     mine = [C.sizeof(t) for t in (ProposeArgs, ChainState, History, AcceptArgs, LgFirstArgs, FusedArgs, LocalSurrogate, StepArgs)]
@@ -152,7 +153,7 @@ EXPORTS = [
     "sapt_problem_rows", "sapt_problem_tc_supported", "sapt_loglik", "sapt_loglik_host", "sapt_evaluate_proposal",
     "sapt_prior", "sapt_propose", "sapt_fused_steps", "sapt_langevin", "sapt_surrogate_predict", "sapt_mh_accept", "sapt_lg_first_eval",
     "sapt_swap_sweep", "sapt_swap_sweep_dev", "sapt_advance", "sapt_philox_host", "sapt_philox_fill",
-    "sapt_local_surrogate_train", "sapt_local_surrogate_predict", "sapt_step", "sapt_measure_pipes",
+    "sapt_local_surrogate_train", "sapt_local_surrogate_predict", "sapt_step", "sapt_measure_pipes", "sapt_loglik_work_model",
 ]
 
 
@@ -168,3 +169,10 @@ def measure_pipes(device: int = 0) -> dict:
         hz = d["sm_hz_mufu"] if k in ("ex2", "rcp") else d["sm_hz"]
         d[k + "_per_clk_sm"] = d[k] / (d["sms"] * hz)
     return d
+
+
+def work_model(problem_handle, path: int = PATH_AUTO) -> dict:
+    """Per-evaluation work the selected likelihood kernel executes (sapt_loglik_work_model)."""
+    out = (f64 * 5)()
+    check(lib().sapt_loglik_work_model(problem_handle, path, out, 5), "sapt_loglik_work_model")
+    return dict(path=int(out[0]), mufu=float(out[1]), mma_flops=float(out[2]), ffma=float(out[3]), flops_algorithmic=float(out[4]))

@@ -624,6 +624,21 @@ bool tc2_supported(int D, int H, int O) {
   return upt >= 1;
 }
 
+// What ONE replica x row evaluation executes on this path (bench.py's governing roofline is computed from this, not from a
+// model of what an ideal kernel would do): MUFU operations and tensor-pipe FLOPs including padding and the split products.
+//   phase 1: HP sigmoids = HP ex2 + HP/4 shared reciprocals (sigmoid4);  phase 2: O ex2 + (quads, pair, single) reciprocals for
+//   the output sigmoids, O ex2 for the softmax, one lg2.
+void tc2_work_model(int D, int H, int O, double* mufu, double* mma_flops) {
+  sapt_problem q{}; q.D = D; q.H = H; q.O = O;
+  int HP, ON, DK; tc2_shape(&q, HP, ON, DK);
+  const int DKC = DK & 7;
+  const int rcp2 = O / 4 + ((O & 2) ? 1 : 0) + ((O & 1) ? 1 : 0);
+  *mufu = (double)HP + HP / 4 + O + rcp2 + O + 1;
+  const int k1 = 16 * (6 * DKC + (DK >= 8 ? 0 : 1));           // MMA-1: six piece products (+ bias chunk) of 16 DKC features
+  const int n2 = (ON == 16) ? (48 + 32) : (64 + 32 + 64);       // MMA-2: output columns summed over the passes h1.[w1|w2(|w3)], h2.[w1|w2]
+  *mma_flops = 2.0 * k1 * HP + 2.0 * HP * n2;                   // every pass has K = HP
+}
+
 int tc2_a_row_elems(int D) { return ((48 * tc2_dkc(D) + 16 + 63) / 64) * 64; }
 int tc2_piece_width(int D) { return 16 * tc2_dkc(D); }
 

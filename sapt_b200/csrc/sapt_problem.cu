@@ -137,6 +137,29 @@ extern "C" int sapt_problem_num_param(const sapt_problem_t* p) { return p ? p->P
 extern "C" int64_t sapt_problem_rows(const sapt_problem_t* p, int which) { return (p && (which == 0 || which == 1)) ? p->set[which].n : SAPT_ERR_INVALID; }
 extern "C" int sapt_problem_tc_supported(const sapt_problem_t* p) { return (p && p->tc_ok) ? 1 : 0; }
 
+namespace sapt { void tc2_work_model(int D, int H, int O, double* mufu, double* mma_flops); }
+
+// see sapt.h: the per-evaluation work the selected likelihood kernel EXECUTES
+extern "C" int sapt_loglik_work_model(const sapt_problem_t* p, int path, double* out, int n_out) {
+  SAPT_REQUIRE(p && out && n_out >= SAPT_WORK_COUNT, "problem / out[SAPT_WORK_COUNT]");
+  if (path == SAPT_PATH_TC && !p->tc_ok) { set_error("tcgen05 path unavailable for topology %d-%d-%d", p->D, p->H, p->O); return SAPT_ERR_UNSUPPORTED; }
+  const bool tc = (path == SAPT_PATH_TC) || (path == SAPT_PATH_AUTO && p->tc_ok && p->D * p->H + p->H * p->O >= 220);
+  const int D = p->D, H = p->H, O = p->O;
+  out[SAPT_WORK_PATH] = tc ? SAPT_PATH_TC : SAPT_PATH_F32;
+  out[SAPT_WORK_FLOPS_ALGORITHMIC] = 2.0 * D * H + 2.0 * H * O;
+  if (tc) {
+    sapt::tc2_work_model(D, H, O, &out[SAPT_WORK_MUFU], &out[SAPT_WORK_MMA_FLOPS]);
+    out[SAPT_WORK_FFMA] = 0.0;
+  } else {
+    // fp32 tiles (sapt_eval_f32.cuh): hidden units padded to HP4 = 4*ceil(H/4), 2 MUFU per sigmoid, O output sigmoids + O exp + 1 lg2
+    const int HP4 = p->HP;
+    out[SAPT_WORK_MUFU] = 2.0 * HP4 + 3.0 * O + 1.0;
+    out[SAPT_WORK_MMA_FLOPS] = 0.0;
+    out[SAPT_WORK_FFMA] = (double)p->DP * HP4 + (double)HP4 * p->OP;
+  }
+  return SAPT_OK;
+}
+
 extern "C" int sapt_loglik(sapt_problem_t* p, int which, const float* theta, int64_t ld_theta, int R, const int32_t* rows,
                            const int32_t* n_rows, double* L, int32_t* ncorrect, double* sqerr, int path, void* stream) {
   SAPT_REQUIRE(p && (which == 0 || which == 1), "problem / set selector");

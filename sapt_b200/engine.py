@@ -183,7 +183,8 @@ class PTEngine:
             self.train_L = torch.zeros((self.Rg, self.train_cap), **f64)
             self.train_count = torch.zeros(self.Rg, **i32)
         self._train_synced = False
-        self.surr_batches: List[torch.Tensor] = []   # device tensors; keep_batches=False drops them after training
+        self.surr_batches: List[torch.Tensor] = []   # device tensors of every rendezvous (what the parity tests compare)
+        self.keep_batches = True                     # False: a batch is dropped once the trainer has seen it (long / huge runs)
         # injected streams (parity tests): numpy arrays indexed [step, chain(, P)]
         self.inj = None
         if inject is not None:
@@ -494,7 +495,8 @@ class PTEngine:
         if self.ls is not None:
             return self.local_surrogate_train(i)
         batch = self.gather_training_rows()
-        self.surr_batches.append(batch)
+        if self.keep_batches:
+            self.surr_batches.append(batch)
         if batch.shape[0] == 0:
             return
         sur = self.surrogate
