@@ -371,10 +371,10 @@ int sapt_loglik_work_model(const sapt_problem_t* p, int path, double* out_host, 
 /* ---- measurement: SM pipe micro-benchmarks (the denominators of bench.py's "governing" roofline; SURVEY.md 8d:
  * "pipe peaks must be re-measured by microbenchmark"). Fills out[SAPT_PIPE_COUNT]: lane-operations per second of
  * MUFU.EX2, MUFU.RCP, FFMA, FMUL, fma.rn.f32x2 (instructions x 32 lanes; one f32x2 counts once), LOP3, a 1:3
- * MUFU:FFMA mix, and the SM clock seen by clock64 during the FFMA / MUFU loops. Takes ~30 ms; synchronises. */
+ * MUFU:FFMA mix, cvt.rn.bf16x2.f32 (F2FP, with one LOP3 per conversion), and the SM clock seen by clock64 during the FFMA / MUFU loops. Takes ~30 ms; synchronises. */
 enum {
   SAPT_PIPE_SMS = 0, SAPT_PIPE_SM_HZ = 1, SAPT_PIPE_EX2 = 2, SAPT_PIPE_RCP = 3, SAPT_PIPE_FFMA = 4, SAPT_PIPE_FMUL = 5,
-  SAPT_PIPE_FFMA2 = 6, SAPT_PIPE_LOP3 = 7, SAPT_PIPE_MIX = 8, SAPT_PIPE_SM_HZ_MUFU = 9, SAPT_PIPE_COUNT = 10
+  SAPT_PIPE_FFMA2 = 6, SAPT_PIPE_LOP3 = 7, SAPT_PIPE_MIX = 8, SAPT_PIPE_SM_HZ_MUFU = 9, SAPT_PIPE_F2FP = 10, SAPT_PIPE_COUNT = 11
 };
 int sapt_measure_pipes(int device, double* out_host, int n_out, void* stream);
 

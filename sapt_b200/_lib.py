@@ -157,7 +157,7 @@ EXPORTS = [
 ]
 
 
-PIPE_NAMES = ("sms", "sm_hz", "ex2", "rcp", "ffma", "fmul", "ffma2", "lop3", "mix", "sm_hz_mufu")
+PIPE_NAMES = ("sms", "sm_hz", "ex2", "rcp", "ffma", "fmul", "ffma2", "lop3", "mix", "sm_hz_mufu", "f2fp")
 
 
 def measure_pipes(device: int = 0) -> dict:
@@ -165,7 +165,7 @@ def measure_pipes(device: int = 0) -> dict:
     out = (f64 * len(PIPE_NAMES))()
     check(lib().sapt_measure_pipes(device, out, len(PIPE_NAMES), None), "sapt_measure_pipes")
     d = dict(zip(PIPE_NAMES, [float(v) for v in out]))
-    for k in ("ex2", "rcp", "ffma", "fmul", "ffma2", "lop3", "mix"):
+    for k in ("ex2", "rcp", "ffma", "fmul", "ffma2", "lop3", "mix", "f2fp"):
         hz = d["sm_hz_mufu"] if k in ("ex2", "rcp") else d["sm_hz"]
         d[k + "_per_clk_sm"] = d[k] / (d["sms"] * hz)
     return d

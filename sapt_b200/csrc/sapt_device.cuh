@@ -97,6 +97,59 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // sigmoid of z given t = -z*log2(e):  1 / (1 + 2^t)   (2 MUFU + 1 FADD)
 __device__ __forceinline__ float sigmoid_from_neg_log2e(float t) { return rcp_approx(1.0f + ex2_approx(t)); }
 
+// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 process two fp32 lanes per issue slot; the epilogues are bound by
+// instruction issue and the SFU pipe, not by the FP32 pipe) ------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// Four sigmoids s_i = scale / (1 + 2^min(t_i, lim)) with one reciprocal, packed: the results come out as the pairs
+// s10 = (s1, s0) and s32 = (s3, s2) (low lane first) — 4 FMNMX + 4 MUFU.EX2 + 2 FADD2 + 3 FMUL + MUFU.RCP + 3 FMUL2 (+1 FMUL for a scale)
+template <bool SCALED>
+__device__ __forceinline__ void sigmoid4_packed(float t0, float t1, float t2, float t3, float lim, float scale, f32x2& s10, f32x2& s32) {
+  const float e0 = ex2_approx(fminf(t0, lim)), e1 = ex2_approx(fminf(t1, lim));
+  const float e2 = ex2_approx(fminf(t2, lim)), e3 = ex2_approx(fminf(t3, lim));
+  const f32x2 one = pack2(1.0f, 1.0f);
+  const f32x2 a01 = add2(pack2(e0, e1), one), a23 = add2(pack2(e2, e3), one);
+  float a0, a1, a2, a3;
+  unpack2(a01, a0, a1); unpack2(a23, a2, a3);
+  const float ab = a0 * a1, cd = a2 * a3;
+  float r = rcp_approx(ab * cd);
+  if constexpr (SCALED) r *= scale;
+  float rcd, rab;
+  unpack2(mul2(pack2(cd, ab), pack2(r, r)), rcd, rab);
+  s10 = mul2(a01, pack2(rcd, rcd));   // (a0 r cd, a1 r cd) = (s1, s0)
+  s32 = mul2(a23, pack2(rab, rab));   // (a2 r ab, a3 r ab) = (s3, s2)
+}
+
+// four sigmoids with ONE reciprocal:  s_i = 1 / a_i,  a_i = 1 + 2^min(t_i, 30)  (the clamp costs < 1e-9 and keeps the product of
+// four below 2^120):  1/a0 = (1/(a0 a1 a2 a3)) a1 a2 a3, ...  = 4 MUFU.EX2 + 1 MUFU.RCP + 9 FMUL instead of 8 MUFU
+__device__ __forceinline__ void sigmoid4_from_neg_log2e(float t0, float t1, float t2, float t3, float& s0, float& s1, float& s2, float& s3) {
+  const float a0 = 1.0f + ex2_approx(fminf(t0, 30.0f));
+  const float a1 = 1.0f + ex2_approx(fminf(t1, 30.0f));
+  const float a2 = 1.0f + ex2_approx(fminf(t2, 30.0f));
+  const float a3 = 1.0f + ex2_approx(fminf(t3, 30.0f));
+  const float ab = a0 * a1, cd = a2 * a3;
+  const float r = rcp_approx(ab * cd);
+  const float rab = r * cd, rcd = r * ab;
+  s0 = rab * a1; s1 = rab * a0; s2 = rcd * a3; s3 = rcd * a2;
+}
+
+// Two fp32 values -> two packed bf16 pairs (low half = a, high half = b) with v = hi + lo to 2^-17 |v|, integer
+// instructions only: hi = v truncated to bf16 (one PRMT packs the pair), lo = the exact residual v - hi (same sign,
+// < 2^-8 |v|) with its magnitude rounded half-up to bf16. The conversion instructions (F2FP, cvt.rn.bf16x2.f32) issue on
+// the SFU pipe like MUFU (measured: sapt_measure_pipes), which is the pipe these kernels are short of.
+__device__ __forceinline__ void split_pack_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  hi = __byte_perm(ua, ub, 0x7632);
+  const uint32_t ra = __float_as_uint(a - __uint_as_float(ua & 0xffff0000u)) + 0x8000u;
+  const uint32_t rb = __float_as_uint(b - __uint_as_float(ub & 0xffff0000u)) + 0x8000u;
+  lo = __byte_perm(ra, rb, 0x7632);
+}
+
 // prior: -(P/2) ln s2 - sum(w^2)/(2 s2)   (_revamp.py:404-410)
 __device__ __forceinline__ double prior_from_sumsq(double sumsq, int P, double s2) {
   return -1.0 * ((double)P / 2.0) * log(s2) - (1.0 / (2.0 * s2)) * sumsq;

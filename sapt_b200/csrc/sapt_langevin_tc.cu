@@ -110,20 +110,12 @@ __device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[N]) {
   else if constexpr (N == 8) tmem_ld8(taddr, r);
   else tmem_ld4(taddr, r);
 }
-// two bf16 pieces of v (round to nearest): v ~ hi + lo to 2^-17 relative
-__device__ __forceinline__ void split2(float v, float& hi, float& lo) {
-  hi = __bfloat162float(__float2bfloat16_rn(v));
-  lo = v - hi;
-}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 
-// writes n bf16 values (n = 4, 8 or 16) of one data row into a swizzled [128 rows][64 bf16] block at column col0
+// writes n bf16 values (n = 4, 8 or 16; packed pairs, N/2 words) of one data row into a swizzled [128 rows][64 bf16] block at column col0
 template <int N>
-__device__ __forceinline__ void store_row_bf16(uint8_t* block, int row, int col0, const float (&v)[N]) {
-  uint32_t w[N / 2];
-#pragma unroll
-  for (int j = 0; j < N / 2; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+__device__ __forceinline__ void store_row_packed(uint8_t* block, int row, int col0, const uint32_t (&w)[N / 2]) {
   uint8_t* rowp = block + row * 128;
   if constexpr (N == 4) {
     const int chunk = col0 >> 3;
@@ -361,14 +353,18 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
             uint32_t zr[HW];
             tmem_ldN<HW>(tmem_base + lane_base + (uint32_t)(C::kDS + b * 64 + slice * HW), zr);
             tmem_ld_wait();
-            float h1[HW], h2[HW];
+            // The epilogue is SFU bound: one shared reciprocal per four sigmoids and an integer bf16 split instead of
+            // conversion instructions (16 hidden units: 20 SFU operations instead of 80, see split_pack_bf16x2)
+            uint32_t h1[HW / 2], h2[HW / 2];
 #pragma unroll
-            for (int j = 0; j < HW; ++j) {
-              h[b][j] = rcp_approx(1.0f + ex2_approx(fminf(__uint_as_float(zr[j]), 60.0f)));
-              split2(h[b][j], h1[j], h2[j]);
+            for (int j = 0; j < HW; j += 4) {
+              sigmoid4_from_neg_log2e(__uint_as_float(zr[j]), __uint_as_float(zr[j + 1]), __uint_as_float(zr[j + 2]), __uint_as_float(zr[j + 3]),
+                                      h[b][j], h[b][j + 1], h[b][j + 2], h[b][j + 3]);
+              split_pack_bf16x2(h[b][j], h[b][j + 1], h1[j / 2], h2[j / 2]);
+              split_pack_bf16x2(h[b][j + 2], h[b][j + 3], h1[j / 2 + 1], h2[j / 2 + 1]);
             }
-            store_row_bf16<HW>(hs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, h1);
-            store_row_bf16<HW>(hs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, h2);
+            store_row_packed<HW>(hs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, h1);
+            store_row_packed<HW>(hs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, h2);
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
@@ -385,23 +381,31 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
             const uint32_t ta = tmem_base + lane_base + C::kDS + b * 64;
             tmem_ldN<NRL>(ta, d0); tmem_ldN<NRL>(ta + ON, d1); tmem_ldN<NRL>(ta + 2 * ON, d2);
             tmem_ld_wait();
-            float dhi[ON], dlo[ON];
+            uint32_t dhi[ON / 2], dlo[ON / 2];
 #pragma unroll
-            for (int o = NRL; o < ON; ++o) { dhi[o] = 0.f; dlo[o] = 0.f; }
+            for (int o = NRL / 2; o < ON / 2; ++o) { dhi[o] = 0u; dlo[o] = 0u; }
+            const bool live = (y[b] >= 0);
 #pragma unroll
-            for (int o = 0; o < NRL; ++o) {
-              float dv = 0.f;
-              if (o < O && y[b] >= 0) {
-                float tt = (__uint_as_float(d0[o]) + __uint_as_float(d1[o])) + __uint_as_float(d2[o]);
-                if (!p.fold_bias) tt += __ldg(p.bias2 + (int64_t)pos * ON + o);
-                const float out = rcp_approx(1.0f + ex2_approx(fminf(tt, 60.0f)));
-                dv = ((o == y[b] ? 1.0f : 0.0f) - out) * (out * (1.0f - out));     // LG:100
-                accB2[o] += dv;
+            for (int o4 = 0; o4 < NRL; o4 += 4) {
+              float tt[4], out[4], dv[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int o = o4 + j;
+                tt[j] = (__uint_as_float(d0[o]) + __uint_as_float(d1[o])) + __uint_as_float(d2[o]);
+                if (!p.fold_bias) tt[j] += __ldg(p.bias2 + (int64_t)pos * ON + o);
               }
-              split2(dv, dhi[o], dlo[o]);
+              sigmoid4_from_neg_log2e(tt[0], tt[1], tt[2], tt[3], out[0], out[1], out[2], out[3]);   // columns >= O hold t = 0: finite, masked below
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int o = o4 + j;
+                dv[j] = (o < O && live) ? ((o == y[b] ? 1.0f : 0.0f) - out[j]) * (out[j] * (1.0f - out[j])) : 0.0f;     // LG:100
+                accB2[o] += dv[j];
+              }
+              split_pack_bf16x2(dv[0], dv[1], dhi[o4 / 2], dlo[o4 / 2]);
+              split_pack_bf16x2(dv[2], dv[3], dhi[o4 / 2 + 1], dlo[o4 / 2 + 1]);
             }
-            store_row_bf16<ON>(sDs, row_in_tile, 32 * b, dhi);
-            store_row_bf16<ON>(sDs, row_in_tile, 32 * b + ON, dlo);
+            store_row_packed<ON>(sDs, row_in_tile, 32 * b, dhi);
+            store_row_packed<ON>(sDs, row_in_tile, 32 * b + ON, dlo);
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
@@ -419,11 +423,13 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
             uint32_t zr[HW];
             tmem_ldN<HW>(tmem_base + lane_base + (uint32_t)(C::kDS + b * 64 + slice * HW), zr);
             tmem_ld_wait();
-            float g1[HW], g2[HW];
+            uint32_t g1[HW / 2], g2[HW / 2];
 #pragma unroll
-            for (int j = 0; j < HW; ++j) split2(__uint_as_float(zr[j]) * (h[b][j] * (1.0f - h[b][j])), g1[j], g2[j]);   // LG:101
-            store_row_bf16<HW>(hs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, g1);
-            store_row_bf16<HW>(hs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, g2);
+            for (int j = 0; j < HW; j += 2)
+              split_pack_bf16x2(__uint_as_float(zr[j]) * (h[b][j] * (1.0f - h[b][j])),                 // LG:101
+                                __uint_as_float(zr[j + 1]) * (h[b][j + 1] * (1.0f - h[b][j + 1])), g1[j / 2], g2[j / 2]);
+            store_row_packed<HW>(hs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, g1);
+            store_row_packed<HW>(hs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, g2);
             fence_async_smem();
             tc_fence_before();
             __syncwarp();

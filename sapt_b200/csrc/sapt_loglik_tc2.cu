@@ -202,6 +202,9 @@ __device__ __forceinline__ void sigmoid4_lim(float t0, float t1, float t2, float
   const float rab = r * cd, rcd = r * ab;
   s0 = rab * a1; s1 = rab * a0; s2 = rcd * a3; s3 = rcd * a2;
 }
+#ifndef SAPT_F32X2
+#define SAPT_F32X2 1      // packed fp32 pairs (FADD2 / FMUL2) in the epilogue arithmetic
+#endif
 #ifndef SAPT_P1_CHAIN
 #define SAPT_P1_CHAIN 2   // quads per ordered group in phase 1 (0: let ptxas schedule freely)
 #endif
@@ -404,6 +407,25 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
       float lim = 30.0f;
 #pragma unroll
       for (int j = 0; j < HW / 4; ++j) {
+#if SAPT_F32X2
+        // packed fp32 pairs (FADD2 / FMUL2): 31 instead of 38 instructions per four hidden units
+        f32x2 s10, s32;
+        sigmoid4_packed<false>(__uint_as_float(zr[4 * j]), __uint_as_float(zr[4 * j + 1]), __uint_as_float(zr[4 * j + 2]),
+                               __uint_as_float(zr[4 * j + 3]), lim, 1.0f, s10, s32);
+        float h0, h1, h2, h3;
+        unpack2(s10, h1, h0); unpack2(s32, h3, h2);
+#if SAPT_P1_CHAIN > 0
+        if (j % SAPT_P1_CHAIN == SAPT_P1_CHAIN - 1) lim = fmaf(h0, 0.0f, 30.0f);
+#endif
+        const uint32_t u0 = __float_as_uint(h0), u1 = __float_as_uint(h1), u2 = __float_as_uint(h2), u3 = __float_as_uint(h3);
+        hv[2 * j] = __byte_perm(u0, u1, 0x7632);
+        hv[2 * j + 1] = __byte_perm(u2, u3, 0x7632);
+        float r0, r1, r2, r3;
+        unpack2(sub2(s10, pack2(__uint_as_float(u1 & 0xffff0000u), __uint_as_float(u0 & 0xffff0000u))), r1, r0);
+        unpack2(sub2(s32, pack2(__uint_as_float(u3 & 0xffff0000u), __uint_as_float(u2 & 0xffff0000u))), r3, r2);
+        hv[HW / 2 + 2 * j] = __byte_perm(__float_as_uint(r0) + 0x8000u, __float_as_uint(r1) + 0x8000u, 0x7632);
+        hv[HW / 2 + 2 * j + 1] = __byte_perm(__float_as_uint(r2) + 0x8000u, __float_as_uint(r3) + 0x8000u, 0x7632);
+#else
         float h0, h1, h2, h3;
         sigmoid4_lim(__uint_as_float(zr[4 * j]), __uint_as_float(zr[4 * j + 1]), __uint_as_float(zr[4 * j + 2]),
                      __uint_as_float(zr[4 * j + 3]), lim, h0, h1, h2, h3);
@@ -421,6 +443,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
         const uint32_t r3 = __float_as_uint(h3 - __uint_as_float(u3 & 0xffff0000u)) + 0x8000u;
         hv[HW / 2 + 2 * j] = __byte_perm(r0, r1, 0x7632);
         hv[HW / 2 + 2 * j + 1] = __byte_perm(r2, r3, 0x7632);
+#endif
       }
     };
     auto publish_hv = [&](int u) {  // activations of unit u -> TMEM (A operand of MMA-2), then tell the MMA warp
@@ -486,6 +509,14 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
             if constexpr (!FOLD) v += bias[o];
             return v;
           };
+          // two neighbouring outputs at once: the partial sums are added as packed pairs (o is even; the registers of a
+          // tcgen05.ld are consecutive, so the pairs need no moves)
+          auto tpair = [&](int o, float& ta, float& tb) {
+            f32x2 v = add2(pack2(__uint_as_float(dr0[o]), __uint_as_float(dr0[o + 1])), pack2(__uint_as_float(dr1[o]), __uint_as_float(dr1[o + 1])));
+            if constexpr (PARTS == 3) v = add2(v, pack2(__uint_as_float(dr2[o]), __uint_as_float(dr2[o + 1])));
+            if constexpr (!FOLD) v = add2(v, pack2(bias[o], bias[o + 1]));
+            unpack2(v, ta, tb);
+          };
           auto emit = [&](int o, float t, float sv) {
             if (t < tmin) { tmin = t; pm = o; }
             sum += ex2_approx(sv);
@@ -499,13 +530,27 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
           for (int g = 0; g < NR / 4; ++g) {
             const int rem = O - 4 * g;   // warp-uniform
             if (rem >= 4) {
+#if SAPT_F32X2
+              float t0, t1, t2, t3;
+              tpair(4 * g, t0, t1); tpair(4 * g + 2, t2, t3);
+              f32x2 s10, s32;
+              sigmoid4_packed<true>(t0, t1, t2, t3, 30.0f, kLog2e, s10, s32);
+              float s0, s1, s2, s3;
+              unpack2(s10, s1, s0); unpack2(s32, s3, s2);
+#else
               const float t0 = tval(4 * g), t1 = tval(4 * g + 1), t2 = tval(4 * g + 2), t3 = tval(4 * g + 3);
               float s0, s1, s2, s3;
               sigmoid4_scaled(t0, t1, t2, t3, kLog2e, s0, s1, s2, s3);
+#endif
               emit(4 * g, t0, s0); emit(4 * g + 1, t1, s1); emit(4 * g + 2, t2, s2); emit(4 * g + 3, t3, s3);
             } else if (rem > 0) {
               if (rem & 2) {
+#if SAPT_F32X2
+                float t0, t1;
+                tpair(4 * g, t0, t1);
+#else
                 const float t0 = tval(4 * g), t1 = tval(4 * g + 1);
+#endif
                 const float a0 = 1.0f + ex2_approx(fminf(t0, 30.0f)), a1 = 1.0f + ex2_approx(fminf(t1, 30.0f));
                 const float r = rcp_approx(a0 * a1) * kLog2e;
                 emit(4 * g, t0, r * a1); emit(4 * g + 1, t1, r * a0);

@@ -15,7 +15,7 @@ namespace {
 constexpr int kChains = 8;
 constexpr int kInner = 64;
 
-enum PipeOp { OP_EX2 = 0, OP_RCP = 1, OP_FFMA = 2, OP_FMUL = 3, OP_FFMA2 = 4, OP_LOP3 = 5, OP_MIX = 6, OP_COUNT = 7 };
+enum PipeOp { OP_EX2 = 0, OP_RCP = 1, OP_FFMA = 2, OP_FMUL = 3, OP_FFMA2 = 4, OP_LOP3 = 5, OP_MIX = 6, OP_F2FP = 7, OP_COUNT = 8 };
 
 template <int OP>
 __global__ void __launch_bounds__(1024, 2) pipe_kernel(float* out, long long* cycles, int iters, float a, float b) {
@@ -45,6 +45,11 @@ __global__ void __launch_bounds__(1024, 2) pipe_kernel(float* out, long long* cy
         else if constexpr (OP == OP_FMUL) asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(v[c]) : "f"(a));
         else if constexpr (OP == OP_FFMA2) { if (c < kChains / 2) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(w[c]) : "l"(ab), "l"(bb)); }
         else if constexpr (OP == OP_LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(q[c]) : "r"(q[(c + 1) % kChains]), "r"(0x9E3779B9u));
+        else if constexpr (OP == OP_F2FP) {   // cvt.rn.bf16x2.f32 (F2FP.BF16.F32.PACK_AB): which pipe do conversions run on?
+          uint32_t pk;
+          asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(v[c]), "f"(v[(c + 1) % kChains]));
+          v[c] = __uint_as_float(pk & 0x3f800000u | 0x3f000000u);
+        }
         else {  // OP_MIX: one MUFU per four FFMA (roughly the likelihood epilogue's ratio), to see whether the pipes overlap
           if (c % 4 == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[c]));
           else asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(v[c]) : "f"(a), "f"(b));
@@ -114,6 +119,7 @@ extern "C" int sapt_measure_pipes(int device, double* out, int n_out, void* stre
   if (!rc) rc = run_pipe<OP_FFMA2>(sms, 4 * iters, d_out, d_cyc, st, &ops[OP_FFMA2], &hz[OP_FFMA2]);
   if (!rc) rc = run_pipe<OP_LOP3>(sms, 4 * iters, d_out, d_cyc, st, &ops[OP_LOP3], &hz[OP_LOP3]);
   if (!rc) rc = run_pipe<OP_MIX>(sms, 2 * iters, d_out, d_cyc, st, &ops[OP_MIX], &hz[OP_MIX]);
+  if (!rc) rc = run_pipe<OP_F2FP>(sms, iters, d_out, d_cyc, st, &ops[OP_F2FP], &hz[OP_F2FP]);
   cudaFree(d_out); cudaFree(d_cyc);
   if (rc) return rc;
   out[SAPT_PIPE_SMS] = sms;
@@ -126,5 +132,6 @@ extern "C" int sapt_measure_pipes(int device, double* out, int n_out, void* stre
   out[SAPT_PIPE_LOP3] = ops[OP_LOP3];
   out[SAPT_PIPE_MIX] = ops[OP_MIX];
   out[SAPT_PIPE_SM_HZ_MUFU] = hz[OP_EX2];
+  out[SAPT_PIPE_F2FP] = ops[OP_F2FP];
   return SAPT_OK;
 }
