@@ -274,6 +274,18 @@ def _stored_traffic(kernel_key, chains):
         return None, f"no stored traffic figure ({type(ex).__name__})"
 
 
+class FixedTrainer:
+    """Stands in for surrogate.train in the throughput legs: hands out one fixed MLP at the first rendezvous and never looks
+    at the batch (accepts_lazy_batch: the engine then does not read the batch length back to the host)."""
+    accepts_lazy_batch = True
+
+    def __init__(self, weights):
+        self.w = weights
+
+    def __call__(self, batch, signature):
+        return self.w if signature == 1 else None
+
+
 def _fixed_surrogate(P, h1, h2, seed):
     rs = np.random.RandomState(seed)
     u = lambda *s: rs.uniform(-0.05, 0.05, s).astype(np.float32)
@@ -495,7 +507,7 @@ def secondary_c5(rank, world, local, flush, pipes, n_sm, sm_mhz, peaks):
     cfg = EngineConfig(variant="rw", samples=warm + steps + 2, swap_interval=W["swap_interval"], surrogate_interval=W["swap_interval"],
                        surrogate_prob=0.5, use_surrogate=True, surrogate_topology=3, seed=W["seed"], record_pos=False, train_cap=W["swap_interval"],
                        rank=rank, world=world)
-    eng = PTEngine(prob, assign_temperatures(Rl * world, W["maxtemp"]), cfg, surrogate_trainer=lambda batch, sig: (w if sig == 1 else None))
+    eng = PTEngine(prob, assign_temperatures(Rl * world, W["maxtemp"]), cfg, surrogate_trainer=FixedTrainer(w))
     eng.keep_batches = False
     eng.initialize(np.random.RandomState(3).randn(prob.P) * 0.5)
     for i in range(warm):

@@ -179,6 +179,20 @@ int sapt_surrogate_predict(const float* theta, int64_t ld, int R, int P,
                            const float* W2, const float* b2, int h2,
                            const float* W3, const float* b3, float* s, void* stream);
 
+/* ---- surrogate rendezvous: the interval's training rows (theta', L_untempered) that sapt_mh_accept / sapt_lg_first_eval
+ * appended to the slot-indexed buffers train_theta[n_slots][cap][P], train_L[n_slots][cap] — replaces the (n, P+1) float64
+ * blocks the chains put on surrogate_parameterqueue (RW:626-627, LG:822) and their concatenation chain by chain
+ * (RW:1105-1116). Index vectors come from the caller (static shapes, computed on the device from the per-chain counts).
+ * pack: payload[i] = [theta' (P fp32) | L (fp64 bits, two words) | dest[i] | 0], row width P + 4 words, for
+ *       src[i] = slot * cap + j >= 0; src[i] < 0 marks a padding row (destination -1).
+ * scatter: batch[dest][0..P] = (double) payload row for every row with dest >= 0 of `payload` (the rows of all ranks,
+ *       gathered on the trainer rank), and batch[zero_rows[k]][:] = 0 for the all-zero first row of every chain that the
+ *       RW / LG forks ship (RW:496,626). batch is fp64 [.][P + 1], the reference trainer's input layout (RV:976-985). */
+int sapt_train_rows_pack(const float* train_theta, const double* train_L, const int32_t* src, const int32_t* dest, int n_rows, int P,
+                         float* payload, void* stream);
+int sapt_train_rows_scatter(const float* payload, int64_t n_payload, int P, const int64_t* zero_rows, int n_zero, double* batch,
+                            void* stream);
+
 /* ---- chain state: scalars of the reference's ptReplica.run locals. Indexed by GLOBAL chain id
  * ("slot") except slot_of_row, which maps the rank-local theta rows to the chain each hosts.
  * Every rank keeps full-size arrays and only touches the slots its rows host; the caller

@@ -1,0 +1,83 @@
+// Surrogate rendezvous (RW:621-657, RW:1105-1116; LG:819-844): moving the interval's (theta', L) training rows.
+// The reference pickles an (n, P+1) float64 block per chain through a multiprocessing queue and concatenates them
+// chain by chain. Here the rows sit in slot-indexed device buffers on whichever rank hosted the chain when they were
+// written; two kernels do all row movement, driven by index vectors the host logic (parallel.py) computes with
+// static shapes — no data-dependent allocation, no host synchronisation:
+//
+//   train_rows_pack    payload[i] = [ theta' (P fp32) | L (fp64 as two words) | destination row | 0 ]  for the i-th
+//                      row this rank owns (src[i] = slot * cap + j), or destination -1 for the padding rows
+//   train_rows_scatter batch[dest] = (double) payload row, for the payloads of all ranks (gathered on the trainer
+//                      rank), plus the all-zero first row of every chain the RW / LG forks ship (RW:496,626)
+//
+// One CTA per row; the copies are coalesced over P. HBM-bound: 4 (P + 4) bytes read + written per row in pack,
+// 4 (P + 4) read + 8 (P + 1) written in scatter.
+#include "sapt_device.cuh"
+#include "sapt_internal.h"
+
+namespace sapt {
+
+__global__ void train_rows_pack_kernel(const float* __restrict__ train_theta, const double* __restrict__ train_L, const int32_t* __restrict__ src,
+                                       const int32_t* __restrict__ dest, int P, float* __restrict__ payload) {
+  const int64_t i = blockIdx.x;
+  const int W = P + 4;
+  float* out = payload + i * W;
+  const int s = src[i];
+  if (s < 0) {                      // padding row: only the destination word is read downstream
+    if (threadIdx.x == 0) reinterpret_cast<int32_t*>(out)[P + 2] = -1;
+    return;
+  }
+  const float* in = train_theta + (int64_t)s * P;
+  for (int c = threadIdx.x; c < P; c += blockDim.x) out[c] = in[c];
+  if (threadIdx.x == 0) {
+    const long long bits = __double_as_longlong(train_L[s]);
+    reinterpret_cast<int32_t*>(out)[P] = (int32_t)(bits & 0xffffffffll);
+    reinterpret_cast<int32_t*>(out)[P + 1] = (int32_t)(bits >> 32);
+    reinterpret_cast<int32_t*>(out)[P + 2] = dest[i];
+    out[P + 3] = 0.f;
+  }
+}
+
+__global__ void train_rows_scatter_kernel(const float* __restrict__ payload, int64_t n_payload, int P, const int64_t* __restrict__ zero_rows,
+                                          int n_zero, double* __restrict__ batch) {
+  const int64_t i = blockIdx.x;
+  const int W = P + 4;
+  if (i >= n_payload) {             // the all-zero first row of chain i - n_payload
+    double* out = batch + zero_rows[i - n_payload] * (P + 1);
+    for (int c = threadIdx.x; c <= P; c += blockDim.x) out[c] = 0.0;
+    return;
+  }
+  const float* in = payload + i * W;
+  const int d = reinterpret_cast<const int32_t*>(in)[P + 2];
+  if (d < 0) return;
+  double* out = batch + (int64_t)d * (P + 1);
+  for (int c = threadIdx.x; c < P; c += blockDim.x) out[c] = (double)in[c];
+  if (threadIdx.x == 0) {
+    const unsigned long long lo = (uint32_t)reinterpret_cast<const int32_t*>(in)[P];
+    const unsigned long long hi = (uint32_t)reinterpret_cast<const int32_t*>(in)[P + 1];
+    out[P] = __longlong_as_double((long long)(lo | (hi << 32)));
+  }
+}
+
+}  // namespace sapt
+
+using namespace sapt;
+
+extern "C" int sapt_train_rows_pack(const float* train_theta, const double* train_L, const int32_t* src, const int32_t* dest, int n_rows, int P,
+                                    float* payload, void* stream) {
+  SAPT_REQUIRE(train_theta && train_L && src && dest && payload && n_rows >= 0 && P > 0, "sapt_train_rows_pack");
+  if (n_rows == 0) return SAPT_OK;
+  train_rows_pack_kernel<<<n_rows, 128, 0, (cudaStream_t)stream>>>(train_theta, train_L, src, dest, P, payload);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}
+
+extern "C" int sapt_train_rows_scatter(const float* payload, int64_t n_payload, int P, const int64_t* zero_rows, int n_zero, double* batch,
+                                       void* stream) {
+  SAPT_REQUIRE(payload && batch && n_payload >= 0 && P > 0 && n_zero >= 0 && (n_zero == 0 || zero_rows), "sapt_train_rows_scatter");
+  const int64_t grid = n_payload + n_zero;
+  if (grid == 0) return SAPT_OK;
+  SAPT_REQUIRE(grid < (int64_t)1 << 31, "too many rows for one launch");
+  train_rows_scatter_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(payload, n_payload, P, zero_rows, n_zero, batch);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}

@@ -89,17 +89,55 @@ class Surrogate:
         self.P = P
         self.device = device
         self.weights: Optional[Dict[str, torch.Tensor]] = None
+        self.flat: Optional[torch.Tensor] = None
         self.min_y = 0.0
         self.max_y = 0.0
         self.signature = 0
 
-    def set_weights(self, w: Dict[str, np.ndarray]):
-        self.weights = {k: torch.as_tensor(np.ascontiguousarray(v, dtype=np.float32)).reshape(-1).to(self.device)
-                        for k, v in w.items()}
+    @property
+    def shapes(self):
+        return ((self.P, self.h1), (self.h1,), (self.h1, self.h2), (self.h2,), (self.h2, 1), (1,))
+
+    def set_weights(self, w):
+        """w: dict W1,b1,W2,b2,W3,b3 (numpy or tensors, Keras Dense layout). Stored as views into ONE flat fp32 device
+        buffer, so that a later set of weights can be taken on the device without the host looking at it."""
+        sizes = [int(np.prod(sh)) for sh in self.shapes]
+        if self.flat is None:
+            self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=self.device)
+            views, o = {}, 0
+            for k, n in zip(parallel.SURROGATE_WEIGHT_KEYS, sizes):
+                views[k] = self.flat[o:o + n]
+                o += n
+            self._views = views
+        for k, n in zip(parallel.SURROGATE_WEIGHT_KEYS, sizes):
+            v = w[k]
+            v = v.to(torch.float32) if torch.is_tensor(v) else torch.as_tensor(np.ascontiguousarray(v, dtype=np.float32))
+            if v.numel() != n:
+                raise ValueError(f"surrogate weight {k}: {v.numel()} values, expected {n} for P={self.P}, hidden {self.h1}/{self.h2}")
+            self._views[k].copy_(v.reshape(-1).to(self.device))
+        self.weights = self._views
 
     @property
     def ready(self) -> bool:
         return self.weights is not None
+
+
+class TrainingBatch:
+    """The rendezvous batch on the trainer rank: a preallocated fp64 [n_max, P+1] buffer and the number of valid rows as
+    a DEVICE scalar. `tensor()` is the exact [n, P+1] view (one host read of n); a trainer that sets
+    `accepts_lazy_batch = True` receives this object instead and decides itself whether to look."""
+
+    def __init__(self, buf: torch.Tensor, n_dev: torch.Tensor):
+        self.buf, self.n_dev, self._n = buf, n_dev, None
+
+    @property
+    def n(self) -> int:
+        if self._n is None:
+            self._n = int(self.n_dev.item())
+        return self._n
+
+    def tensor(self) -> torch.Tensor:
+        return self.buf[: self.n]
 
 
 class PTEngine:
@@ -182,6 +220,14 @@ class PTEngine:
             self.train_theta = torch.zeros((self.Rg, self.train_cap, self.P), dtype=torch.float32, device=dev)
             self.train_L = torch.zeros((self.Rg, self.train_cap), **f64)
             self.train_count = torch.zeros(self.Rg, **i32)
+            # rows stay on the rank that wrote them (parallel.py "surrogate rendezvous"): which entries this rank owns, the
+            # counts at the last synchronisation, and the fixed-size payload it ships to the trainer rank
+            self.train_seen = torch.zeros(self.Rg, **i32)
+            self.train_mine = torch.zeros((self.Rg, self.train_cap), dtype=torch.bool, device=dev)
+            self.train_npad = self.R * max(self.train_cap, interval + 1)   # a rank appends <= R rows per step of the interval
+            self.train_payload = torch.zeros((self.train_npad, self.P + 4), dtype=torch.float32, device=dev)
+            self._batch_buf = None
+        self.trainer_rank = 0
         self._train_synced = False
         self.surr_batches: List[torch.Tensor] = []   # device tensors of every rendezvous (what the parity tests compare)
         self.keep_batches = True                     # False: a batch is dropped once the trainer has seen it (long / huge runs)
@@ -409,7 +455,7 @@ class PTEngine:
         if self.Rg < 2:
             return
         self.sync_slots()
-        self._sync_training_buffers()
+        self._sync_training_counts()
         if self.cfg.world > 1 and self.hist is not None and "pos_w" in self.hist:
             # a rejected step copies pos_w history row i (RV:608): the row must follow the slot across ranks
             import torch.distributed as dist
@@ -432,41 +478,47 @@ class PTEngine:
         self.sweep_count += 1
         self.total_swap_proposals += self.Rg - 1
 
-    def _sync_training_buffers(self):
-        """Multi-rank: a chain's training rows are appended on whichever rank hosts the chain. Taking every chain's
-        buffer from its CURRENT host (masked all-reduce, in place) makes the buffers complete and identical on all
-        ranks; it must run before an exchange re-binds the chains (the rows of the interval were written under the
-        old binding) and before the rows are handed to the trainer."""
-        if self.cfg.world == 1 or self.train_theta is None or self._train_synced:
+    def _sync_training_counts(self):
+        """A chain's training rows are appended on whichever rank hosts the chain, and they STAY there. What follows the
+        chain is its row count: before an exchange re-binds the chains (and before a rendezvous) every rank marks the
+        entries it has written since the last call as its own and the counts are taken from the current hosts (one
+        [R_global] int32 all-reduce), so the next host continues at the right index."""
+        if self.train_theta is None or self._train_synced:
             return
-        parallel.sync_training_buffers(self.train_theta, self.train_L, self.train_count, self._hosted_mask(), self.pg)
+        mask = self._hosted_mask()
+        parallel.mark_owned(self.train_mine, self.train_seen, self.train_count, mask)
+        if self.cfg.world > 1:
+            parallel.sync_train_counts(self.train_count, self.train_seen, mask, self.pg)
+        else:
+            self.train_seen.copy_(self.train_count)
         self._train_synced = True
 
-    def gather_training_rows(self) -> torch.Tensor:
-        """(theta', L_untempered) rows of the interval's true steps, chain by chain (RW:1105-1116), as ONE device
-        tensor [n, P+1] (fp64): the training set never visits the host (the reference pickles it through queues)."""
-        self._sync_training_buffers()
-        cnt = self.train_count
-        th, tl = self.train_theta, self.train_L
-        cap = self.train_cap
-        j = torch.arange(cap, device=self.dev)[None, :]
-        valid = j < cnt.long()[:, None]                       # [Rg, cap]
-        if self.spec.name == "rv":
-            valid = valid & (j >= 1)                           # RV ships surr_train_set[1:count_real] (RV:683)
-        # Only the valid rows are touched: gather them in fp32, widen once into the output. (Materialising the whole
-        # [Rg, cap, P+1] fp64 array first cost ~4x the traffic and dominated the rendezvous at 65 536 chains.)
-        ck, cj = torch.nonzero(valid, as_tuple=True)          # chain-major, step order within a chain
-        zero = 1 if self.spec.ship_zero_row else 0            # RW:496,626 / LG:543,822: all-zero first row per chain
-        per_chain = valid.sum(dim=1) + zero
-        start = torch.cumsum(per_chain, 0) - per_chain         # first output row of every chain
-        n_out = int(per_chain.sum().item())
-        batch = torch.zeros((n_out, self.P + 1), dtype=torch.float64, device=self.dev)
-        if ck.numel():
-            rank_in_chain = torch.cumsum(valid.to(torch.int64), dim=1)[ck, cj] - 1
-            dst = start[ck] + zero + rank_in_chain
-            batch[dst, : self.P] = th[ck, cj].double()
-            batch[dst, self.P] = tl[ck, cj]
-        self.train_count.zero_()
+    def gather_training_rows(self):
+        """(theta', L_untempered) rows of the interval's true steps, chain by chain (RW:1105-1116), as ONE device tensor
+        [n, P+1] (fp64) on the trainer rank: the training set never visits the host (the reference pickles it through
+        queues). Every rank packs the rows it owns with their final batch position (sapt_train_rows_pack), the fixed-size
+        payloads are gathered on the trainer rank and scattered into the batch (sapt_train_rows_scatter). All shapes are
+        static: no host synchronisation. Returns a TrainingBatch on the trainer rank, None elsewhere; `self.last_n_out`
+        is the device scalar with the number of rows (known on every rank)."""
+        self._sync_training_counts()
+        src, dest, zero_rows, n_out = parallel.training_row_plan(self.train_count, self.train_mine, self.train_npad,
+                                                                 skip_first=(self.spec.name == "rv"),      # RV ships surr_train_set[1:count_real] (RV:683)
+                                                                 zero_row=self.spec.ship_zero_row)          # RW:496,626 / LG:543,822
+        self.last_n_out = n_out
+        st = current_stream_ptr()
+        _lib.check(self.L.sapt_train_rows_pack(_ptr(self.train_theta), _ptr(self.train_L), _ptr(src), _ptr(dest), self.train_npad, self.P,
+                                               _ptr(self.train_payload), st), "sapt_train_rows_pack")
+        allp = parallel.gather_payloads(self.train_payload, self.trainer_rank, self.cfg.world, self.pg)
+        batch = None
+        if self.cfg.rank == self.trainer_rank:
+            if self._batch_buf is None:
+                zero = 1 if self.spec.ship_zero_row else 0
+                self._batch_buf = torch.zeros((self.Rg * (self.train_cap + zero), self.P + 1), dtype=torch.float64, device=self.dev)
+            _lib.check(self.L.sapt_train_rows_scatter(_ptr(allp), allp.shape[0], self.P, _ptr(zero_rows) if zero_rows.numel() else None,
+                                                      int(zero_rows.numel()), _ptr(self._batch_buf), st), "sapt_train_rows_scatter")
+            batch = TrainingBatch(self._batch_buf, n_out)
+        self.train_count.zero_(); self.train_seen.zero_(); self.train_mine.zero_()
+        self._train_synced = False
         return batch
 
     def _ls_sync_history(self, upto: int):
@@ -492,24 +544,41 @@ class PTEngine:
         self.ls_ready = True
 
     def surrogate_rendezvous(self, i: int):
+        """RW:1105-1116 / RV:976-1026: collect the interval's rows, retrain, hand the model back to the chains. With
+        several ranks the rows go to ONE trainer rank and only the weights (and, once, minY / maxY) come back."""
         if self.ls is not None:
             return self.local_surrogate_train(i)
         batch = self.gather_training_rows()
-        if self.keep_batches:
-            self.surr_batches.append(batch)
-        if batch.shape[0] == 0:
-            return
+        if not self.spec.ship_zero_row and int(self.last_n_out.item()) == 0:
+            return            # RV ships no zero rows: an interval of surrogate steps only leaves nothing to train on
         sur = self.surrogate
         sur.signature += 1
-        if sur.signature == 1:  # minmax.txt is written once and read once (RV:996-997, RV:707-710)
-            sur.min_y = float(torch.min(batch[:, self.P]).item() * 2)
-            sur.max_y = -1.0
-        if self.inj is not None and self.inj_weights is not None:
-            sur.set_weights(self.inj_weights[sur.signature - 1])
-        elif self.trainer is not None:
-            w = self.trainer(batch, sur.signature)
+        first = sur.signature == 1
+        multi = self.cfg.world > 1
+        w, min_y, max_y = None, sur.min_y, sur.max_y
+        if self.cfg.rank == self.trainer_rank:
+            if self.keep_batches:
+                self.surr_batches.append(batch.tensor().clone())
+            if first:  # minmax.txt is written once and read once (RV:996-997, RV:707-710)
+                min_y, max_y = float(torch.min(batch.tensor()[:, self.P]).item() * 2), -1.0
+            if self.inj is not None and self.inj_weights is not None:
+                w = self.inj_weights[sur.signature - 1]
+            elif self.trainer is not None:
+                w = self.trainer(batch if getattr(self.trainer, "accepts_lazy_batch", False) else batch.tensor(), sur.signature)
+        if not multi:
+            sur.min_y, sur.max_y = min_y, max_y
             if w is not None:
                 sur.set_weights(w)
+            return
+        head, flat = parallel.broadcast_surrogate_device(w, sur.shapes, min_y, max_y, self.trainer_rank, self.dev, self.pg)
+        if first or not sur.ready:
+            h = head.cpu()     # the only host read: until a model exists every rank must learn whether one arrived (and minY / maxY once)
+            if first:
+                sur.min_y, sur.max_y = float(h[1]), float(h[2])
+            if h[0] > 0:
+                sur.set_weights(parallel.split_flat(flat, sur.shapes))
+        else:                  # later models are taken on the device: new weights if the trainer produced any, else the old ones
+            sur.flat.copy_(torch.where(head[0] > 0, flat, sur.flat))
 
     def rendezvous(self, i: int):
         cfg, sp = self.cfg, self.spec

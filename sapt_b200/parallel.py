@@ -68,19 +68,124 @@ def merge_history(hist: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
-def sync_training_buffers(train_theta: torch.Tensor, train_L: torch.Tensor, train_count: torch.Tensor, mask: torch.Tensor, group=None) -> None:
-    """Surrogate training rows are appended on whichever rank hosts a chain. In place: every chain's buffer
-    ([R_global, cap, P] rows, [R_global, cap] likelihoods, [R_global] counts) is taken from its CURRENT host, so
-    afterwards the buffers are complete and identical on all ranks. Must run before an exchange re-binds the chains
-    (the rows of the interval were written under the old binding) and before the rows go to the trainer."""
+# ---- surrogate rendezvous: training rows stay where they were written -----------------------------------------------
+# A chain's (theta', L) rows are appended to slot-indexed buffers on whichever rank hosts the chain at that step; the
+# per-chain count travels with the chain (one [R_global] int32 all-reduce per exchange), so the new host continues at the
+# right index and every rank knows which entries it wrote itself ("owned"). At the rendezvous each rank packs its owned
+# rows with their final position in the chain-by-chain batch (RW:1105-1116) into a fixed-size payload, the payloads are
+# gathered on the trainer rank, scattered into the batch, and only the retrained weights (<= 3.2 MB) come back by
+# broadcast. Nothing here has a data-dependent shape, so the host never waits for the device.
+
+def mark_owned(train_mine: torch.Tensor, train_seen: torch.Tensor, train_count: torch.Tensor, mask: torch.Tensor) -> None:
+    """Entries [seen, count) of the slots this rank hosts were written here since the counts were last synchronised."""
+    cap = train_mine.shape[1]
+    j = torch.arange(cap, device=train_mine.device)[None, :]
+    new = (mask[:, None] > 0) & (j >= train_seen[:, None]) & (j < train_count[:, None])
+    train_mine.logical_or_(new)
+
+
+def sync_train_counts(train_count: torch.Tensor, train_seen: torch.Tensor, mask: torch.Tensor, group=None) -> None:
+    """The count of a chain is current on the rank that hosts it (stale elsewhere): take it from there, everywhere."""
     import torch.distributed as dist
-    cnt = train_count.to(torch.float64) * mask
-    train_theta.mul_(mask[:, None, None].to(train_theta.dtype))
-    train_L.mul_(mask[:, None].to(train_L.dtype))
+    cnt = torch.where(mask > 0, train_count, torch.zeros_like(train_count))
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(train_theta, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(train_L, op=dist.ReduceOp.SUM, group=group)
-    train_count.copy_(cnt.round().to(train_count.dtype))
+    train_count.copy_(cnt)
+    train_seen.copy_(cnt)
+
+
+def training_row_plan(train_count: torch.Tensor, train_mine, n_pad: int, skip_first: bool, zero_row: bool):
+    """Index vectors of the rendezvous, all with static shapes (device-side, no host synchronisation):
+    src [n_pad] int32   : slot * cap + j of the i-th row this rank owns, chain-major, -1 for padding
+    dest [n_pad] int32  : its row in the chain-by-chain batch (RW:1105-1116): chains in order, within a chain step order, after
+                          the chain's all-zero first row when `zero_row` (RW:496,626); `skip_first` drops entry 0 (RV:683)
+    zero_rows [R_global] int64 : batch row of every chain's zero row (empty when not shipped)
+    n_out [] int64      : rows of the batch
+    train_mine None = one rank owns everything it counts."""
+    Rg = train_count.shape[0]
+    dev = train_count.device
+    cap = train_mine.shape[1] if train_mine is not None else None
+    lo = 1 if skip_first else 0
+    zero = 1 if zero_row else 0
+    cnt = train_count.to(torch.int64)
+    if cap is None:
+        raise ValueError("training_row_plan needs the [R_global, cap] ownership mask (use an all-true mask on one rank)")
+    cnt = torch.clamp(cnt, max=cap)
+    n_valid = torch.clamp(cnt - lo, min=0)
+    per_chain = n_valid + zero
+    start = torch.cumsum(per_chain, 0) - per_chain                      # first batch row of every chain
+    n_out = per_chain.sum()
+    j = torch.arange(cap, device=dev, dtype=torch.int64)[None, :]
+    own = train_mine & (j >= lo) & (j < cnt[:, None])                   # [Rg, cap]
+    own_i = own.to(torch.int64)
+    owned_per_slot = own_i.sum(dim=1)
+    local_start = torch.cumsum(owned_per_slot, 0) - owned_per_slot
+    rank_in_slot = torch.cumsum(own_i, dim=1) - 1
+    pos = torch.where(own, local_start[:, None] + rank_in_slot, torch.full_like(rank_in_slot, n_pad))   # non-owned -> dummy slot n_pad
+    pos = torch.clamp(pos, max=n_pad)                                    # more owned rows than n_pad cannot happen (see engine); never write out of range
+    flat = (torch.arange(Rg, device=dev, dtype=torch.int64)[:, None] * cap + j).reshape(-1)
+    src = torch.full((n_pad + 1,), -1, dtype=torch.int64, device=dev)
+    src.scatter_(0, pos.reshape(-1), flat)
+    dst_val = (start[:, None] + zero + (j - lo)).expand(Rg, cap).reshape(-1)
+    dest = torch.full((n_pad + 1,), -1, dtype=torch.int64, device=dev)
+    dest.scatter_(0, pos.reshape(-1), dst_val)
+    src, dest = src[:n_pad], dest[:n_pad]
+    dest = torch.where(src >= 0, dest, torch.full_like(dest, -1))
+    zero_rows = start if zero_row else start[:0]
+    return src.to(torch.int32).contiguous(), dest.to(torch.int32).contiguous(), zero_rows.contiguous(), n_out
+
+
+def gather_payloads(payload: torch.Tensor, trainer_rank: int, world: int, group=None):
+    """Fixed-size payloads of all ranks -> one [world * n_pad, W] tensor on the trainer rank (None elsewhere)."""
+    import torch.distributed as dist
+    if world == 1:
+        return payload
+    rank = dist.get_rank(group)
+    if rank == trainer_rank:
+        parts = [torch.empty_like(payload) for _ in range(world)]
+        dist.gather(payload, gather_list=parts, dst=trainer_rank, group=group)
+        return torch.cat(parts, dim=0)
+    dist.gather(payload, gather_list=None, dst=trainer_rank, group=group)
+    return None
+
+
+SURROGATE_WEIGHT_KEYS = ("W1", "b1", "W2", "b2", "W3", "b3")
+
+
+def _sizes(shapes):
+    out = []
+    for sh in shapes:
+        n = 1
+        for v in sh:
+            n *= int(v)
+        out.append(n)
+    return out
+
+
+def split_flat(flat: torch.Tensor, shapes) -> dict:
+    out, o = {}, 0
+    for k, n in zip(SURROGATE_WEIGHT_KEYS, _sizes(shapes)):
+        out[k] = flat[o:o + n]
+        o += n
+    return out
+
+
+def broadcast_surrogate_device(weights, shapes, min_y: float, max_y: float, trainer_rank: int, device, group=None):
+    """Trainer rank -> everyone, as DEVICE tensors (the caller decides whether the host has to look): head = [has_weights,
+    min_y, max_y] (fp64) and the flattened fp32 weights in the order W1, b1, W2, b2, W3, b3 (P h1 + h1 + h1 h2 + h2 + h2 + 1
+    values: <= 3.2 MB at P = 3975 with topology 3). `weights` is the trainer's dict (or None) on the trainer rank and
+    ignored elsewhere."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    head = torch.zeros(3, dtype=torch.float64, device=device)
+    flat = torch.zeros(sum(_sizes(shapes)), dtype=torch.float32, device=device)
+    if rank == trainer_rank:
+        head[1], head[2] = float(min_y), float(max_y)
+        if weights is not None:
+            head[0] = 1.0
+            flat.copy_(torch.cat([torch.as_tensor(weights[k]).to(torch.float32).reshape(-1).to(device) for k in SURROGATE_WEIGHT_KEYS]))
+    dist.broadcast(head, src=trainer_rank, group=group)
+    dist.broadcast(flat, src=trainer_rank, group=group)
+    return head, flat
 
 
 def sync_history_rows(hist_rows: torch.Tensor, group=None) -> None:

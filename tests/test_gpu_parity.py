@@ -1039,3 +1039,43 @@ def test_posterior_parity_same_seed_c2(lib):
                                surrogate_prob=0.4, use_surrogate=True, use_langevin=True, learn_rate=0.01, surrogate_topology=1, seed=5)
     assert np.asarray(res["is_surrogate_step"]).sum() > 0
     _assert_posterior_parity(res, ora, S, 0.5, "C2", mean_tol=1.5, std_factor=1.6, std_abs=0.5)
+
+
+@pytest.mark.parametrize("skip_first,zero_row", [(False, True), (True, False), (False, False)])
+def test_train_rows_pack_scatter_kernels(lib, skip_first, zero_row):
+    """The two row-movement kernels of the surrogate rendezvous against a direct chain-by-chain concatenation
+    (RW:1105-1116): ragged counts including empty and full chains, partial ownership (two simulated ranks)."""
+    from sapt_b200 import parallel
+    L = lib.lib()
+    rs = np.random.RandomState(3)
+    Rg, cap, P = 37, 6, 23
+    cnt = rs.randint(0, cap + 1, Rg).astype(np.int32); cnt[0] = 0; cnt[1] = cap
+    theta = rs.standard_normal((Rg, cap, P)).astype(np.float32)
+    Lv = rs.standard_normal((Rg, cap)) * 1e3
+    owner = rs.randint(0, 2, (Rg, cap))                      # which "rank" wrote entry (slot, j)
+    lo, zero = (1 if skip_first else 0), (1 if zero_row else 0)
+    rows = []
+    for s_ in range(Rg):
+        if zero:
+            rows.append(np.zeros(P + 1))
+        for j in range(lo, cnt[s_]):
+            rows.append(np.concatenate([theta[s_, j].astype(np.float64), [Lv[s_, j]]]))
+    want = np.array(rows) if rows else np.zeros((0, P + 1))
+    th = torch.as_tensor(theta).cuda(); tl = torch.as_tensor(Lv).cuda(); c = torch.as_tensor(cnt).cuda()
+    n_pad = Rg * cap
+    payloads = []
+    for r in range(2):
+        mine = torch.as_tensor(owner == r).cuda()
+        src, dest, zero_rows, n_out = parallel.training_row_plan(c, mine, n_pad, skip_first, zero_row)
+        assert int(n_out.item()) == want.shape[0]
+        payload = torch.full((n_pad, P + 4), 7.0, dtype=torch.float32).cuda()
+        lib.check(L.sapt_train_rows_pack(th.data_ptr(), tl.data_ptr(), src.data_ptr(), dest.data_ptr(), n_pad, P, payload.data_ptr(), None))
+        payloads.append(payload)
+    allp = torch.cat(payloads, 0)
+    batch = torch.full((Rg * (cap + zero), P + 1), 99.0, dtype=torch.float64).cuda()
+    lib.check(L.sapt_train_rows_scatter(allp.data_ptr(), allp.shape[0], P, zero_rows.data_ptr() if zero else None, int(zero_rows.numel()),
+                                        batch.data_ptr(), None))
+    torch.cuda.synchronize()
+    got = batch.cpu().numpy()
+    assert np.array_equal(got[: want.shape[0]], want)
+    assert np.all(got[want.shape[0]:] == 99.0)

@@ -64,17 +64,90 @@ def _worker(rank, world, port, q):
         assert torch.equal(merged, want)
         h8 = torch.zeros((2, Rg), dtype=torch.uint8); h8[:, slot_of_row.long()] = 1
         assert parallel.merge_history(h8).sum().item() == 2 * Rg
-        # surrogate training rows follow the chains: each rank holds the rows of the slots it hosts (stale garbage elsewhere)
-        cap, P = 3, 5
-        full_cnt = torch.tensor([3, 0, 2, 1, 3, 3, 0, 2], dtype=torch.int32)
-        full_th = torch.arange(Rg * cap * P, dtype=torch.float32).reshape(Rg, cap, P) + 1.0
-        full_L = -torch.arange(Rg * cap, dtype=torch.float64).reshape(Rg, cap) - 0.25
-        hosted = mask > 0
-        th = torch.where(hosted[:, None, None], full_th, torch.full_like(full_th, -777.0))
-        tl = torch.where(hosted[:, None], full_L, torch.full_like(full_L, 555.0))
-        cnt = torch.where(hosted, full_cnt, torch.full_like(full_cnt, 9))
-        parallel.sync_training_buffers(th, tl, cnt, mask)
-        assert torch.equal(th, full_th) and torch.equal(tl, full_L) and torch.equal(cnt, full_cnt)
+        # surrogate rendezvous: training rows STAY on the rank that wrote them, the per-chain counts follow the chains, the
+        # trainer rank assembles the chain-by-chain batch (RW:1105-1116) from fixed-size payloads; weights come back by broadcast
+        cap, P = 4, 5
+        truth_theta = torch.arange(Rg * cap * P, dtype=torch.float32).reshape(Rg, cap, P) + 1.0      # what entry (slot, j) holds, whoever wrote it
+        truth_L = -torch.arange(Rg * cap, dtype=torch.float64).reshape(Rg, cap) - 0.25 + 1e-9
+        th = torch.full((Rg, cap, P), -777.0); tl = torch.full((Rg, cap), 555.0, dtype=torch.float64)
+        cnt = torch.zeros(Rg, dtype=torch.int32); seen = torch.zeros(Rg, dtype=torch.int32); mine = torch.zeros((Rg, cap), dtype=torch.bool)
+
+        def append(slots, n_rows):     # the accept kernel's append, for the slots this rank hosts
+            for s_, n_ in zip(slots, n_rows):
+                for _ in range(n_):
+                    c = int(cnt[s_])
+                    if c < cap:
+                        th[s_, c] = truth_theta[s_, c]; tl[s_, c] = truth_L[s_, c]; cnt[s_] = c + 1
+        # epoch 1 under the first binding (slot_of_row), then an exchange re-binds the chains, then epoch 2
+        n1 = {2: 2, 0: 1, 4: 0, 6: 2, 1: 1, 7: 2, 3: 0, 5: 1}
+        append(slot_of_row.tolist(), [n1[s_] for s_ in slot_of_row.tolist()])
+        parallel.mark_owned(mine, seen, cnt, mask)
+        parallel.sync_train_counts(cnt, seen, mask)
+        assert cnt.tolist() == [n1[s_] for s_ in range(Rg)] and torch.equal(cnt, seen)
+        mask2 = parallel.hosted_mask(new_local, Rg)
+        n2 = {s_: (s_ % 3) for s_ in range(Rg)}
+        append(new_local.tolist(), [n2[s_] for s_ in new_local.tolist()])
+        parallel.mark_owned(mine, seen, cnt, mask2)
+        parallel.sync_train_counts(cnt, seen, mask2)
+        total = [min(cap, n1[s_] + n2[s_]) for s_ in range(Rg)]
+        assert cnt.tolist() == total
+        for skip_first, zero_row in ((False, True), (True, False), (False, False)):
+            n_pad = R * (cap + 1)
+            src, dest, zero_rows, n_out = parallel.training_row_plan(cnt, mine, n_pad, skip_first, zero_row)
+            assert src.shape == (n_pad,) and dest.shape == (n_pad,)
+            lo, zero = (1 if skip_first else 0), (1 if zero_row else 0)
+            want_rows = []
+            for s_ in range(Rg):
+                if zero:
+                    want_rows.append(torch.zeros(P + 1, dtype=torch.float64))
+                for j_ in range(lo, total[s_]):
+                    want_rows.append(torch.cat([truth_theta[s_, j_].double(), truth_L[s_, j_][None]]))
+            want = torch.stack(want_rows) if want_rows else torch.zeros((0, P + 1), dtype=torch.float64)
+            assert int(n_out) == want.shape[0]
+            # the contract of sapt_train_rows_pack / sapt_train_rows_scatter (include/sapt.h), restated in torch for the CPU
+            payload = torch.zeros((n_pad, P + 4), dtype=torch.float32)
+            pi = payload.view(torch.int32)
+            for i_ in range(n_pad):
+                if src[i_] < 0:
+                    pi[i_, P + 2] = -1
+                    continue
+                payload[i_, :P] = th.reshape(-1, P)[src[i_]]
+                bits = tl.reshape(-1)[src[i_]].view(torch.int64)
+                pi[i_, P] = ((bits & 0xffffffff) - (1 << 32) * ((bits >> 31) & 1)).to(torch.int32)
+                pi[i_, P + 1] = (bits >> 32).to(torch.int32)
+                pi[i_, P + 2] = dest[i_]
+            allp = parallel.gather_payloads(payload, 0, world)
+            if rank == 0:
+                assert allp.shape == (world * n_pad, P + 4)
+                batch = torch.full((Rg * (cap + zero), P + 1), 99.0, dtype=torch.float64)
+                ai = allp.view(torch.int32)
+                for i_ in range(allp.shape[0]):
+                    d_ = int(ai[i_, P + 2])
+                    if d_ >= 0:
+                        batch[d_, :P] = allp[i_, :P].double()
+                        lo_w, hi_w = int(ai[i_, P]) & 0xffffffff, int(ai[i_, P + 1]) & 0xffffffff
+                        batch[d_, P] = torch.tensor([(hi_w << 32) | lo_w], dtype=torch.int64).view(torch.float64)[0] if (hi_w >> 31) == 0 else \
+                            torch.tensor([((hi_w << 32) | lo_w) - (1 << 64)], dtype=torch.int64).view(torch.float64)[0]
+                for z_ in zero_rows.tolist():
+                    batch[z_] = 0.0
+                assert torch.equal(batch[: int(n_out)], want), (skip_first, zero_row)
+            else:
+                assert allp is None
+        # every entry is owned by exactly one rank
+        owned = mine.to(torch.int32)
+        dist.all_reduce(owned)
+        jj = torch.arange(cap)[None, :]
+        assert torch.equal(owned, (jj < cnt[:, None]).to(torch.int32))
+        # the retrained model goes back as one flat fp32 vector + [has_weights, minY, maxY]
+        shapes = ((P, 3), (3,), (3, 2), (2,), (2, 1), (1,))
+        wts = {k: torch.arange(int(np.prod(sh)), dtype=torch.float32).reshape(sh) + 10 * n_ for n_, (k, sh) in enumerate(zip(parallel.SURROGATE_WEIGHT_KEYS, shapes))}
+        head, flat = parallel.broadcast_surrogate_device(wts if rank == 0 else None, shapes, -123.5, -1.0, 0, torch.device("cpu"))
+        assert head.tolist() == [1.0, -123.5, -1.0]
+        got = parallel.split_flat(flat, shapes)
+        for k in parallel.SURROGATE_WEIGHT_KEYS:
+            assert torch.equal(got[k], wts[k].reshape(-1))
+        head, flat = parallel.broadcast_surrogate_device(None, shapes, 0.0, 0.0, 0, torch.device("cpu"))
+        assert head[0] == 0
         # history rows written since the last exchange: non-zero on the writing rank only, NaN markers included
         rows = torch.zeros((4, Rg, 3), dtype=torch.float64)
         rows[:, slot_of_row.long(), :] = float(rank + 1)
