@@ -53,6 +53,9 @@ struct DataSet {
   // tcgen05 operand image: [n_pad][KA] bf16, KA = 64: [x_hi | x_lo | x_hi | 1 1 0..] (see sapt_loglik_tc.cu)
   void* a_bf16 = nullptr;
   void* tmap = nullptr; // CUtensorMap (128 B, 64-byte aligned host copy) for a_bf16
+  // likelihood kernel's operand image: [n_pad][64 KBA] fp16 = [x_hi | x_lo | (1 1 0..)] (two fp16 pieces, see sapt_loglik_tc2.cu)
+  void* a_f16 = nullptr;
+  void* tmap_f16 = nullptr;
 };
 
 }  // namespace sapt

@@ -36,9 +36,20 @@
 #include <type_traits>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "sapt_device.cuh"
 #include "sapt_internal.h"
 #include "sapt_tc_ptx.cuh"
+
+// First-layer operands as TWO fp16 pieces (x = x_hi + x_lo, w = w_hi + w_lo: 22 significant bits each) instead of three bf16
+// pieces: MMA-1 then needs the products (x_hi,w_hi) (x_hi,w_lo) (x_lo,w_hi) — 3 instead of 6 K passes — for a dropped term of
+// 2^-22 |x w|, and an operand row is 1/3 shorter (D = 54: 2 instead of 3 K blocks per row and stage). fp16's range is no
+// obstacle: features are z-scored, weights pre-scaled by log2(e) saturate at +-65504, and subnormals keep the absolute error
+// of a small operand below 2^-25. 0: the three-piece bf16 operands of round 1 (kept for A/B measurements).
+#ifndef SAPT_X_FP16
+#define SAPT_X_FP16 1
+#endif
 
 namespace sapt {
 
@@ -75,7 +86,10 @@ struct TcCfg {
   static constexpr int UC = 4 / HALVES;                   // chains per unit (one MMA-1)
   static constexpr int HW = HP / HALVES;                  // hidden units per epilogue warp
   static constexpr int N1 = UC * HP;                      // MMA-1 N (<= 128)
-  static constexpr int KA = 48 * DKC + (BIASX ? 0 : 16);  // used bf16 per A / B1 row: [x1|x2|x3|bias chunk]
+  static constexpr bool XF16 = (SAPT_X_FP16 != 0);        // first-layer operands: two fp16 pieces, else three bf16 pieces
+  static constexpr int XP = XF16 ? 2 : 3;                 // pieces per operand
+  static constexpr int NPROD = XF16 ? 3 : 6;              // piece products accumulated by MMA-1
+  static constexpr int KA = 16 * XP * DKC + (BIASX ? 0 : 16);  // used elements per A / B1 row: [pieces | bias chunk]
   static constexpr int KBA = (KA + 63) / 64;              // 128-byte K blocks per row
   static constexpr int N2 = (ON == 16) ? 48 : 64;         // D2 columns per chain
   static constexpr int PARTS = N2 / ON;
@@ -116,7 +130,7 @@ struct Tc2Params {
 // W2: [group][CH][3 ON rows][64]  : row (p, o) = piece p of -log2(e) W2[:, o] over the HP hidden units (rest 0).
 //     MMA-2 reads rows [0, N2) as one operand against h1 and rows [0, 2 ON) again against h2.
 __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O,
-                                int HP, int ON, int CH, int DKC, int KROW, int biasx, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2) {
+                                int HP, int ON, int CH, int DKC, int KROW, int biasx, int xf16, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2) {
   constexpr int KW = 64;
   const int nact = n_rows ? *n_rows : R;
   const int pos = blockIdx.x;
@@ -136,6 +150,32 @@ __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* r
   const int row = rows ? rows[pos] : pos;
   const float* src = theta + (int64_t)row * ld;
   const int DW = 16 * DKC;                      // features per piece (padded)
+  if (xf16) {
+    // two fp16 pieces per weight: row (chain, h) = [w_hi (DW) | w_lo (DW) | bias chunk | 0..]; the bias pieces sit in column D of
+    // the two weight pieces (they meet the 1.0 in column D of the x_hi piece) or in the first two slots of the bias chunk
+    __half* hrow0 = reinterpret_cast<__half*>(brow0);
+    const __half hz = __float2half_rn(0.f);
+    for (int i = threadIdx.x; i < HP * KROW; i += blockDim.x) hrow0[i] = hz;
+    __syncthreads();
+    auto split_h = [](float v, __half& hi, __half& lo) {
+      v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+      hi = __float2half_rn(v);
+      lo = __float2half_rn(v - __half2float(hi));
+    };
+    for (int i = threadIdx.x; i < H * (D + 1); i += blockDim.x) {
+      const int h = i / (D + 1), d = i - h * (D + 1);
+      __half hi, lo;
+      __half* dst = hrow0 + (int64_t)h * KROW;
+      if (d < D) {
+        split_h(-kLog2e * src[d * H + h], hi, lo);
+        dst[d] = hi; dst[DW + d] = lo;
+      } else {
+        split_h(kLog2e * src[D * H + H * O + h], hi, lo);
+        if (biasx) { dst[D] = hi; dst[DW + D] = lo; }
+        else { dst[2 * DW] = hi; dst[2 * DW + 1] = lo; }
+      }
+    }
+  } else {
   for (int i = threadIdx.x; i < HP * DW; i += blockDim.x) {
     const int h = i / DW, d = i - h * DW;
     __nv_bfloat16 p[3] = {zero, zero, zero};
@@ -158,6 +198,7 @@ __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* r
       dst[D] = b[0]; dst[DW + D] = b[1]; dst[2 * DW + D] = b[2];
     }
   }
+  }
   for (int i = threadIdx.x; i < ON * KW; i += blockDim.x) {
     const int o = i / KW, h = i - o * KW;
     __nv_bfloat16 p[3] = {zero, zero, zero};
@@ -172,7 +213,7 @@ __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* r
 
 int launch_tc2_pack(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O, int HP, int ON, int CH,
                     int DKC, int KROW, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2, int n_blocks, cudaStream_t st) {
-  tc2_pack_kernel<<<n_blocks, 256, 0, st>>>(theta, ld, rows, n_rows, R, D, H, O, HP, ON, CH, DKC, KROW, 0, b1img, w2img, bias2);
+  tc2_pack_kernel<<<n_blocks, 256, 0, st>>>(theta, ld, rows, n_rows, R, D, H, O, HP, ON, CH, DKC, KROW, 0, 0, b1img, w2img, bias2);   // three bf16 pieces
   SAPT_CHECK_LAUNCH();
   return SAPT_OK;
 }
@@ -317,8 +358,10 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
+      // instruction descriptor (kind::f16): D fp32 (bit 4), A / B format in bits 7-9 / 10-12 (0 = fp16, 1 = bf16), N >> 3, M >> 4
       auto idesc = [](int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24); };
-      const uint32_t idesc1 = idesc(N1), idesc2a = idesc(N2), idesc2b = idesc(2 * ON), idesc2c = idesc(ON);
+      const uint32_t idesc1 = C::XF16 ? ((1u << 4) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24)) : idesc(N1);
+      const uint32_t idesc2a = idesc(N2), idesc2b = idesc(2 * ON), idesc2c = idesc(ON);
       const uint32_t b1_addr = smem_u32(sB1);
       const uint32_t w2_addr = smem_u32(sW2);
       mbar_wait(b_full, 0);
@@ -330,18 +373,18 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA + s * kAStage);
         const uint32_t b_addr = b1_addr + (uint32_t)(uu * N1) * 128;
-        // split product: (piece of x, piece of w) = x1w1 x1w2 x2w1 x1w3 x2w2 x3w1, DKC chunks of 16 features each,
-        // then the bias chunk. chunk c = 16 elements = 32 bytes inside K block c/4.
+        // split product over (piece of x, piece of w): fp16 pieces x_hi w_hi, x_hi w_lo, x_lo w_hi; bf16 pieces x1w1 x1w2 x2w1 x1w3
+        // x2w2 x3w1. DKC chunks of 16 features each, then the bias chunk. chunk c = 16 elements = 32 bytes inside K block c/4.
         constexpr int pa[6] = {0, 0, 1, 0, 1, 2};
         constexpr int pb[6] = {0, 1, 0, 2, 1, 0};
         auto a_at = [&](int chunk) { return umma_desc_sw128(a_addr + (uint32_t)(chunk >> 2) * kABlock + (uint32_t)(chunk & 3) * 32); };
         auto b_at = [&](int chunk) { return umma_desc_sw128(b_addr + (uint32_t)(chunk >> 2) * kB1Block + (uint32_t)(chunk & 3) * 32); };
 #pragma unroll
-        for (int q = 0; q < 6; ++q)
+        for (int q = 0; q < C::NPROD; ++q)
 #pragma unroll
           for (int j = 0; j < DKC; ++j)
             tc_mma_bf16(tmem_base, a_at(pa[q] * DKC + j), b_at(pb[q] * DKC + j), idesc1, (q | j) ? 1u : 0u);
-        if constexpr (!C::BIASX) tc_mma_bf16(tmem_base, a_at(3 * DKC), b_at(3 * DKC), idesc1, 1u);
+        if constexpr (!C::BIASX) tc_mma_bf16(tmem_base, a_at(C::XP * DKC), b_at(C::XP * DKC), idesc1, 1u);
         if (uu == UPT - 1) tc_commit(&empty_a[s]);
         tc_commit(d1_full);
       };
@@ -679,12 +722,16 @@ void tc2_work_model(int D, int H, int O, double* mufu, double* mma_flops) {
   const int DKC = DK & 7;
   const int rcp2 = O / 4 + ((O & 2) ? 1 : 0) + ((O & 1) ? 1 : 0);
   *mufu = (double)HP + HP / 4 + O + rcp2 + O + 1;
-  const int k1 = 16 * (6 * DKC + (DK >= 8 ? 0 : 1));           // MMA-1: six piece products (+ bias chunk) of 16 DKC features
+  const int k1 = 16 * ((SAPT_X_FP16 ? 3 : 6) * DKC + (DK >= 8 ? 0 : 1));   // MMA-1: piece products (+ bias chunk) of 16 DKC features
   const int n2 = (ON == 16) ? (48 + 32) : (64 + 32 + 64);       // MMA-2: output columns summed over the passes h1.[w1|w2(|w3)], h2.[w1|w2]
   *mma_flops = 2.0 * k1 * HP + 2.0 * HP * n2;                   // every pass has K = HP
 }
 
-int tc2_a_row_elems(int D) { return ((48 * tc2_dkc(D) + 16 + 63) / 64) * 64; }
+int tc2_a_row_elems(int D) { return ((48 * tc2_dkc(D) + 16 + 63) / 64) * 64; }          // three-piece bf16 image (batch-Langevin kernel)
+int tc2_a16_row_elems(int D) {                                                            // two-piece fp16 image (this kernel)
+  const int dkc = tc2_dkc(D);
+  return ((32 * dkc + (D < 16 * dkc ? 0 : 16) + 63) / 64) * 64;
+}
 int tc2_piece_width(int D) { return 16 * tc2_dkc(D); }
 
 static int gcd_int2(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
@@ -725,8 +772,8 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   int32_t* partNc = reinterpret_cast<int32_t*>(partL + (size_t)n_chunks * R);
   int32_t* partSq = partNc + (size_t)n_chunks * R;
 
-  tc2_pack_kernel<<<n_groups * CH, 256, 0, st>>>(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, ON, CH, DKC & 7, g.KROW, DKC >= 8 ? 1 : 0, b1img,
-                                                 w2img, bias2);
+  tc2_pack_kernel<<<n_groups * CH, 256, 0, st>>>(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, ON, CH, DKC & 7, g.KROW, DKC >= 8 ? 1 : 0, SAPT_X_FP16,
+                                                 b1img, w2img, bias2);
   SAPT_CHECK_LAUNCH();
   CUtensorMap mb1, mw2;
   rc = tc_make_map_2d(&mb1, b1img, (uint64_t)g.KROW, (uint64_t)n_groups * CH * HP, (uint32_t)(CH * HP));
@@ -737,7 +784,7 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   a.y = ds.y; a.n_pad = ds.n_pad; a.bias2 = bias2; a.n_rows = n_rows; a.R = R; a.O = p->O; a.fold_bias = (p->H < HP) ? 1 : 0;
   a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.partL = partL; a.partNc = partNc; a.partSq = partSq;
   dim3 grid((unsigned)n_chunks, (unsigned)n_groups);
-  const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(ds.tmap);
+  const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(SAPT_X_FP16 ? ds.tmap_f16 : ds.tmap);
   rc = tc2_dispatch(HP, ONX, DKC, [&](auto h, auto o, auto k) { return launch_tc2<h(), o(), k()>(ma, mb1, mw2, a, grid, st); });
   if (rc) return rc;
   return launch_loglik_finalize(partL, partNc, partSq, (int)n_chunks, R, rows, n_rows, L, nc, sq, st);

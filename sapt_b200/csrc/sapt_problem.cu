@@ -123,6 +123,8 @@ extern "C" int sapt_problem_destroy(sapt_problem_t* p) {
     if (p->set[w].y) cudaFree(p->set[w].y);
     if (p->set[w].a_bf16) cudaFree(p->set[w].a_bf16);
     if (p->set[w].tmap) free(p->set[w].tmap);
+    if (p->set[w].a_f16) cudaFree(p->set[w].a_f16);
+    if (p->set[w].tmap_f16) free(p->set[w].tmap_f16);
   }
   if (p->ws) cudaFree(p->ws);
   if (p->h2d_theta) cudaFree(p->h2d_theta);

@@ -7,8 +7,10 @@
 // pairs, so no piece is stored twice.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -25,6 +27,7 @@ constexpr int kKA = 64;  // bf16 per A / B1 row
 bool tc2_supported(int D, int H, int O);   // sapt_loglik_tc2.cu
 int tc2_a_row_elems(int D);
 int tc2_piece_width(int D);
+int tc2_a16_row_elems(int D);
 bool tc_topology_supported(int D, int H, int O) { return tc2_supported(D, H, O); }
 
 // ---- per-step operand packing -----------------------------------------------------------------
@@ -93,7 +96,32 @@ int tc_prepare_dataset(sapt_problem* p, int which, const float* x_host, int64_t 
   SAPT_CUDA(cudaMalloc(&ds.a_bf16, img.size() * 2));
   SAPT_CUDA(cudaMemcpy(ds.a_bf16, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
   ds.tmap = aligned_alloc(64, sizeof(CUtensorMap));
-  return tc_make_map_2d(reinterpret_cast<CUtensorMap*>(ds.tmap), ds.a_bf16, (uint64_t)krow, (uint64_t)ds.n_pad, kTileM);
+  int rc = tc_make_map_2d(reinterpret_cast<CUtensorMap*>(ds.tmap), ds.a_bf16, (uint64_t)krow, (uint64_t)ds.n_pad, kTileM);
+  if (rc) return rc;
+  // the likelihood kernel's image: two fp16 pieces x = x_hi + x_lo (22 significant bits; fp16 subnormals keep the absolute error
+  // of a feature below 2^-25), [x_hi | x_lo | 1 0..]: half the MMA-1 products of the three-piece bf16 image
+  const int krow16 = tc2_a16_row_elems(p->D);
+  std::vector<uint16_t> img16((size_t)ds.n_pad * krow16, 0);
+  const __half h_one = __float2half_rn(1.0f);
+  uint16_t one16; memcpy(&one16, &h_one, 2);
+  for (int64_t i = 0; i < ds.n_pad; ++i) {
+    uint16_t* row = &img16[(size_t)i * krow16];
+    if (i < n) {
+      for (int d = 0; d < p->D; ++d) {
+        float v = x_host[(size_t)i * p->DP + d];
+        v = std::min(65504.0f, std::max(-65504.0f, v));
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        memcpy(&row[d], &hi, 2); memcpy(&row[dw + d], &lo, 2);
+      }
+    }
+    if (p->D < dw) row[p->D] = one16;          // bias rides in the spare x_hi column (TcCfg BIASX)
+    else { row[2 * dw] = one16; row[2 * dw + 1] = one16; }   // else a bias chunk [1 1 0 ..] after the two pieces: it meets [b_hi b_lo 0 ..]
+  }
+  SAPT_CUDA(cudaMalloc(&ds.a_f16, img16.size() * 2));
+  SAPT_CUDA(cudaMemcpy(ds.a_f16, img16.data(), img16.size() * 2, cudaMemcpyHostToDevice));
+  ds.tmap_f16 = aligned_alloc(64, sizeof(CUtensorMap));
+  return tc_make_map_2d(reinterpret_cast<CUtensorMap*>(ds.tmap_f16), ds.a_f16, (uint64_t)krow16, (uint64_t)ds.n_pad, kTileM);
 }
 
 int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld, int R, const int32_t* rows, const int32_t* n_rows,
