@@ -296,7 +296,10 @@ int sapt_lg_first_eval(const sapt_lg_first_args* a, void* stream);
  * Effects: row_of_slot is re-bound (parameter vectors never move); with SAPT_F_TAKE_POST_LIK
  * lik_post[k] takes the received message's value (LG:813-815); swapped[k] = decision of pair k;
  * *num_swap += accepted pairs; src_slot[k] = chain whose message chain k received; for the
- * rank-local rows [row0, row0+R_local) slot_of_row_local is refreshed. */
+ * rank-local rows [row0, row0+R_local) slot_of_row_local is refreshed.
+ * Scratch (O(R_global log R_global) bytes for long ladders) is kept per (device, stream) inside the library, behind a mutex:
+ * concurrent sweeps on different streams / from different host threads do not share it. The first sweep of a given size on a
+ * stream synchronises that stream and allocates, so it must not be issued under CUDA-graph capture; later ones may be. */
 int sapt_swap_sweep(int R_global, double* lik_post, const double* temperature, int32_t* row_of_slot,
                     uint32_t flags, uint32_t seed, int sweep, const double* u_inject,
                     uint8_t* swapped, int32_t* num_swap, int32_t* src_slot,

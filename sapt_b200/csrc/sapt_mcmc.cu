@@ -3,6 +3,10 @@
 // Reference lines are cited per kernel (RV=_revamp.py, RW/LG = the two misc_codeapril2020 forks).
 #include <math.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "sapt_device.cuh"
 #include "sapt_internal.h"
 #include "sapt_mh.cuh"
@@ -472,15 +476,23 @@ extern "C" int sapt_swap_sweep_dev(int R_global, double* lik_post, const double*
                                    int32_t* num_swap, int32_t* src_slot, int row0, int R_local, int32_t* slot_of_row_local,
                                    void* stream) {
   SAPT_REQUIRE(R_global >= 1 && lik_post && temperature && row_of_slot, "sapt_swap_sweep");
-  // scratch: src[R] + old_rows[R] (int32) and post[R] (double), one small buffer per device of this process
-  constexpr int kMaxDev = 64;
-  static int32_t* sc_i_dev[kMaxDev] = {nullptr}; static double* sc_d_dev[kMaxDev] = {nullptr}; static int sc_cap_dev[kMaxDev] = {0};
+  // Scratch: src[R] + old_rows[R] (int32), post[R] (double) and, for the parallel kernel, the range-minimum table, jump lists
+  // and marks. One set per (device, stream) of this process, found under a mutex: sweeps enqueued on one stream are ordered by
+  // the stream, sweeps on different streams (two engines in one process) never share a buffer. A set grows on demand: the call
+  // that grows it synchronises ITS stream and reallocates, so the first sweep of a given size on a stream is not capturable
+  // into a CUDA graph (later ones are) — see sapt.h.
+  struct SweepScratch { int32_t* sc_i = nullptr; double* sc_d = nullptr; int sc_cap = 0;
+                        long long* sp_st = nullptr; int32_t* sp_i = nullptr; uint8_t* sp_m = nullptr; int sp_cap = 0; };
+  static std::mutex mu;
+  static std::map<std::pair<int, void*>, SweepScratch> table;
   int dev = 0;
   SAPT_CUDA(cudaGetDevice(&dev));
-  SAPT_REQUIRE(dev >= 0 && dev < kMaxDev, "device ordinal");
-  int32_t*& sc_i = sc_i_dev[dev]; double*& sc_d = sc_d_dev[dev]; int& sc_cap = sc_cap_dev[dev];
+  std::unique_lock<std::mutex> lock(mu);
+  SweepScratch& sc = table[std::make_pair(dev, stream)];
+  lock.unlock();     // the entry is only ever touched by callers of this (device, stream); std::map never moves it
+  int32_t*& sc_i = sc.sc_i; double*& sc_d = sc.sc_d; int& sc_cap = sc.sc_cap;
   if (R_global > sc_cap) {
-    SAPT_CUDA(cudaDeviceSynchronize());
+    SAPT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     if (sc_i) { SAPT_CUDA(cudaFree(sc_i)); SAPT_CUDA(cudaFree(sc_d)); }
     const int cap = R_global + R_global / 4 + 64;
     SAPT_CUDA(cudaMalloc(&sc_i, sizeof(int32_t) * 2 * cap));
@@ -490,27 +502,25 @@ extern "C" int sapt_swap_sweep_dev(int R_global, double* lik_post, const double*
   // NOTE: old_rows lives at sc_i + R_global (the kernel derives it from scratch_src + R)
   const bool parallel = (flags & SAPT_F_SWEEP_PARALLEL) || R_global >= 4096;
   if (parallel && R_global >= 3) {
-    static long long* sp_st[kMaxDev] = {nullptr}; static int32_t* sp_i[kMaxDev] = {nullptr}; static uint8_t* sp_m[kMaxDev] = {nullptr};
-    static int sp_cap[kMaxDev] = {0};
     int levels = 1;
     while ((1 << levels) <= R_global - 1) ++levels;
-    if (R_global > sp_cap[dev]) {
-      SAPT_CUDA(cudaDeviceSynchronize());
-      if (sp_st[dev]) { SAPT_CUDA(cudaFree(sp_st[dev])); SAPT_CUDA(cudaFree(sp_i[dev])); SAPT_CUDA(cudaFree(sp_m[dev])); }
+    if (R_global > sc.sp_cap) {
+      SAPT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+      if (sc.sp_st) { SAPT_CUDA(cudaFree(sc.sp_st)); SAPT_CUDA(cudaFree(sc.sp_i)); SAPT_CUDA(cudaFree(sc.sp_m)); }
       const int cap = R_global + R_global / 4 + 64;
       int lv = 1;
       while ((1 << lv) <= cap) ++lv;
-      SAPT_CUDA(cudaMalloc(&sp_st[dev], sizeof(long long) * (size_t)(lv + 1) * cap));       // table levels + kp
-      SAPT_CUDA(cudaMalloc(&sp_i[dev], sizeof(int32_t) * (2 * (size_t)(cap + 1) + 4)));      // jump arrays + the literal flag
-      SAPT_CUDA(cudaMalloc(&sp_m[dev], 2 * (size_t)(cap + 1)));
-      SAPT_CUDA(cudaMemset(sp_i[dev], 0, sizeof(int32_t) * (2 * (size_t)(cap + 1) + 4)));
-      sp_cap[dev] = cap;
+      SAPT_CUDA(cudaMalloc(&sc.sp_st, sizeof(long long) * (size_t)(lv + 1) * cap));       // table levels + kp
+      SAPT_CUDA(cudaMalloc(&sc.sp_i, sizeof(int32_t) * (2 * (size_t)(cap + 1) + 4)));      // jump arrays + the literal flag
+      SAPT_CUDA(cudaMalloc(&sc.sp_m, 2 * (size_t)(cap + 1)));
+      SAPT_CUDA(cudaMemsetAsync(sc.sp_i, 0, sizeof(int32_t) * (2 * (size_t)(cap + 1) + 4), (cudaStream_t)stream));
+      sc.sp_cap = cap;
     }
-    long long* kp = sp_st[dev] + (size_t)levels * R_global;
-    int32_t* lit = sp_i[dev];                    // fixed slot; the jump arrays follow it
+    long long* kp = sc.sp_st + (size_t)levels * R_global;
+    int32_t* lit = sc.sp_i;                    // fixed slot; the jump arrays follow it
     swap_sweep_parallel_kernel<<<1, kParThreads, 0, (cudaStream_t)stream>>>(R_global, lik_post, temperature, row_of_slot, flags, seed, sweep,
                                                                             sweep_dev, u_inject, swapped, num_swap, src_slot, row0, R_local,
-                                                                            slot_of_row_local, sc_i, sc_d, sp_st[dev], kp, sp_i[dev] + 4, sp_m[dev], lit);
+                                                                            slot_of_row_local, sc_i, sc_d, sc.sp_st, kp, sc.sp_i + 4, sc.sp_m, lit);
     SAPT_CHECK_LAUNCH();
     if (!u_inject) return SAPT_OK;              // Philox uniforms lie in (0, 1]: the literal formula is never needed
     int32_t h_lit = 0;                          // injected streams (parity tests): u <= 0 is possible, check and redo serially
