@@ -6,6 +6,8 @@
 // theta is staged in shared memory P-chunk by P-chunk, thread j owns hidden unit j and streams
 // column j of W1 (coalesced across j) against the TR staged rows (broadcast LDS), fp32 FMA like
 // Keras. Layers 2 and 3 are tiny and stay in shared memory.
+#include <stdlib.h>
+
 #include "sapt_device.cuh"
 #include "sapt_internal.h"
 
@@ -82,6 +84,12 @@ __global__ void __launch_bounds__(kSurThreads) surrogate_predict_kernel(const fl
 
 }  // namespace sapt
 
+namespace sapt {
+bool surrogate_tc_supported(int P, int h1, int h2);                                                             // sapt_surrogate_tc.cu
+int launch_surrogate_tc(const float* theta, int64_t ld, int R, int P, const int32_t* rows, const int32_t* n_rows, const float* W1, const float* b1,
+                        int h1, const float* W2, const float* b2, int h2, const float* W3, const float* b3, float* s, cudaStream_t stream);
+}
+
 using namespace sapt;
 
 extern "C" int sapt_surrogate_predict(const float* theta, int64_t ld, int R, int P, const int32_t* rows, const int32_t* n_rows,
@@ -89,6 +97,12 @@ extern "C" int sapt_surrogate_predict(const float* theta, int64_t ld, int R, int
                                       const float* W3, const float* b3, float* s, void* stream) {
   SAPT_REQUIRE(theta && W1 && b1 && W2 && b2 && W3 && b3 && s && R >= 0 && P > 0 && h1 > 0 && h2 > 0 && ld >= P, "sapt_surrogate_predict");
   if (R == 0) return SAPT_OK;
+  // From a few hundred chains on, layer 1 is a GEMM worth the tensor cores (sapt_surrogate_tc.cu: tcgen05, fp16 two-piece operands);
+  // below that the CUDA-core kernel needs no operand images. SAPT_SURROGATE_TC=0 / 1 forces one path (A/B measurements, tests).
+  static const int force = [] { const char* e = getenv("SAPT_SURROGATE_TC"); return e ? atoi(e) : -1; }();
+  const bool tc_ok = surrogate_tc_supported(P, h1, h2);
+  if (tc_ok && (force == 1 || (force != 0 && R >= 256)))
+    return launch_surrogate_tc(theta, ld, R, P, rows, n_rows, W1, b1, h1, W2, b2, h2, W3, b3, s, (cudaStream_t)stream);
   const size_t smem = (size_t)(kTR * kPC + kTR * h1 + kTR * h2) * sizeof(float);
   if (smem > 200 * 1024) { set_error("sapt_surrogate_predict: hidden sizes too large"); return SAPT_ERR_UNSUPPORTED; }
   if (smem > 48 * 1024) SAPT_CUDA(cudaFuncSetAttribute(surrogate_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

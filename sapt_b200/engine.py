@@ -739,6 +739,11 @@ class PTEngine:
             g = self._graphs.get(key)
             self.step_dev[0] = i
             if g is None and length >= 4:
+                if ready and self.ls is None:   # library workspaces grow on first use: that must not happen under capture
+                    w = self.surrogate.weights
+                    _lib.check(self.L.sapt_surrogate_predict(_ptr(self.prop), self.ld, self.R, self.P, None, None, _ptr(w["W1"]), _ptr(w["b1"]),
+                                                             self.surrogate.h1, _ptr(w["W2"]), _ptr(w["b2"]), self.surrogate.h2, _ptr(w["W3"]),
+                                                             _ptr(w["b3"]), _ptr(self.sur_s), current_stream_ptr()), "sapt_surrogate_predict")
                 self._graph_mode = True
                 try:
                     g = torch.cuda.CUDAGraph()

@@ -1079,3 +1079,38 @@ def test_train_rows_pack_scatter_kernels(lib, skip_first, zero_row):
     got = batch.cpu().numpy()
     assert np.array_equal(got[: want.shape[0]], want)
     assert np.all(got[want.shape[0]:] == 99.0)
+
+
+@pytest.mark.parametrize("topology_id,P,R", [(3, 643, 1000), (3, 3975, 300), (1, 146, 513), (2, 820, 257)])
+def test_surrogate_predict_tcgen05(lib, topology_id, P, R):
+    """Layer 1 of the surrogate MLP on the tensor cores (sapt_surrogate_tc.cu: fp16 two-piece operands, fp32 accumulation in TMEM,
+    layers 2 / 3 fused in the epilogue), from 256 listed chains on: C5 (P = 643, topology 3), C4-size P, ragged row lists.
+    Oracle = the fp32 Keras-style forward restated from RV:217-233 (Keras itself is not installed: unpinned)."""
+    L = lib.lib()
+    w = so.make_surrogate_weights(P, topology_id, 5, scale=0.08)
+    rs = np.random.RandomState(4)
+    theta = (rs.randn(R, P) * 0.7).astype(np.float32)
+    ld = P + 3
+    th = torch.zeros((R, ld), dtype=torch.float32).cuda(); th[:, :P] = torch.as_tensor(theta).cuda()
+    wd = {k: torch.as_tensor(v.reshape(-1).copy()).cuda() for k, v in w.items()}
+    h1, h2 = so.SURROGATE_HIDDEN[topology_id]
+    n_list = R - 7
+    rows_np = np.sort(rs.choice(R, n_list, replace=False)).astype(np.int32)
+    rows = torch.zeros(R, dtype=torch.int32).cuda(); rows[:n_list] = torch.as_tensor(rows_np).cuda()
+    n_rows = torch.tensor([n_list], dtype=torch.int32).cuda()
+    s = torch.full((R,), -1.0, dtype=torch.float32).cuda()
+    lib.check(L.sapt_surrogate_predict(th.data_ptr(), ld, R, P, rows.data_ptr(), n_rows.data_ptr(), wd["W1"].data_ptr(), wd["b1"].data_ptr(), h1,
+                                       wd["W2"].data_ptr(), wd["b2"].data_ptr(), h2, wd["W3"].data_ptr(), wd["b3"].data_ptr(), s.data_ptr(), None))
+    torch.cuda.synchronize()
+    got = s.cpu().numpy()
+    ref64 = 1.0 / (1.0 + np.exp(-(np.maximum(np.maximum(theta.astype(np.float64) @ w["W1"] + w["b1"], 0) @ w["W2"] + w["b2"], 0) @ w["W3"] + w["b3"]))).reshape(-1)
+    ref32 = so.surrogate_forward(theta, w)
+    np.testing.assert_allclose(got[rows_np], ref64[rows_np], rtol=2e-5, atol=1e-6)      # vs exact arithmetic
+    np.testing.assert_allclose(got[rows_np], ref32[rows_np], rtol=3e-5, atol=2e-6)      # vs the fp32 restatement (its own rounding included)
+    assert np.all(got[np.setdiff1d(np.arange(R), rows_np)] == -1.0)
+    assert 0.02 < got[rows_np].std()                                                      # the outputs are not saturated: the check means something
+    # all rows, no list
+    s2 = torch.full((R,), -1.0, dtype=torch.float32).cuda()
+    lib.check(L.sapt_surrogate_predict(th.data_ptr(), ld, R, P, None, None, wd["W1"].data_ptr(), wd["b1"].data_ptr(), h1, wd["W2"].data_ptr(),
+                                       wd["b2"].data_ptr(), h2, wd["W3"].data_ptr(), wd["b3"].data_ptr(), s2.data_ptr(), None))
+    np.testing.assert_allclose(s2.cpu().numpy(), ref64, rtol=2e-5, atol=1e-6)
