@@ -8,5 +8,5 @@ for pat in 'loglik_tc2_kernelILi32ELi16ELi1E' 'loglik_tc2_kernelILi64ELi8ELi12E'
   fn=$(cuobjdump -sass $LIB 2>/dev/null | grep -o "Function : [^ ]*${pat}[^ ]*" | head -1 | sed 's/Function : //')
   [ -z "$fn" ] && continue
   echo; echo "== $fn"
-  cuobjdump -sass -fun "$fn" $LIB 2>/dev/null | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed 's/^ *\/\*[0-9a-f]*\*\/ *//' | sed 's/^@!*U*P[0-9T] *//' | awk '{print $1}' | sed 's/;$//' | sed -E 's/^(UTC[A-Z]*MMA|LDTM|STTM|UTMALDG|UTCBAR|MUFU\.[A-Z0-9]+|SYNCS)\..*/\1/; s/^([A-Z0-9]+)\..*/\1/' | sort | uniq -c | sort -rn | awk '{printf "%6d %s\n", $1, $2}'
+  cuobjdump -sass -fun "$fn" $LIB 2>/dev/null | grep -E "^\s+/\*[0-9a-f]{4,6}\*/" | sed 's/^ *\/\*[0-9a-f]*\*\/ *//' | sed 's/^@!*U*P[0-9T] *//' | awk '{print $1}' | sed 's/;$//' | sed -E 's/^(UTC[A-Z]*MMA|LDTM|STTM|UTMALDG|UTCBAR|MUFU\.[A-Z0-9]+|SYNCS)\..*/\1/; s/^([A-Z0-9]+)\..*/\1/' | sort | uniq -c | sort -rn | awk '{printf "%6d %s\n", $1, $2}'
 done
