@@ -246,6 +246,9 @@ __device__ __forceinline__ void sigmoid4_lim(float t0, float t1, float t2, float
 #ifndef SAPT_F32X2
 #define SAPT_F32X2 1      // packed fp32 pairs (FADD2 / FMUL2) in the epilogue arithmetic
 #endif
+#ifndef SAPT_CONST_O
+#define SAPT_CONST_O 1    // compile-time output count for the BASELINE shapes (see loglik_tc2_kernel)
+#endif
 #ifndef SAPT_P1_CHAIN
 #define SAPT_P1_CHAIN 2   // quads per ordered group in phase 1 (0: let ptxas schedule freely)
 #endif
@@ -263,7 +266,9 @@ __device__ __forceinline__ void sigmoid4_scaled(float t0, float t1, float t2, fl
   s0 = rab * a1; s1 = rab * a0; s2 = rcd * a3; s3 = rcd * a2;
 }
 
-template <int HP, int ONX, int DK>
+// OC: the number of outputs as a compile-time constant (0 = read it from the parameters). With a constant O the output phase has
+// no branches and ptxas schedules all its sigmoid groups together; instantiated for the topologies of the BASELINE configs.
+template <int HP, int ONX, int DK, int OC = 0>
 __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b1,
                                                                      const __grid_constant__ CUtensorMap map_w2, Tc2Params p) {
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
     const int quarter = warp & 3;
     const int e = warp >> 2;
     const int c = e / HALVES, hf = e % HALVES;
-    const int O = p.O;
+    const int O = OC ? OC : p.O;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     double accL[UPT];
     int accNc[UPT], accSq[UPT];
@@ -654,7 +659,7 @@ static Tc2Geom geom_of() {
   return Tc2Geom{C::CH, C::KBA * 64, C::kW2Box, C::UPT, (size_t)C::smem_bytes(C::UPT > 0 ? C::UPT : 1)};
 }
 
-template <int HP, int ON, int DKC>
+template <int HP, int ON, int DKC, int OC = 0>
 static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb1, const CUtensorMap& mw2, const Tc2Params& a, dim3 grid, cudaStream_t st) {
   using C = TcCfg<HP, ON, DKC>;
   if constexpr (C::UPT < 1) {
@@ -662,7 +667,7 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb1, const CUten
     return SAPT_ERR_UNSUPPORTED;
   } else {
     const size_t smem = C::smem_bytes(C::UPT);
-    auto k = loglik_tc2_kernel<HP, ON, DKC>;
+    auto k = loglik_tc2_kernel<HP, ON, DKC, OC>;
     SAPT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, v2::kThreads, smem, st>>>(ma, mb1, mw2, a);
     SAPT_CHECK_LAUNCH();
@@ -785,6 +790,14 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.partL = partL; a.partNc = partNc; a.partSq = partSq;
   dim3 grid((unsigned)n_chunks, (unsigned)n_groups);
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(SAPT_X_FP16 ? ds.tmap_f16 : ds.tmap);
+#if SAPT_CONST_O
+  // output count known at compile time for the shapes of the BASELINE configs (C3 16-30-10, C4 54-64-7, C5 6-25-18, C2 34-50-2)
+  if (HP == 32 && ONX == 16 && DKC == 1 && p->O == 10) rc = launch_tc2<32, 16, 1, 10>(ma, mb1, mw2, a, grid, st);
+  else if (HP == 64 && ONX == 8 && DKC == 12 && p->O == 7) rc = launch_tc2<64, 8, 12, 7>(ma, mb1, mw2, a, grid, st);
+  else if (HP == 32 && ONX == 32 && DKC == 9 && p->O == 18) rc = launch_tc2<32, 32, 9, 18>(ma, mb1, mw2, a, grid, st);
+  else if (HP == 64 && ONX == 8 && DKC == 11 && p->O == 2) rc = launch_tc2<64, 8, 11, 2>(ma, mb1, mw2, a, grid, st);
+  else
+#endif
   rc = tc2_dispatch(HP, ONX, DKC, [&](auto h, auto o, auto k) { return launch_tc2<h(), o(), k()>(ma, mb1, mw2, a, grid, st); });
   if (rc) return rc;
   return launch_loglik_finalize(partL, partNc, partSq, (int)n_chunks, R, rows, n_rows, L, nc, sq, st);
