@@ -19,8 +19,8 @@
 // and as MN-major operands (gradients: K = rows): only the descriptor changes.
 // B1 gradient: a column of ones in the X image (the bias chunk, or for D > 32 the first spare column of the x1
 // piece) makes -sum(dh) a row of G1. B2 gradient: per-thread sums of do, reduced at the end of the chain.
-// fp32-grade accuracy from bf16 operands as in sapt_loglik_tc2.cu: x = x1 + x2 (+ x3 dropped: 2^-17), w = w1 + w2 + w3,
-// h, do, dh = two pieces each; the cross terms kept are listed at each MMA.
+// Operands are bf16 pieces as in round 1 of sapt_loglik_tc2.cu: x = x1 + x2 (+ x3 dropped: 2^-17), w = w1 + w2 (+ w3 in the
+// output layer), h, do, dh = two pieces each; the cross terms kept are listed at each MMA (gradient accuracy: 2e-6 max|g|).
 //
 // Work item = (chain, row chunk); one CTA per SM takes items round-robin, one after the other (the accumulators are per item).
 // Warp 16 lane 0: TMA producer (X tile ring; per-chain weight panels). Warp 17: TMEM alloc + MMA issue. Warps 0-15:
@@ -265,16 +265,21 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
         if (c > 0) mbar_wait(g_free, (c - 1) & 1);     // accumulators of the previous item have been read out
         for (int q = 0; q < n_pairs; ++q) {
           const int nb = (2 * q + 1 < n_tiles) ? 2 : 1;
-          // ---- MMA-1: x1w1 x1w2 x2w1 x1w3 x2w2 + bias. x chunks: x1 = [0, DKC), x2 = [DKC, 2 DKC) ----
+          // ---- MMA-1: x1w1 x1w2 x2w1 + bias. x chunks: x1 = [0, DKC), x2 = [DKC, 2 DKC) ----
           for (int b = 0; b < nb; ++b) {
             const uint32_t xa = smem_u32(sA + b * C::kAStage), tD = tmem_base + C::kDS + b * 64;
             mbar_wait(&full_a[b], use[b] & 1);
             ++use[b];
             tc_fence_after();
+            // Three piece products x1w1 x1w2 x2w1: the dropped x1w3 / x2w2 terms are 2^-16 |x w|, i.e. ~1e-4 absolute on a
+            // pre-activation, zero-mean over rows — far inside the 1e-4 (relative to max |g|) the gradient needs, and 9 of 21
+            // MMA-1 instructions less per tile at D = 54. (The likelihood kernel keeps fp32-grade products: an MH decision
+            // hangs on a difference of sums over all rows.)
+            constexpr int kProd = 3;
             constexpr int pa[5] = {0, 0, 1, 0, 1};
             constexpr int pb[5] = {0, 1, 0, 2, 1};
 #pragma unroll
-            for (int k = 0; k < 5; ++k)
+            for (int k = 0; k < kProd; ++k)
 #pragma unroll
               for (int j = 0; j < DKC; ++j)
                 tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, pa[k] * DKC + j)), umma_desc_sw128(b1_chunk(pb[k] * DKC + j)), id1, (k | j) ? 1u : 0u);
