@@ -56,6 +56,7 @@ struct DataSet {
   // likelihood kernel's operand image: [n_pad][64 KBA] fp16 = [x_hi | x_lo | (1 1 0..)] (two fp16 pieces, see sapt_loglik_tc2.cu)
   void* a_f16 = nullptr;
   void* tmap_f16 = nullptr;
+  bool f16_range_ok = true;  // every |feature| <= 6e4: representable by the fp16 pieces (else the tcgen05 likelihood path is refused for this set)
 };
 
 }  // namespace sapt

@@ -745,6 +745,10 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
                       double* L, int32_t* nc, double* sq, cudaStream_t st) {
   const DataSet& ds = p->set[which];
   if (R <= 0 || ds.n <= 0) return SAPT_OK;
+  if (SAPT_X_FP16 && !ds.f16_range_ok) {
+    set_error("tcgen05 path: this data set has features beyond the fp16 operand range (|x| > 6e4); use SAPT_PATH_F32 / SAPT_PATH_AUTO");
+    return SAPT_ERR_UNSUPPORTED;
+  }
   int HP, ON, DKC; tc2_shape(p, HP, ON, DKC);
   if (ON > HP) { set_error("tcgen05 path: O=%d needs H > 16", p->O); return SAPT_ERR_UNSUPPORTED; }
   Tc2Geom g{};

@@ -145,7 +145,7 @@ namespace sapt { void tc2_work_model(int D, int H, int O, double* mufu, double* 
 extern "C" int sapt_loglik_work_model(const sapt_problem_t* p, int path, double* out, int n_out) {
   SAPT_REQUIRE(p && out && n_out >= SAPT_WORK_COUNT, "problem / out[SAPT_WORK_COUNT]");
   if (path == SAPT_PATH_TC && !p->tc_ok) { set_error("tcgen05 path unavailable for topology %d-%d-%d", p->D, p->H, p->O); return SAPT_ERR_UNSUPPORTED; }
-  const bool tc = (path == SAPT_PATH_TC) || (path == SAPT_PATH_AUTO && p->tc_ok && p->D * p->H + p->H * p->O >= 220);
+  const bool tc = (path == SAPT_PATH_TC) || (path == SAPT_PATH_AUTO && p->tc_ok && p->set[0].f16_range_ok && p->D * p->H + p->H * p->O >= 220);
   const int D = p->D, H = p->H, O = p->O;
   out[SAPT_WORK_PATH] = tc ? SAPT_PATH_TC : SAPT_PATH_F32;
   out[SAPT_WORK_FLOPS_ALGORITHMIC] = 2.0 * D * H + 2.0 * H * O;
@@ -170,7 +170,7 @@ extern "C" int sapt_loglik(sapt_problem_t* p, int which, const float* theta, int
   if (path == SAPT_PATH_TC && !p->tc_ok) { set_error("tcgen05 path unavailable for topology %d-%d-%d on this device", p->D, p->H, p->O); return SAPT_ERR_UNSUPPORTED; }
   // AUTO: below ~220 multiply-adds per evaluation (9-12-2, 8-16-4 ...) the fp32 tiles win (measured crossover:
   // 8-16-4 fp32 +10 %, 12-16-2 tcgen05 +16 %), above it the tensor-core path is 1.1x-4x faster.
-  const bool tc = (path == SAPT_PATH_TC) || (path == SAPT_PATH_AUTO && p->tc_ok && p->D * p->H + p->H * p->O >= 220);
+  const bool tc = (path == SAPT_PATH_TC) || (path == SAPT_PATH_AUTO && p->tc_ok && p->set[which].f16_range_ok && p->D * p->H + p->H * p->O >= 220);
   if (tc) return launch_loglik_tc(p, which, theta, ld_theta, R, rows, n_rows, L, ncorrect, sqerr, (cudaStream_t)stream);
   return launch_loglik_f32(p, which, theta, ld_theta, R, rows, n_rows, L, ncorrect, sqerr, (cudaStream_t)stream);
 }

@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -101,6 +102,11 @@ int tc_prepare_dataset(sapt_problem* p, int which, const float* x_host, int64_t 
   // the likelihood kernel's image: two fp16 pieces x = x_hi + x_lo (22 significant bits; fp16 subnormals keep the absolute error
   // of a feature below 2^-25), [x_hi | x_lo | 1 0..]: half the MMA-1 products of the three-piece bf16 image
   const int krow16 = tc2_a16_row_elems(p->D);
+  float amax = 0.f;
+  for (int64_t i = 0; i < n; ++i)
+    for (int d = 0; d < p->D; ++d) amax = std::max(amax, fabsf(x_host[(size_t)i * p->DP + d]));
+  ds.f16_range_ok = (amax <= 6.0e4f);     // un-normalised features beyond fp16's range: the fp32 tiles serve this data set
+  if (!ds.f16_range_ok) return SAPT_OK;
   std::vector<uint16_t> img16((size_t)ds.n_pad * krow16, 0);
   const __half h_one = __float2half_rn(1.0f);
   uint16_t one16; memcpy(&one16, &h_one, 2);
