@@ -1114,3 +1114,20 @@ def test_surrogate_predict_tcgen05(lib, topology_id, P, R):
     lib.check(L.sapt_surrogate_predict(th.data_ptr(), ld, R, P, None, None, wd["W1"].data_ptr(), wd["b1"].data_ptr(), h1, wd["W2"].data_ptr(),
                                        wd["b2"].data_ptr(), h2, wd["W3"].data_ptr(), wd["b3"].data_ptr(), s2.data_ptr(), None))
     np.testing.assert_allclose(s2.cpu().numpy(), ref64, rtol=2e-5, atol=1e-6)
+
+
+def test_features_beyond_fp16_range_take_the_fp32_path(lib):
+    """The tcgen05 likelihood kernel holds the features as two fp16 pieces: a data set with |x| > 6e4 (un-normalised inputs) is
+    served by the fp32 tiles under SAPT_PATH_AUTO and refused — not silently saturated — under SAPT_PATH_TC."""
+    from sapt_b200.problem import Problem
+    topo = [16, 30, 10]
+    data = _synthetic(16, 10, 500, 3)
+    data[7, 3] = 1.0e5
+    pr = Problem(topo, data, None)
+    W = (np.random.RandomState(2).standard_normal((3, so.num_param(topo))) * 0.01).astype(np.float32)
+    th = torch.as_tensor(W).cuda()
+    L = pr.loglik(th, 0, path=lib.PATH_AUTO)[0].cpu().numpy()
+    ref = [so.loglik_stats(data, W[k].astype(np.float64), topo)[0] for k in range(3)]
+    np.testing.assert_allclose(L, ref, rtol=3e-6)
+    with pytest.raises(NotImplementedError):
+        pr.loglik(th, 0, path=lib.PATH_TC)
