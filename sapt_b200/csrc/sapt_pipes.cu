@@ -17,7 +17,15 @@ constexpr int kInner = 64;
 
 enum PipeOp { OP_EX2 = 0, OP_RCP = 1, OP_FFMA = 2, OP_FMUL = 3, OP_FFMA2 = 4, OP_LOP3 = 5, OP_MIX = 6, OP_F2FP = 7, OP_COUNT = 8 };
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int OP>
+// cycles[0] = SM cycles, cycles[1] = nanoseconds (%globaltimer) block 0 spent in the loop: their ratio is the SM clock whatever
+// the residency (the event time covers the whole grid, possibly several waves)
 __global__ void __launch_bounds__(1024, 2) pipe_kernel(float* out, long long* cycles, int iters, float a, float b) {
   float v[kChains];
   unsigned long long w[kChains / 2];
@@ -33,6 +41,7 @@ __global__ void __launch_bounds__(1024, 2) pipe_kernel(float* out, long long* cy
   unsigned long long ab, bb;
   asm("mov.b64 %0, {%1, %1};" : "=l"(ab) : "f"(a));
   asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  const unsigned long long g0 = global_timer_ns();
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -62,13 +71,14 @@ __global__ void __launch_bounds__(1024, 2) pipe_kernel(float* out, long long* cy
     }
   }
   const long long t1 = clock64();
+  const unsigned long long g1 = global_timer_ns();
   float s = 0.f;
 #pragma unroll
   for (int c = 0; c < kChains; ++c) s += v[c] + __uint_as_float(q[c] & 0x3fffffu);
 #pragma unroll
   for (int c = 0; c < kChains / 2; ++c) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(w[c])); s += lo + hi; }
   if (s == 123.456f) out[0] = s;   // keeps the chains alive, practically never true
-  if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+  if (threadIdx.x == 0 && blockIdx.x == 0) { cycles[0] = t1 - t0; cycles[1] = (long long)(g1 - g0); }
 }
 
 template <int OP>
@@ -86,12 +96,12 @@ int run_pipe(int num_sms, int iters, float* d_out, long long* d_cyc, cudaStream_
   SAPT_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;
   SAPT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  long long cyc = 0;
-  SAPT_CUDA(cudaMemcpy(&cyc, d_cyc, sizeof(cyc), cudaMemcpyDeviceToHost));
+  long long cyc[2] = {0, 1};
+  SAPT_CUDA(cudaMemcpy(cyc, d_cyc, sizeof(cyc), cudaMemcpyDeviceToHost));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   const double per_thread = (double)iters * kInner * ((OP == OP_FFMA2) ? kChains / 2 : kChains);
   *ops_per_s = per_thread * 1024.0 * grid / (ms * 1e-3);   // warp-lane operations (an f32x2 instruction counts once)
-  *sm_hz = (double)cyc / (ms * 1e-3);                       // the loop is ~all of the kernel
+  *sm_hz = (double)cyc[0] / ((double)cyc[1] * 1e-9);        // SM cycles per second of block 0's loop (clock64 over %globaltimer)
   return SAPT_OK;
 }
 }  // namespace

@@ -1016,7 +1016,7 @@ def _assert_posterior_parity(res, ora, S, burn, name, mean_tol=1.0, std_factor=1
 def test_posterior_parity_same_seed_c1(lib):
     """BASELINE configs[0] (C1): Wisconsin breast-cancer 9-12-2, 8 replicas, random-walk PT, no surrogate — the device
     engine (both the fused n-steps-per-launch kernel and the step-by-step kernels) against the oracle on the same
-    random numbers. Sanity envelope of the reference's committed run: 95.6 +- 0.6 / 98.8 +- 0.5 (master_result_file.txt:5)."""
+    random numbers (test_c1_posterior_accuracy_envelope checks a long run against the reference's committed 95.6 / 98.8 %)."""
     g = gu.load("unit_cancer")
     topo = [int(v) for v in g["topology"]]
     for fused in (True, False):
@@ -1024,8 +1024,7 @@ def test_posterior_parity_same_seed_c1(lib):
         res, ora = _same_seed_pair(lib, "rw", topo, g["train"], g["test"], R=8, S=S, maxtemp=2.0, swap_interval=5, surrogate_interval=5,
                                    surrogate_prob=0.0, use_surrogate=False, use_langevin=False, learn_rate=0.01, surrogate_topology=1, seed=11,
                                    fused=fused)
-        a, b = _assert_posterior_parity(res, ora, S, 0.5, f"C1 fused={fused}")
-        assert a["acc_train"][0] > 90.0 and a["acc_test"][0] > 94.0
+        _assert_posterior_parity(res, ora, S, 0.5, f"C1 fused={fused}")
 
 
 def test_posterior_parity_same_seed_c2(lib):
