@@ -12,8 +12,6 @@ build() { name=$1; shift
   nvcc $FLAGS "$@" -c sapt_loglik_tc2.cu -o ../variants/tc2_$name.o
   nvcc $ARCH -shared -o ../variants/libsapt_$name.so $OTHERS ../variants/tc2_$name.o -lcuda
   echo built $name; }
-build r1   -DSAPT_F32X2=0 -DSAPT_X_FP16=0 -DSAPT_CONST_O=0 &
-build f2   -DSAPT_F32X2=1 -DSAPT_X_FP16=0 -DSAPT_CONST_O=0 &
-build x16  -DSAPT_F32X2=0 -DSAPT_X_FP16=1 -DSAPT_CONST_O=0 &
-build nco  -DSAPT_F32X2=1 -DSAPT_X_FP16=1 -DSAPT_CONST_O=0 &
+build r1   -DSAPT_F32X2=0 -DSAPT_X_FP16=0 -DSAPT_CONST_O=0 -DSAPT_HS_SMEM=0 &
+build nohs -DSAPT_HS_SMEM=0 &
 wait
