@@ -116,15 +116,15 @@ __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n
 // writes n bf16 values (n = 4, 8 or 16; packed pairs, N/2 words) of one data row into a swizzled [128 rows][64 bf16] block at column col0
 template <int N>
 __device__ __forceinline__ void store_row_packed(uint8_t* block, int row, int col0, const uint32_t (&w)[N / 2]) {
-  uint8_t* rowp = block + row * 128;
+  const uint32_t rowp = smem_u32(block) + (uint32_t)row * 128;
   if constexpr (N == 4) {
     const int chunk = col0 >> 3;
-    *reinterpret_cast<uint2*>(rowp + (((chunk ^ (row & 7)) << 4) | ((col0 & 7) * 2))) = make_uint2(w[0], w[1]);
+    st_shared_v2(rowp + (uint32_t)(((chunk ^ (row & 7)) << 4) | ((col0 & 7) * 2)), w[0], w[1]);
   } else {
 #pragma unroll
     for (int c = 0; c < N / 8; ++c) {
       const int chunk = (col0 >> 3) + c;
-      *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      st_shared_v4(rowp + (uint32_t)((chunk ^ (row & 7)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
     }
   }
 }

@@ -528,13 +528,13 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
         // this warp's 32 hidden units of data row (quarter, lane): 64 B of the h1 block and 64 B of the h2 block of chain c,
         // as four 16-byte chunks each, XOR-swizzled with the row like the TMA-written operand tiles
         const int row = quarter * 32 + lane;
-        uint8_t* b1p = sHs + (uint32_t)c * (2 * kABlock) + row * 128;
-        uint8_t* b2p = b1p + kABlock;
+        const uint32_t b1p = smem_u32(sHs) + (uint32_t)c * (2 * kABlock) + (uint32_t)row * 128;
+        const uint32_t b2p = b1p + kABlock;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (hf * 4 + q4) ^ (row & 7);
-          *reinterpret_cast<uint4*>(b1p + chunk * 16) = make_uint4(hv[4 * q4], hv[4 * q4 + 1], hv[4 * q4 + 2], hv[4 * q4 + 3]);
-          *reinterpret_cast<uint4*>(b2p + chunk * 16) = make_uint4(hv[16 + 4 * q4], hv[16 + 4 * q4 + 1], hv[16 + 4 * q4 + 2], hv[16 + 4 * q4 + 3]);
+          const uint32_t chunk = (uint32_t)((hf * 4 + q4) ^ (row & 7));
+          st_shared_v4(b1p + chunk * 16, hv[4 * q4], hv[4 * q4 + 1], hv[4 * q4 + 2], hv[4 * q4 + 3]);
+          st_shared_v4(b2p + chunk * 16, hv[16 + 4 * q4], hv[16 + 4 * q4 + 1], hv[16 + 4 * q4 + 2], hv[16 + 4 * q4 + 3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async proxy
       } else if constexpr (HALVES == 1) {
