@@ -1,6 +1,7 @@
 #!/bin/bash
 # The job of the next GPU call (edited between calls; `devtools/gpu.sh <log> <timeout> -- 'bash devtools/gpu_job.sh'`).
 mkdir -p gpurun_out
+sha256sum sapt_b200/csrc/sapt_loglik_tc2.cu sapt_b200/csrc/sapt_langevin_tc.cu sapt_b200/libsapt.so > gpurun_out/j2_src_sha.txt
 python devtools/pipes.py gpurun_out/r2_pipes.json > /dev/null 2> gpurun_out/j2_pipes.err
 timeout 1800 python -m pytest tests -m gpu -q 2>&1 | tail -60 > gpurun_out/j2_pytest.txt
 for v in "" nohs r1; do
