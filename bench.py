@@ -438,7 +438,8 @@ def run_ours(args):
         del prob
         torch.cuda.empty_cache()
         sec = {}
-        for name, fn in (("C4", secondary_c4), ("C5", secondary_c5)):
+        legs = (("C4", secondary_c4), ("C5", secondary_c5)) + ((("C2", secondary_c2),) if world == 1 else ())
+        for name, fn in legs:
             try:
                 sec[name] = fn(rank, world, local, flush, pipes, n_sm, sm_mhz, peaks)
             except Exception as ex:   # noqa: BLE001
@@ -449,6 +450,29 @@ def run_ours(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_c2(rank, world, local, flush, pipes, n_sm, sm_mhz, peaks):
+    """BASELINE configs[1]: Ionosphere-shape 34-50-2 (245 train / 109 test rows), 10 replicas, Langevin-gradient PT with the
+    reference's exact per-row SGD epoch (LG:138-156), surrogate interval enabled, the PyTorch surrogate trainer in the loop —
+    through the reference-facing class (ParallelTempering). Latency-bound (microseconds of work per step): steps/s, no roofline."""
+    import torch
+    from sapt_b200.parallel_tempering import ParallelTempering
+    D, H, O, R, S = 34, 50, 2, 10, 300
+    rs = np.random.RandomState(7)
+    mk = lambda n: np.concatenate([rs.standard_normal((n, D)), rs.randint(0, O, n)[:, None].astype(np.float64)], axis=1)
+    tr, te = mk(245), mk(109)
+    out = {}
+    for label, use_sur, samples in (("warm-up (untimed)", True, 120), ("surrogate_off", False, S), ("surrogate_on", True, S)):
+        pt = ParallelTempering(use_sur, True, 0.01, False, tr, te, [D, H, O], R, 4.0, R * samples, 100000, 50, 0.5, "", "", 1, variant="lg", seed=3)
+        pt.initialize_chains(0.25)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        pt.run_chains()
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        if not label.startswith("warm"):
+            out[label] = dict(wall_s=dt, steps_per_s=(samples - 1) / dt, samples_per_s=R * (samples - 1) / dt)
+    return dict(workload="C2 Ionosphere-shape 34-50-2 synthetic (245 + 109 rows), 10 chains, exact-SGD Langevin p=0.5, surrogate interval 50 / prob 0.5, torch trainer",
+                chains=R, samples_per_chain=S, api="ParallelTempering.run_chains (wall clock, host loop included)", **out)
 
 
 def secondary_c4(rank, world, local, flush, pipes, n_sm, sm_mhz, peaks):
