@@ -12,6 +12,7 @@ SAPT_SURROGATE_TC=0 python devtools/prof_kernels.py c5sp 32768 > gpurun_out/j2_s
 SAPT_SURROGATE_TC=1 python devtools/prof_kernels.py c5sp 32768 >> gpurun_out/j2_sp.txt 2>&1
 SAPT_SURROGATE_TC=0 python devtools/prof_kernels.py c5sp 4096 >> gpurun_out/j2_sp.txt 2>&1
 SAPT_SURROGATE_TC=1 python devtools/prof_kernels.py c5sp 4096 >> gpurun_out/j2_sp.txt 2>&1
+timeout 120 devtools/mma_cost > gpurun_out/j2_mma_cost.txt 2>&1
 NCU="ncu --set full --clock-control none --import-source on"
 python devtools/prof_kernels.py c4lt 64 > gpurun_out/j2_plain_lt.log 2>&1 && \
   $NCU -k regex:langevin_tc_kernel -s 1 -c 1 -f -o gpurun_out/r2_langevin_prof python devtools/prof_kernels.py c4lt 64 > gpurun_out/j2_ncu_lt.log 2>&1
@@ -19,4 +20,4 @@ python devtools/prof_kernels.py c3 > gpurun_out/j2_plain_c3.log 2>&1 && \
   $NCU -k regex:loglik_tc2_kernel -s 1 -c 1 -f -o gpurun_out/r2_c3_prof python devtools/prof_kernels.py c3 > gpurun_out/j2_ncu_c3.log 2>&1
 python devtools/prof_kernels.py c4ll > gpurun_out/j2_plain_c4.log 2>&1 && \
   $NCU -k regex:loglik_tc2_kernel -s 1 -c 1 -f -o gpurun_out/r2_c4_prof python devtools/prof_kernels.py c4ll > gpurun_out/j2_ncu_c4.log 2>&1
-tail -c 2500 gpurun_out/j2_pytest.txt; cat gpurun_out/j2_ab.jsonl; cat gpurun_out/j2_sp.txt; ls -la gpurun_out/*.ncu-rep | tail -4
+tail -c 2500 gpurun_out/j2_pytest.txt; cat gpurun_out/j2_ab.jsonl; cat gpurun_out/j2_sp.txt; cat gpurun_out/j2_mma_cost.txt; ls -la gpurun_out/*.ncu-rep | tail -4
