@@ -22,10 +22,10 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo_byt
   return d;
 }
 
-constexpr int kBatch = 16, kRep = 200;
+constexpr int kRep = 100;
 
 // form: 0 = K-major SS bf16, 1 = K-major SS fp16, 2 = TS (A in TMEM), 3 = MN-major SS
-__global__ void __launch_bounds__(128) cost_kernel(int form, int N, long long* out) {
+__global__ void __launch_bounds__(128) cost_kernel(int form, int N, int kBatch, long long* out) {
   extern __shared__ __align__(1024) uint8_t raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -78,12 +78,18 @@ int main() {
       const int N = Ns[ni];
       if (form == 2 && N > 64) continue;
       if (form == 3 && N != 64 && N != 128) continue;
-      cost_kernel<<<148, 128, smem>>>(form, N, d);
-      cudaError_t e = cudaDeviceSynchronize();
-      long long h[2] = {0, 0};
-      cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-      printf("%-16s M=128 N=%3d K=16: %6.1f cycles per MMA (best batch), %6.1f (mean), batch of %d + commit + wait; %s\n", names[form], N,
-             (double)h[0] / kBatch, (double)h[1] / kBatch, kBatch, cudaGetErrorString(e));
+      long long t[2] = {0, 0};
+      cudaError_t e = cudaSuccess;
+      for (int bi = 0; bi < 2; ++bi) {     // two batch sizes: the difference removes the commit / mbarrier / wake-up overhead
+        cost_kernel<<<148, 128, smem>>>(form, N, bi ? 64 : 16, d);
+        e = cudaDeviceSynchronize();
+        long long h[2] = {0, 0};
+        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        t[bi] = h[0];
+        if (e != cudaSuccess) break;
+      }
+      printf("%-16s M=128 N=%3d K=16: %6.1f cycles per MMA (incremental: (T64 - T16) / 48), fixed overhead per batch %6.0f; T16 %lld T64 %lld; %s\n", names[form], N,
+             (double)(t[1] - t[0]) / 48.0, (double)t[0] - 16.0 * (double)(t[1] - t[0]) / 48.0, t[0], t[1], cudaGetErrorString(e));
       if (e != cudaSuccess) return 1;
     }
   return 0;

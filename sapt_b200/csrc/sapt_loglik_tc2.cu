@@ -51,14 +51,6 @@
 #define SAPT_X_FP16 1
 #endif
 
-// HP = 64: the hidden activations go to MMA-2 through SHARED memory (SS form) instead of tensor memory (TS form). An MMA whose A
-// operand sits in TMEM costs ~64-73 cycles whatever its N (the operand is read at ~64 B per clock), 8 of them per chain and tile
-// at HP = 64 — more tensor-pipe time than the first layer. From shared memory the same K step costs max(smem read 32, math 16-24)
-// cycles. The 32 KB per chain fit because the fp16 first-layer operands shrank the A ring. 0: round-1 TS form everywhere.
-#ifndef SAPT_HS_SMEM
-#define SAPT_HS_SMEM 1
-#endif
-
 namespace sapt {
 
 namespace v2 {
@@ -103,12 +95,10 @@ struct TcCfg {
   static constexpr int PARTS = N2 / ON;
   static constexpr int W2ROWS = 3 * ON;                   // W2 image rows per chain (pieces w1, w2, w3), K = HP <= 64
   static constexpr uint32_t kAStage = KBA * 128 * 128;    // bytes per A stage
-  static constexpr bool HS = (SAPT_HS_SMEM != 0) && (HP == 64);   // activations of a unit in shared memory: [UC chains][h1 | h2 blocks][128 rows x 128 B]
-  static constexpr uint32_t kHsBytes = HS ? (uint32_t)UC * 2 * 128 * 128 : 0u;
-  static constexpr int STAGES = (KBA == 1) ? 4 : ((KBA == 2) ? (HS ? 2 : 3) : 2);
+  static constexpr int STAGES = (KBA == 1) ? 4 : ((KBA == 2) ? 3 : 2);
   static constexpr uint32_t smem_bytes(int upt) {
     const int ch = UC * upt;
-    return 1024u + kHsBytes + (uint32_t)ch * HP * KBA * 128 + STAGES * kAStage + (uint32_t)ch * W2ROWS * 128 + (uint32_t)ch * ON * 4 + 2048u +
+    return 1024u + (uint32_t)ch * HP * KBA * 128 + STAGES * kAStage + (uint32_t)ch * W2ROWS * 128 + (uint32_t)ch * ON * 4 + 2048u +
            (uint32_t)ch * 4 * HALVES * 3 * 8;
   }
   static constexpr int pick_upt() {
@@ -301,8 +291,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   constexpr int kD2Base = 2 * N1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sHs = smem;                       // [UC][2 blocks][128 x 128 B] when C::HS (else empty)
-  uint8_t* sB1 = sHs + C::kHsBytes;
+  uint8_t* sB1 = smem;
   uint8_t* sA = sB1 + kB1Bytes;
   uint8_t* sW2 = sA + STAGES * kAStage;
   float* sBias = reinterpret_cast<float*>(sW2 + kW2Bytes);          // [CH][ON]
@@ -418,21 +407,6 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
           const uint32_t wb = w2_addr + (uint32_t)(uu * UC + c) * kW2ChainBytes;
           // ON=16: D2[:, 0:3ON] = h1.[w1|w2|w3], D2[:, 0:2ON] += h2.[w1|w2]
           // ON=32: D2[:, 0:2ON] = h1.[w1|w2],    D2[:, 0:ON] += h1.w3,  D2[:, 0:2ON] += h2.[w1|w2]   (h piece = HP/2 columns)
-          if constexpr (C::HS) {
-            // A = the chain's activations in shared memory: block 0 = h1 pieces, block 1 = h2 pieces (K-major, SWIZZLE_128B)
-            const uint32_t hs1 = smem_u32(sHs) + (uint32_t)c * (2 * kABlock), hs2 = hs1 + kABlock;
-#pragma unroll
-            for (int half = 0; half < HP / 16; ++half)
-              tc_mma_bf16(d2, umma_desc_sw128(hs1 + half * 32), umma_desc_sw128(wb + half * 32), idesc2a, half ? 1u : 0u);
-            if constexpr (ON == 32) {
-#pragma unroll
-              for (int half = 0; half < HP / 16; ++half)
-                tc_mma_bf16(d2, umma_desc_sw128(hs1 + half * 32), umma_desc_sw128(wb + 2 * ON * 128 + half * 32), idesc2c, 1u);
-            }
-#pragma unroll
-            for (int half = 0; half < HP / 16; ++half)
-              tc_mma_bf16(d2, umma_desc_sw128(hs2 + half * 32), umma_desc_sw128(wb + half * 32), idesc2b, 1u);
-          } else {
 #pragma unroll
           for (int half = 0; half < HP / 16; ++half)
             tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), umma_desc_sw128(wb + half * 32), idesc2a, half ? 1u : 0u);
@@ -444,7 +418,6 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
 #pragma unroll
           for (int half = 0; half < HP / 16; ++half)
             tc_mma_bf16_ts(d2, hv + (uint32_t)(HP / 2 + half * 8), umma_desc_sw128(wb + half * 32), idesc2b, 1u);
-          }
           tc_commit(&d2_full[(u & 1) * UC + c]);
         }
       }
@@ -524,20 +497,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
     auto publish_hv = [&](int u) {  // activations of unit u -> TMEM (A operand of MMA-2), then tell the MMA warp
       // chain HV region = [h1 pairs of all HP hidden units (HP/2 cols) | h2 pairs (HP/2 cols)]
       const uint32_t hva = tmem_hv + lane_base + (uint32_t)(c * HP);
-      if constexpr (C::HS) {
-        // this warp's 32 hidden units of data row (quarter, lane): 64 B of the h1 block and 64 B of the h2 block of chain c,
-        // as four 16-byte chunks each, XOR-swizzled with the row like the TMA-written operand tiles
-        const int row = quarter * 32 + lane;
-        const uint32_t b1p = smem_u32(sHs) + (uint32_t)c * (2 * kABlock) + (uint32_t)row * 128;
-        const uint32_t b2p = b1p + kABlock;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t chunk = (uint32_t)((hf * 4 + q4) ^ (row & 7));
-          st_shared_v4(b1p + chunk * 16, hv[4 * q4], hv[4 * q4 + 1], hv[4 * q4 + 2], hv[4 * q4 + 3]);
-          st_shared_v4(b2p + chunk * 16, hv[16 + 4 * q4], hv[16 + 4 * q4 + 1], hv[16 + 4 * q4 + 2], hv[16 + 4 * q4 + 3]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async proxy
-      } else if constexpr (HALVES == 1) {
+      if constexpr (HALVES == 1) {
         if constexpr (HW == 32) tmem_st32(hva, hv); else tmem_st16(hva, hv);
         tmem_st_wait();
       } else {

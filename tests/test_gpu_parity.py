@@ -1107,7 +1107,7 @@ def test_surrogate_predict_tcgen05(lib, topology_id, P, R):
     np.testing.assert_allclose(got[rows_np], ref64[rows_np], rtol=2e-5, atol=1e-6)      # vs exact arithmetic
     np.testing.assert_allclose(got[rows_np], ref32[rows_np], rtol=3e-5, atol=2e-6)      # vs the fp32 restatement (its own rounding included)
     assert np.all(got[np.setdiff1d(np.arange(R), rows_np)] == -1.0)
-    assert 0.02 < got[rows_np].std()                                                      # the outputs are not saturated: the check means something
+    assert 0.005 < got[rows_np].std() and 0.2 < got[rows_np].mean() < 0.8                 # the outputs are neither constant nor saturated: the check means something
     # all rows, no list
     s2 = torch.full((R,), -1.0, dtype=torch.float32).cuda()
     lib.check(L.sapt_surrogate_predict(th.data_ptr(), ld, R, P, None, None, wd["W1"].data_ptr(), wd["b1"].data_ptr(), h1, wd["W2"].data_ptr(),
