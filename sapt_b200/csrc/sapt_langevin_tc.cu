@@ -218,35 +218,42 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == kTmaWarp) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer: the warp stays converged, one elected lane issues (see elect_one) =================
+    {
       uint32_t use[2] = {0, 0};               // how often each X buffer has been filled
       for (int item = blockIdx.x, c = 0; item < n_items; item += gridDim.x, ++c) {
         const Item w = get_item(item);
         const int n_tiles = w.n_tiles;
         const int64_t t_begin = w.t_begin;
         if (c > 0) mbar_wait<500>(w_free, (c - 1) & 1);
-        mbar_expect_tx(w_full, C::kB1Bytes + C::kW2Bytes + C::kW2TBytes);
+        if (elect_one()) {
+          mbar_expect_tx(w_full, C::kB1Bytes + C::kW2Bytes + C::kW2TBytes);
 #pragma unroll
-        for (int kb = 0; kb < KBA; ++kb) tma_load_2d(&map_b1, w_full, sB1 + kb * HP * 128, kb * 64, w.pos * HP);
-        tma_load_2d(&map_w2, w_full, sW2, 0, w.pos * N2);
-        tma_load_2d(&map_w2t, w_full, sW2T, 0, w.pos * HP);
+          for (int kb = 0; kb < KBA; ++kb) tma_load_2d(&map_b1, w_full, sB1 + kb * HP * 128, kb * 64, w.pos * HP);
+          tma_load_2d(&map_w2, w_full, sW2, 0, w.pos * N2);
+          tma_load_2d(&map_w2t, w_full, sW2T, 0, w.pos * HP);
+        }
+        __syncwarp();
         for (int t = 0; t < n_tiles; ++t) {
           const int b = t & 1;
           mbar_wait<500>(&empty_a[b], (use[b] & 1) ^ 1);
           ++use[b];
-          mbar_expect_tx(&full_a[b], C::kAStage);
+          if (elect_one()) {
+            mbar_expect_tx(&full_a[b], C::kAStage);
 #pragma unroll
-          for (int j = 0; j < NSLOT; ++j) {
-            const int blk = (DKC == 4 && j == 2) ? 3 : j;       // DKC = 4: the x3 block is not needed
-            tma_load_2d(&map_a, &full_a[b], sA + b * C::kAStage + j * kBlk, blk * 64, (int)((t_begin + t) * kTileM));
+            for (int j = 0; j < NSLOT; ++j) {
+              const int blk = (DKC == 4 && j == 2) ? 3 : j;       // DKC = 4: the x3 block is not needed
+              tma_load_2d(&map_a, &full_a[b], sA + b * C::kAStage + j * kBlk, blk * 64, (int)((t_begin + t) * kTileM));
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
+    // ================= MMA issuer: converged warp (waits, descriptor arithmetic on the uniform datapath), an elected lane issues
+    // tcgen05.mma / commit — under `if (lane == 0)` every MMA cost ~105 cycles of ELECT / R2UR.BROADCAST / BRA.U.ANY (see elect_one) ====
+    {
       const uint32_t id1 = idesc_bf16(kTileM, HP, false, false);
       const uint32_t id2a = idesc_bf16(kTileM, N2, false, false), id2b = idesc_bf16(kTileM, 2 * ON, false, false);
       const uint32_t id3 = idesc_bf16(kTileM, HP, false, false);
@@ -278,24 +285,30 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
             constexpr int kProd = 3;
             constexpr int pa[5] = {0, 0, 1, 0, 1};
             constexpr int pb[5] = {0, 1, 0, 2, 1};
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kProd; ++k)
+              for (int k = 0; k < kProd; ++k)
 #pragma unroll
-              for (int j = 0; j < DKC; ++j)
-                tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, pa[k] * DKC + j)), umma_desc_sw128(b1_chunk(pb[k] * DKC + j)), id1, (k | j) ? 1u : 0u);
-            tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, C::BIAS_SLOT_CHUNK)), umma_desc_sw128(b1_chunk(3 * DKC)), id1, 1u);
-            tc_commit(&d1_full[b]);
+                for (int j = 0; j < DKC; ++j)
+                  tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, pa[k] * DKC + j)), umma_desc_sw128(b1_chunk(pb[k] * DKC + j)), id1, (k | j) ? 1u : 0u);
+              tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, C::BIAS_SLOT_CHUNK)), umma_desc_sw128(b1_chunk(3 * DKC)), id1, 1u);
+              tc_commit(&d1_full[b]);
+            }
+            __syncwarp();
           }
           // ---- MMA-2: D2 = h1.[w1|w2|w3] + h2.[w1|w2], A = Hs read K-major ----
           for (int b = 0; b < nb; ++b) {
             const uint32_t hsa = smem_u32(sHs + b * C::kHsBytes), tD = tmem_base + C::kDS + b * 64;
             mbar_wait(&hs_full[b], phb[b]);
             tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, k)), umma_desc_sw128(w2a + k * 32), id2a, k ? 1u : 0u);
+              for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, k)), umma_desc_sw128(w2a + k * 32), id2a, k ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, HP / 16 + k)), umma_desc_sw128(w2a + k * 32), id2b, 1u);
-            tc_commit(&d2_full[b]);
+              for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, HP / 16 + k)), umma_desc_sw128(w2a + k * 32), id2b, 1u);
+              tc_commit(&d2_full[b]);
+            }
+            __syncwarp();
           }
           // ---- G2[b] += Hs^T . Ds (K = rows; all 64 Ds columns, the 32 of buffer b are meaningful), then
           //      MMA-3: D3 = do_hi.w1 + do_hi.w2 + do_lo.w1 ----
@@ -303,14 +316,17 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
             const uint32_t hsa = smem_u32(sHs + b * C::kHsBytes), tD = tmem_base + C::kDS + b * 64, tG2 = tmem_base + C::kG2 + b * 64;
             mbar_wait(&ds_full[b], phb[b]);
             tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < kTileM / 16; ++k)
-              tc_mma_bf16(tG2, desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), desc_mn(dsa + k * 2048, 0), idg2, (q | k) ? 1u : 0u);
             const uint32_t da = dsa + b * 64;
-            tc_mma_bf16(tD, umma_desc_sw128(da), umma_desc_sw128(w2ta), id3, 0u);
-            tc_mma_bf16(tD, umma_desc_sw128(da), umma_desc_sw128(w2ta + 32), id3, 1u);
-            tc_mma_bf16(tD, umma_desc_sw128(da + 32), umma_desc_sw128(w2ta), id3, 1u);
-            tc_commit(&d3_full[b]);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < kTileM / 16; ++k)
+                tc_mma_bf16(tG2, desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), desc_mn(dsa + k * 2048, 0), idg2, (q | k) ? 1u : 0u);
+              tc_mma_bf16(tD, umma_desc_sw128(da), umma_desc_sw128(w2ta), id3, 0u);
+              tc_mma_bf16(tD, umma_desc_sw128(da), umma_desc_sw128(w2ta + 32), id3, 1u);
+              tc_mma_bf16(tD, umma_desc_sw128(da + 32), umma_desc_sw128(w2ta), id3, 1u);
+              tc_commit(&d3_full[b]);
+            }
+            __syncwarp();
           }
           // ---- G1 += X^T . Hs(dh) (K = rows) ----
           for (int b = 0; b < nb; ++b) {
@@ -318,14 +334,20 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
             mbar_wait(&dh_full[b], phb[b]);
             phb[b] ^= 1;
             tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kTileM / 16; ++k)
-              tc_mma_bf16(tG1, desc_mn(xa + k * 2048, NSLOT > 1 ? kBlk : 0), desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), idg1, (q | b | k) ? 1u : 0u);
-            tc_commit(&empty_a[b]);
+              for (int k = 0; k < kTileM / 16; ++k)
+                tc_mma_bf16(tG1, desc_mn(xa + k * 2048, NSLOT > 1 ? kBlk : 0), desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), idg1, (q | b | k) ? 1u : 0u);
+              tc_commit(&empty_a[b]);
+            }
+            __syncwarp();
           }
         }
-        tc_commit(g_full);
-        tc_commit(w_free);
+        if (elect_one()) {
+          tc_commit(g_full);
+          tc_commit(w_free);
+        }
+        __syncwarp();
       }
     }
   } else {

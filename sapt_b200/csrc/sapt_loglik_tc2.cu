@@ -249,6 +249,9 @@ __device__ __forceinline__ void sigmoid4_lim(float t0, float t1, float t2, float
 #ifndef SAPT_CONST_O
 #define SAPT_CONST_O 1    // compile-time output count for the BASELINE shapes (see loglik_tc2_kernel)
 #endif
+#ifndef SAPT_ELECT
+#define SAPT_ELECT 1      // single-thread instructions issued by an elected lane of a converged warp (0: `if (lane == 0)`, round 1)
+#endif
 #ifndef SAPT_P1_CHAIN
 #define SAPT_P1_CHAIN 2   // quads per ordered group in phase 1 (0: let ptxas schedule freely)
 #endif
@@ -342,27 +345,33 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   const uint32_t tmem_hv = tmem_base + kHvBase;
 
   if (warp == kTmaWarp) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer (the warp stays converged, one elected lane issues: see elect_one) =================
+    if (SAPT_ELECT ? elect_one() : (lane == 0)) {
       mbar_expect_tx(b_full, kB1Bytes + kW2Bytes);
 #pragma unroll
       for (int kb = 0; kb < KBA; ++kb) tma_load_2d(&map_b1, b_full, sB1 + kb * kB1Block, kb * 64, blockIdx.y * CH * HP);
 #pragma unroll
       for (int q = 0; q < CH / C::kW2Box; ++q)  // boxes of kW2Box chains x 3 ON rows
         tma_load_2d(&map_w2, b_full, sW2 + q * C::kW2Box * kW2ChainBytes, 0, (blockIdx.y * CH + q * C::kW2Box) * C::W2ROWS);
-      for (int it = 0; it < n_my_tiles; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait<1000>(&empty_a[s], ph ^ 1);
+    }
+    __syncwarp();
+    for (int it = 0; it < n_my_tiles; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      if (!SAPT_ELECT && lane != 0) break;
+      mbar_wait<1000>(&empty_a[s], ph ^ 1);
+      if (SAPT_ELECT ? elect_one() : true) {
         mbar_expect_tx(&full_a[s], kAStage);
 #pragma unroll
         for (int kb = 0; kb < KBA; ++kb)
           tma_load_2d(&map_a, &full_a[s], sA + s * kAStage + kb * kABlock, kb * 64, (int)((t_begin + it) * kTileM));
       }
+      if (SAPT_ELECT) __syncwarp();
     }
   } else if (warp == kMmaWarp) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
+    // ================= MMA issuer: the warp stays converged (waits, descriptor arithmetic on the uniform datapath), one elected
+    // lane issues tcgen05.mma / commit (see elect_one) =================
+    if (SAPT_ELECT || lane == 0) {
       // instruction descriptor (kind::f16): D fp32 (bit 4), A / B format in bits 7-9 / 10-12 (0 = fp16, 1 = bf16), N >> 3, M >> 4
       auto idesc = [](int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24); };
       const uint32_t idesc1 = C::XF16 ? ((1u << 4) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24)) : idesc(N1);
@@ -384,14 +393,17 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
         constexpr int pb[6] = {0, 1, 0, 2, 1, 0};
         auto a_at = [&](int chunk) { return umma_desc_sw128(a_addr + (uint32_t)(chunk >> 2) * kABlock + (uint32_t)(chunk & 3) * 32); };
         auto b_at = [&](int chunk) { return umma_desc_sw128(b_addr + (uint32_t)(chunk >> 2) * kB1Block + (uint32_t)(chunk & 3) * 32); };
+        if (SAPT_ELECT ? elect_one() : true) {
 #pragma unroll
-        for (int q = 0; q < C::NPROD; ++q)
+          for (int q = 0; q < C::NPROD; ++q)
 #pragma unroll
-          for (int j = 0; j < DKC; ++j)
-            tc_mma_bf16(tmem_base, a_at(pa[q] * DKC + j), b_at(pb[q] * DKC + j), idesc1, (q | j) ? 1u : 0u);
-        if constexpr (!C::BIASX) tc_mma_bf16(tmem_base, a_at(C::XP * DKC), b_at(C::XP * DKC), idesc1, 1u);
-        if (uu == UPT - 1) tc_commit(&empty_a[s]);
-        tc_commit(d1_full);
+            for (int j = 0; j < DKC; ++j)
+              tc_mma_bf16(tmem_base, a_at(pa[q] * DKC + j), b_at(pb[q] * DKC + j), idesc1, (q | j) ? 1u : 0u);
+          if constexpr (!C::BIASX) tc_mma_bf16(tmem_base, a_at(C::XP * DKC), b_at(C::XP * DKC), idesc1, 1u);
+          if (uu == UPT - 1) tc_commit(&empty_a[s]);
+          tc_commit(d1_full);
+        }
+        if (SAPT_ELECT) __syncwarp();
       };
       if (n_units > 0) issue_mma1(0);
       for (int u = 0; u < n_units; ++u) {
@@ -407,18 +419,21 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
           const uint32_t wb = w2_addr + (uint32_t)(uu * UC + c) * kW2ChainBytes;
           // ON=16: D2[:, 0:3ON] = h1.[w1|w2|w3], D2[:, 0:2ON] += h2.[w1|w2]
           // ON=32: D2[:, 0:2ON] = h1.[w1|w2],    D2[:, 0:ON] += h1.w3,  D2[:, 0:2ON] += h2.[w1|w2]   (h piece = HP/2 columns)
-#pragma unroll
-          for (int half = 0; half < HP / 16; ++half)
-            tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), umma_desc_sw128(wb + half * 32), idesc2a, half ? 1u : 0u);
-          if constexpr (ON == 32) {
+          if (SAPT_ELECT ? elect_one() : true) {
 #pragma unroll
             for (int half = 0; half < HP / 16; ++half)
-              tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), umma_desc_sw128(wb + 2 * ON * 128 + half * 32), idesc2c, 1u);
-          }
+              tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), umma_desc_sw128(wb + half * 32), idesc2a, half ? 1u : 0u);
+            if constexpr (ON == 32) {
 #pragma unroll
-          for (int half = 0; half < HP / 16; ++half)
-            tc_mma_bf16_ts(d2, hv + (uint32_t)(HP / 2 + half * 8), umma_desc_sw128(wb + half * 32), idesc2b, 1u);
-          tc_commit(&d2_full[(u & 1) * UC + c]);
+              for (int half = 0; half < HP / 16; ++half)
+                tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), umma_desc_sw128(wb + 2 * ON * 128 + half * 32), idesc2c, 1u);
+            }
+#pragma unroll
+            for (int half = 0; half < HP / 16; ++half)
+              tc_mma_bf16_ts(d2, hv + (uint32_t)(HP / 2 + half * 8), umma_desc_sw128(wb + half * 32), idesc2b, 1u);
+            tc_commit(&d2_full[(u & 1) * UC + c]);
+          }
+          if (SAPT_ELECT) __syncwarp();
         }
       }
     }
@@ -680,6 +695,9 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb1, const CUten
 template <typename F>
 static int tc2_dispatch(int HP, int ON, int DKC, F&& fn) {
 #define SAPT_V(H, O, K) if (HP == H && ON == O && DKC == K) return fn(std::integral_constant<int, H>{}, std::integral_constant<int, O>{}, std::integral_constant<int, K>{});
+#ifdef SAPT_TC2_FEW   // development builds: only the BASELINE shapes (C3, C4, C5)
+  SAPT_V(32, 16, 1) SAPT_V(64, 8, 12) SAPT_V(32, 32, 9)
+#else
   SAPT_V(16, 16, 1) SAPT_V(16, 16, 2) SAPT_V(16, 16, 3) SAPT_V(16, 16, 4)
   SAPT_V(32, 16, 1) SAPT_V(32, 16, 2) SAPT_V(32, 16, 3) SAPT_V(32, 16, 4)
   SAPT_V(32, 32, 1) SAPT_V(32, 32, 2) SAPT_V(32, 32, 3) SAPT_V(32, 32, 4)
@@ -694,6 +712,7 @@ static int tc2_dispatch(int HP, int ON, int DKC, F&& fn) {
   // O <= 8 at HP = 64 (see TcCfg)
   SAPT_V(64, 8, 1) SAPT_V(64, 8, 2) SAPT_V(64, 8, 3) SAPT_V(64, 8, 4) SAPT_V(64, 8, 9) SAPT_V(64, 8, 10) SAPT_V(64, 8, 11) SAPT_V(64, 8, 12)
   SAPT_V(64, 12, 1) SAPT_V(64, 12, 2) SAPT_V(64, 12, 3) SAPT_V(64, 12, 4) SAPT_V(64, 12, 9) SAPT_V(64, 12, 10) SAPT_V(64, 12, 11) SAPT_V(64, 12, 12)
+#endif
 #undef SAPT_V
   set_error("tcgen05 path: no variant for HP=%d ON=%d DKC=%d", HP, ON, DKC);
   return SAPT_ERR_UNSUPPORTED;

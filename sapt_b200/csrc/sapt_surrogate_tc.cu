@@ -118,12 +118,13 @@ __global__ void __launch_bounds__(kThreads, 1) surrogate_tc_kernel(const __grid_
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t stage_stride = (kStage + 1023u) & ~1023u;
 
+  // Warps 4 (TMA) and 5 (MMA) stay converged; the single-thread instructions are issued by an elected lane (see elect_one).
   if (warp == 4) {
-    if (lane == 0) {
-      const int KP = KB * 64;
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % kStages;
-        mbar_wait<200>(&empty[s], ((kb / kStages) & 1) ^ 1);
+    const int KP = KB * 64;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % kStages;
+      mbar_wait<200>(&empty[s], ((kb / kStages) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&full[s], kStage);
         uint8_t* st = sStage + s * stage_stride;
         tma_load_2d(&map_a, &full[s], st, kb * 64, row0);
@@ -131,17 +132,18 @@ __global__ void __launch_bounds__(kThreads, 1) surrogate_tc_kernel(const __grid_
         tma_load_2d(&map_b, &full[s], st + 2 * kABlk, kb * 64, 0);
         tma_load_2d(&map_b, &full[s], st + 2 * kABlk + kBBlk, KP + kb * 64, 0);
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      // kind::f16, A and B fp16 (format 0), D fp32 (bit 4), N >> 3 at bit 17, M >> 4 at bit 24
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % kStages;
-        mbar_wait(&full[s], (kb / kStages) & 1);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(sStage + s * stage_stride), a_lo = a_hi + kABlk;
-        const uint32_t b_hi = a_hi + 2 * kABlk, b_lo = b_hi + kBBlk;
+    // kind::f16, A and B fp16 (format 0), D fp32 (bit 4), N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % kStages;
+      mbar_wait(&full[s], (kb / kStages) & 1);
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(sStage + s * stage_stride), a_lo = a_hi + kABlk;
+      const uint32_t b_hi = a_hi + 2 * kABlk, b_lo = b_hi + kBBlk;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {     // four K steps of 16 inside the 64-element block
           tc_mma_bf16(tmem_base, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, (kb | k) ? 1u : 0u);
@@ -149,8 +151,9 @@ __global__ void __launch_bounds__(kThreads, 1) surrogate_tc_kernel(const __grid_
           tc_mma_bf16(tmem_base, umma_desc_sw128(a_lo + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, 1u);
         }
         tc_commit(&empty[s]);
+        if (kb == KB - 1) tc_commit(acc_full);
       }
-      tc_commit(acc_full);
+      __syncwarp();
     }
   } else {
     // ================= epilogue: thread = listed row =================

@@ -53,6 +53,21 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
                "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+// One lane of a CONVERGED warp (the lowest: the election is deterministic for a given member mask). The single-thread instructions
+// (tcgen05.mma / commit, TMA) are issued under this predicate by a warp that otherwise stays converged: ptxas then keeps descriptors
+// and addresses on the uniform datapath. Under `if (lane == 0)` it cannot know that one thread is active and wraps EVERY tcgen05.mma
+// in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~13 dependent instructions, ~105 cycles per MMA measured by devtools/mma_cost).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
