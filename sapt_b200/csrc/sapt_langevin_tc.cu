@@ -36,7 +36,7 @@
 namespace sapt {
 
 int launch_tc2_pack(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O, int HP, int ON, int CH,
-                    int DKC, int KROW, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2, int n_blocks, cudaStream_t st);   // sapt_loglik_tc2.cu
+                    int DKC, int KROW, int biasx, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2, int n_blocks, cudaStream_t st);   // sapt_loglik_tc2.cu
 int tc_make_map_2d(CUtensorMap* map, void* base, uint64_t inner_elems, uint64_t rows, uint32_t box_rows);                       // sapt_tc_host.cu
 int launch_langevin_batch_finalize(const float* part, int n_chunks, int R, int P, const float* theta, float* theta_gd, int64_t ld,
                                    const int32_t* rows, const int32_t* n_rows, double lr_scale, cudaStream_t st);                // sapt_langevin.cu
@@ -51,29 +51,37 @@ constexpr int N2 = 3 * ON;
 constexpr uint32_t kBlk = 128 * 128;      // one 64-column block of a 128-row tile
 
 // DK packs DKC (DK & 7) and "O <= 8" (DK >= 8): the output phase then keeps 8 instead of 16 accumulator columns per
-// partial sum in registers. With 228 KB of shared memory in use the L1 behind local memory is tiny, so spills are
+// partial sum in registers. With ~210 KB of shared memory in use the L1 behind local memory is tiny, so spills are
 // served from L2 (see the same finding for the likelihood kernel, profiles/r1_c4_loglik_summary.json).
+//
+// Shared memory is what limits the overlap, so the X tile is kept to the blocks the products need: x1 and x2 (x3 is not used,
+// see MMA-1) — and for DKC >= 3 the bias rides in the spare x1 column (a 1.0 written by tc_prepare_dataset; the bias pieces sit
+// in that column of the w1 / w2 pieces of B1), so the tile is two 64-column blocks whatever D is: THREE X stages fit beside
+// two Hs buffers, and the tile a group needs next is already in shared memory when its previous tile retires.
 template <int HP, int DK>
 struct Cfg {
   static constexpr int DKC = DK & 7;
   static constexpr int NRL = (DK >= 8) ? 8 : 16;              // output columns read / accumulated per partial sum
+  static constexpr int NQ = NRL / 2;                          // ... per epilogue warp (the two halves of a group split the outputs)
   static constexpr int DW = 16 * DKC;                         // features per x piece (padded)
-  static constexpr int KBA = (3 * DKC + 1 + 3) / 4;           // 128-byte K blocks of an image row
-  static constexpr int NSLOT = (DKC == 4) ? 3 : KBA;          // X blocks kept in shared memory: x1, x2, bias (x3 skipped)
-  static constexpr int BIAS_SLOT_CHUNK = (DKC == 4) ? 8 : 3 * DKC;   // bias chunk index inside the shared-memory tile
+  static constexpr bool BIASX = DKC >= 3;                     // bias in the spare x1 column (needs D < 16 DKC: langevin_tc_supported)
+  static constexpr int KBA = (3 * DKC + 1 + 3) / 4;           // 128-byte K blocks of an image row (host side: row length)
+  static constexpr int NSLOT = BIASX ? 2 : KBA;               // X / B1 blocks kept in shared memory (1 or 2)
+  static constexpr int BIAS_CHUNK = 3 * DKC;                  // bias chunk of the image row (used when !BIASX)
+  static constexpr int NSTAGE = 3;                            // X tile ring
   static constexpr int NBH = (2 * HP + 63) / 64;              // blocks of Hs: [piece 1 (HP) | piece 2 (HP)]
-  static constexpr int HW = HP / 4;                           // hidden units per epilogue warp
+  static constexpr int HW = HP / 2;                           // hidden units per epilogue warp
   static constexpr int NG1 = NBH * 64;                        // G1 columns
   static constexpr uint32_t kAStage = NSLOT * kBlk;
-  static constexpr uint32_t kB1Bytes = HP * KBA * 128;
+  static constexpr uint32_t kB1Bytes = HP * NSLOT * 128;
   static constexpr uint32_t kW2Bytes = N2 * 128;
   static constexpr uint32_t kW2TBytes = HP * 128;
   static constexpr uint32_t kHsBytes = NBH * kBlk;
-  __host__ __device__ static constexpr uint32_t smem_bytes() {   // two tile buffers of X and Hs, one shared Ds block
-    return 1024u + 2 * kAStage + 2 * kHsBytes + kBlk + ((kB1Bytes + 1023u) & ~1023u) + ((kW2TBytes + 1023u) & ~1023u) +
+  __host__ __device__ static constexpr uint32_t smem_bytes() {   // X ring, one Hs buffer per group, one shared Ds block
+    return 1024u + NSTAGE * kAStage + 2 * kHsBytes + kBlk + ((kB1Bytes + 1023u) & ~1023u) + ((kW2TBytes + 1023u) & ~1023u) +
            ((kW2Bytes + 1023u) & ~1023u) + 512u;
   }
-  // TMEM columns: scratch D1/D2/D3 per tile buffer | G1 | G2 per tile buffer
+  // TMEM columns: scratch D1/D2/D3 per group | G1 | G2 per group
   static constexpr int kDS = 0, kG1 = 128, kG2 = 128 + NG1, kCols = 512;
   static_assert(128 + NG1 + 128 <= kCols && HP <= 64 && N2 <= 64, "TMEM budget");
   // column of ones in the X image that turns -sum(dh) into a row of G1 (see tc_prepare_dataset)
@@ -113,9 +121,24 @@ __device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[N]) {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
 
+// one poll of an mbarrier phase with a short suspend hint (the MMA warp serves two tile streams and must not block on either)
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(64u)
+      : "memory");
+  return __all_sync(0xffffffffu, done != 0);
+}
+
 // writes n bf16 values (n = 4, 8 or 16; packed pairs, N/2 words) of one data row into a swizzled [128 rows][64 bf16] block at column col0
 template <int N>
-__device__ __forceinline__ void store_row_packed(uint8_t* block, int row, int col0, const uint32_t (&w)[N / 2]) {
+__device__ __forceinline__ void store_row_packed(uint8_t* block, int row, int col0, const uint32_t* w) {
   const uint32_t rowp = smem_u32(block) + (uint32_t)row * 128;
   if constexpr (N == 4) {
     const int chunk = col0 >> 3;
@@ -151,31 +174,37 @@ __global__ void lt_pack_w2t_kernel(const float* theta, int64_t ld, const int32_t
   }
 }
 
+// Two tile streams per CTA: epilogue warps 0-7 (group 0) take the even tiles of the item's row chunk, warps 8-15 (group 1) the odd
+// ones; each group owns one Hs buffer, one TMEM scratch block and one G2 accumulator and walks its tiles through
+// P1 -> P2 -> P3 at its own pace. The MMA warp serves whichever group is ready (a four-state machine per group, polled), so the
+// tensor pipe works on one tile while the other tile's epilogue computes — round 1 / early round 2 ran the two tiles in lockstep
+// (every stage issued for both before the next one was waited for) and reloaded an X buffer only after its tile had retired:
+// 5 400 cycles per tile against ~2 000 of tensor-pipe and ~2 000 of issue work.
 template <int HP, int DK>
 __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b1,
                                                                   const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2t,
                                                                   Params p) {
   using C = Cfg<HP, DK>;
-  constexpr int DKC = C::DKC, NRL = C::NRL;
-  constexpr int DW = C::DW, KBA = C::KBA, NSLOT = C::NSLOT, NBH = C::NBH, HW = C::HW, NG1 = C::NG1;
+  constexpr int DKC = C::DKC, NRL = C::NRL, NQ = C::NQ, NSTAGE = C::NSTAGE;
+  constexpr int DW = C::DW, NSLOT = C::NSLOT, NBH = C::NBH, HW = C::HW, NG1 = C::NG1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;                                          // [2 buffers][NSLOT blocks]
-  uint8_t* sHs = sA + 2 * C::kAStage;                          // [2 buffers][NBH blocks]
-  uint8_t* sDs = sHs + 2 * C::kHsBytes;                        // ONE block: buffer b owns columns [32 b, 32 b + 32)
+  uint8_t* sA = smem;                                          // [NSTAGE][NSLOT blocks]
+  uint8_t* sHs = sA + NSTAGE * C::kAStage;                     // [2 groups][NBH blocks]
+  uint8_t* sDs = sHs + 2 * C::kHsBytes;                        // ONE block: group g owns columns [32 g, 32 g + 32)
   uint8_t* sB1 = sDs + kBlk;
   uint8_t* sW2T = sB1 + ((C::kB1Bytes + 1023u) & ~1023u);
   uint8_t* sW2 = sW2T + ((C::kW2TBytes + 1023u) & ~1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW2 + ((C::kW2Bytes + 1023u) & ~1023u));
-  // per tile buffer b (two tiles are in flight: while one waits for an MMA the other one computes)
-  uint64_t* full_a = bars;                  // [2]
-  uint64_t* empty_a = full_a + 2;           // [2]
-  uint64_t* d1_full = empty_a + 2;          // [2]
-  uint64_t* hs_full = d1_full + 2;          // [2] 16 warps
+  uint64_t* full_a = bars;                  // [NSTAGE]
+  uint64_t* empty_a = full_a + NSTAGE;      // [NSTAGE]
+  // per group g
+  uint64_t* d1_full = empty_a + NSTAGE;     // [2]
+  uint64_t* hs_full = d1_full + 2;          // [2] 8 warps
   uint64_t* d2_full = hs_full + 2;          // [2]
-  uint64_t* ds_full = d2_full + 2;          // [2] 4 warps
+  uint64_t* ds_full = d2_full + 2;          // [2] 8 warps
   uint64_t* d3_full = ds_full + 2;          // [2]
-  uint64_t* dh_full = d3_full + 2;          // [2] 16 warps
+  uint64_t* dh_full = d3_full + 2;          // [2] 8 warps
   uint64_t* w_full = dh_full + 2;           // weight panels of the current chain landed
   uint64_t* w_free = w_full + 1;            // all MMAs of the chain done: the panels may be overwritten
   uint64_t* g_full = w_free + 1;            // G1 / G2 of the chain complete
@@ -188,26 +217,27 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
   // the number of active chains is only known on the device, so the items are dealt round-robin here
   const int n_items = nact * p.n_chunks;
   if ((int)blockIdx.x >= n_items) return;
-  struct Item { int pos, chunk, n_tiles, n_pairs; int64_t t_begin; };
+  struct Item { int pos, chunk, n_tiles; int64_t t_begin; };
   auto get_item = [&](int item) {
     Item it;
     it.pos = item % nact; it.chunk = item / nact;
     it.t_begin = (int64_t)it.chunk * p.tiles_per_chunk;
     it.n_tiles = (int)max((int64_t)0, min(it.t_begin + (int64_t)p.tiles_per_chunk, p.n_tiles) - it.t_begin);
-    it.n_pairs = (it.n_tiles + 1) / 2;      // tile 2 q uses buffer 0, tile 2 q + 1 buffer 1 (absent in a ragged last pair)
     return it;
   };
 
   if (threadIdx.x == 0) {
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&full_a[b], 1); mbar_init(&empty_a[b], 1);
-      mbar_init(&d1_full[b], 1); mbar_init(&hs_full[b], kEpiWarps); mbar_init(&d2_full[b], 1); mbar_init(&ds_full[b], 4);
-      mbar_init(&d3_full[b], 1); mbar_init(&dh_full[b], kEpiWarps);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&d1_full[g], 1); mbar_init(&hs_full[g], kEpiWarps / 2); mbar_init(&d2_full[g], 1); mbar_init(&ds_full[g], kEpiWarps / 2);
+      mbar_init(&d3_full[g], 1); mbar_init(&dh_full[g], kEpiWarps / 2);
     }
     mbar_init(w_full, 1); mbar_init(w_free, 1); mbar_init(g_full, 1); mbar_init(g_free, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    fence_async_smem();
   }
+  // Ds columns that no output phase writes (outputs >= NRL, and the columns past [do_hi | do_lo]) are operands of MMA-3 / G2: zero once
+  for (int i = threadIdx.x; i < (int)(kBlk / 16); i += kThreads) st_shared_v4(smem_u32(sDs) + 16u * i, 0u, 0u, 0u, 0u);
+  fence_async_smem();
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(C::kCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -219,259 +249,252 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
 
   if (warp == kTmaWarp) {
     // ================= TMA producer: the warp stays converged, one elected lane issues (see elect_one) =================
-    {
-      uint32_t use[2] = {0, 0};               // how often each X buffer has been filled
-      for (int item = blockIdx.x, c = 0; item < n_items; item += gridDim.x, ++c) {
-        const Item w = get_item(item);
-        const int n_tiles = w.n_tiles;
-        const int64_t t_begin = w.t_begin;
-        if (c > 0) mbar_wait<500>(w_free, (c - 1) & 1);
-        if (elect_one()) {
-          mbar_expect_tx(w_full, C::kB1Bytes + C::kW2Bytes + C::kW2TBytes);
+    uint32_t n_fill = 0;                      // tiles loaded so far (over all items): stage = n_fill % NSTAGE
+    for (int item = blockIdx.x, c = 0; item < n_items; item += gridDim.x, ++c) {
+      const Item w = get_item(item);
+      if (c > 0) mbar_wait<500>(w_free, (c - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(w_full, C::kB1Bytes + C::kW2Bytes + C::kW2TBytes);
 #pragma unroll
-          for (int kb = 0; kb < KBA; ++kb) tma_load_2d(&map_b1, w_full, sB1 + kb * HP * 128, kb * 64, w.pos * HP);
-          tma_load_2d(&map_w2, w_full, sW2, 0, w.pos * N2);
-          tma_load_2d(&map_w2t, w_full, sW2T, 0, w.pos * HP);
+        for (int kb = 0; kb < NSLOT; ++kb) tma_load_2d(&map_b1, w_full, sB1 + kb * HP * 128, kb * 64, w.pos * HP);
+        tma_load_2d(&map_w2, w_full, sW2, 0, w.pos * N2);
+        tma_load_2d(&map_w2t, w_full, sW2T, 0, w.pos * HP);
+      }
+      __syncwarp();
+      for (int t = 0; t < w.n_tiles; ++t, ++n_fill) {
+        const uint32_t s = n_fill % NSTAGE;
+        mbar_wait<200>(&empty_a[s], ((n_fill / NSTAGE) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full_a[s], C::kAStage);
+#pragma unroll
+          for (int j = 0; j < NSLOT; ++j) tma_load_2d(&map_a, &full_a[s], sA + s * C::kAStage + j * kBlk, j * 64, (int)((w.t_begin + t) * kTileM));
         }
         __syncwarp();
-        for (int t = 0; t < n_tiles; ++t) {
-          const int b = t & 1;
-          mbar_wait<500>(&empty_a[b], (use[b] & 1) ^ 1);
-          ++use[b];
-          if (elect_one()) {
-            mbar_expect_tx(&full_a[b], C::kAStage);
-#pragma unroll
-            for (int j = 0; j < NSLOT; ++j) {
-              const int blk = (DKC == 4 && j == 2) ? 3 : j;       // DKC = 4: the x3 block is not needed
-              tma_load_2d(&map_a, &full_a[b], sA + b * C::kAStage + j * kBlk, blk * 64, (int)((t_begin + t) * kTileM));
-            }
-          }
-          __syncwarp();
-        }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ================= MMA issuer: converged warp (waits, descriptor arithmetic on the uniform datapath), an elected lane issues
-    // tcgen05.mma / commit — under `if (lane == 0)` every MMA cost ~105 cycles of ELECT / R2UR.BROADCAST / BRA.U.ANY (see elect_one) ====
-    {
-      const uint32_t id1 = idesc_bf16(kTileM, HP, false, false);
-      const uint32_t id2a = idesc_bf16(kTileM, N2, false, false), id2b = idesc_bf16(kTileM, 2 * ON, false, false);
-      const uint32_t id3 = idesc_bf16(kTileM, HP, false, false);
-      const uint32_t idg2 = idesc_bf16(128, 64, true, true), idg1 = idesc_bf16(128, NG1, true, true);
-      const uint32_t b1a = smem_u32(sB1), w2a = smem_u32(sW2), w2ta = smem_u32(sW2T), dsa = smem_u32(sDs);
-      const uint32_t tG1 = tmem_base + C::kG1;
-      // shared-memory chunk (16 bf16 = 32 B) -> address inside a tile / panel made of 64-column blocks
-      auto a_chunk = [&](uint32_t base, int chunk) { return base + (uint32_t)(chunk >> 2) * kBlk + (uint32_t)(chunk & 3) * 32; };
-      auto b1_chunk = [&](int chunk) { return b1a + (uint32_t)(chunk >> 2) * (HP * 128) + (uint32_t)(chunk & 3) * 32; };
-      uint32_t use[2] = {0, 0};
-      uint32_t phb[2] = {0, 0};   // parity of the per-buffer barriers: they complete once per pair that uses the buffer
-      for (int item = blockIdx.x, c = 0; item < n_items; item += gridDim.x, ++c) {
-        const Item w = get_item(item);
-        const int n_tiles = w.n_tiles, n_pairs = w.n_pairs;
-        mbar_wait(w_full, c & 1);
-        if (c > 0) mbar_wait(g_free, (c - 1) & 1);     // accumulators of the previous item have been read out
-        for (int q = 0; q < n_pairs; ++q) {
-          const int nb = (2 * q + 1 < n_tiles) ? 2 : 1;
-          // ---- MMA-1: x1w1 x1w2 x2w1 + bias. x chunks: x1 = [0, DKC), x2 = [DKC, 2 DKC) ----
-          for (int b = 0; b < nb; ++b) {
-            const uint32_t xa = smem_u32(sA + b * C::kAStage), tD = tmem_base + C::kDS + b * 64;
-            mbar_wait(&full_a[b], use[b] & 1);
-            ++use[b];
+    // ================= MMA issuer: converged warp (polls, descriptor arithmetic on the uniform datapath), an elected lane issues
+    // tcgen05.mma / commit — under `if (lane == 0)` every MMA cost ~100 cycles of ELECT / R2UR.BROADCAST / BRA.U.ANY (see elect_one) ====
+    const uint32_t id1 = idesc_bf16(kTileM, HP, false, false);
+    const uint32_t id2a = idesc_bf16(kTileM, N2, false, false), id2b = idesc_bf16(kTileM, 2 * ON, false, false);
+    const uint32_t id3 = idesc_bf16(kTileM, HP, false, false);
+    const uint32_t idg2 = idesc_bf16(128, 64, true, true), idg1 = idesc_bf16(128, NG1, true, true);
+    const uint32_t b1a = smem_u32(sB1), w2a = smem_u32(sW2), w2ta = smem_u32(sW2T), dsa = smem_u32(sDs);
+    const uint32_t tG1 = tmem_base + C::kG1;
+    // shared-memory chunk (16 bf16 = 32 B) -> address inside a tile / panel made of 64-column blocks
+    auto a_chunk = [&](uint32_t base, int chunk) { return base + (uint32_t)(chunk >> 2) * kBlk + (uint32_t)(chunk & 3) * 32; };
+    auto b1_chunk = [&](int chunk) { return b1a + (uint32_t)(chunk >> 2) * (HP * 128) + (uint32_t)(chunk & 3) * 32; };
+    uint32_t n_base = 0;                      // tiles of earlier items (the X ring runs across items)
+    uint32_t ph[2] = {0, 0};                  // parity of the per-group barriers: they complete once per tile of the group
+    for (int item = blockIdx.x, c = 0; item < n_items; item += gridDim.x, ++c) {
+      const Item w = get_item(item);
+      const int n_tiles = w.n_tiles;
+      mbar_wait(w_full, c & 1);
+      if (c > 0) mbar_wait(g_free, (c - 1) & 1);     // accumulators of the previous item have been read out
+      tc_fence_after();
+      int tile[2] = {0, 1};
+      int st[2] = {n_tiles > 0 ? 0 : 4, n_tiles > 1 ? 0 : 4};   // 0: MMA-1, 1: MMA-2, 2: G2 + MMA-3, 3: G1, 4: done
+      bool g1_started = false;
+      while (st[0] != 4 || st[1] != 4) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (st[g] == 4) continue;
+          const uint32_t n = n_base + (uint32_t)tile[g];
+          const uint32_t s = n % NSTAGE;
+          const uint32_t xa = smem_u32(sA + s * C::kAStage), hsa = smem_u32(sHs + g * C::kHsBytes);
+          const uint32_t tD = tmem_base + C::kDS + g * 64, tG2 = tmem_base + C::kG2 + g * 64;
+          if (st[g] == 0) {
+            // ---- MMA-1: x1w1 x1w2 x2w1 (+ bias chunk). x chunks: x1 = [0, DKC), x2 = [DKC, 2 DKC) ----
+            // Three piece products: the dropped x1w3 / x2w2 terms are 2^-16 |x w|, i.e. ~1e-4 absolute on a pre-activation, zero-mean
+            // over rows — far inside the 1e-4 (relative to max |g|) the gradient needs. (The likelihood kernel keeps fp32-grade
+            // products: an MH decision hangs on a difference of sums over all rows.) The scratch block is free (P3 of the group's
+            // previous tile has read D3: dh_full was seen in state 3) and Hs is not written before this batch — issued after that
+            // tile's G1 — has completed.
+            if (!mbar_try(&full_a[s], (n / NSTAGE) & 1)) continue;
             tc_fence_after();
-            // Three piece products x1w1 x1w2 x2w1: the dropped x1w3 / x2w2 terms are 2^-16 |x w|, i.e. ~1e-4 absolute on a
-            // pre-activation, zero-mean over rows — far inside the 1e-4 (relative to max |g|) the gradient needs, and 9 of 21
-            // MMA-1 instructions less per tile at D = 54. (The likelihood kernel keeps fp32-grade products: an MH decision
-            // hangs on a difference of sums over all rows.)
-            constexpr int kProd = 3;
-            constexpr int pa[5] = {0, 0, 1, 0, 1};
-            constexpr int pb[5] = {0, 1, 0, 2, 1};
+            constexpr int pa[3] = {0, 0, 1};
+            constexpr int pb[3] = {0, 1, 0};
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < kProd; ++k)
+              for (int k = 0; k < 3; ++k)
 #pragma unroll
                 for (int j = 0; j < DKC; ++j)
                   tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, pa[k] * DKC + j)), umma_desc_sw128(b1_chunk(pb[k] * DKC + j)), id1, (k | j) ? 1u : 0u);
-              tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, C::BIAS_SLOT_CHUNK)), umma_desc_sw128(b1_chunk(3 * DKC)), id1, 1u);
-              tc_commit(&d1_full[b]);
+              if constexpr (!C::BIASX) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, C::BIAS_CHUNK)), umma_desc_sw128(b1_chunk(C::BIAS_CHUNK)), id1, 1u);
+              tc_commit(&d1_full[g]);
             }
             __syncwarp();
-          }
-          // ---- MMA-2: D2 = h1.[w1|w2|w3] + h2.[w1|w2], A = Hs read K-major ----
-          for (int b = 0; b < nb; ++b) {
-            const uint32_t hsa = smem_u32(sHs + b * C::kHsBytes), tD = tmem_base + C::kDS + b * 64;
-            mbar_wait(&hs_full[b], phb[b]);
+            st[g] = 1;
+          } else if (st[g] == 1) {
+            // ---- MMA-2: D2 = h1.[w1|w2|w3] + h2.[w1|w2], A = Hs read K-major ----
+            if (!mbar_try(&hs_full[g], ph[g])) continue;
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, k)), umma_desc_sw128(w2a + k * 32), id2a, k ? 1u : 0u);
 #pragma unroll
               for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, HP / 16 + k)), umma_desc_sw128(w2a + k * 32), id2b, 1u);
-              tc_commit(&d2_full[b]);
+              tc_commit(&d2_full[g]);
             }
             __syncwarp();
-          }
-          // ---- G2[b] += Hs^T . Ds (K = rows; all 64 Ds columns, the 32 of buffer b are meaningful), then
-          //      MMA-3: D3 = do_hi.w1 + do_hi.w2 + do_lo.w1 ----
-          for (int b = 0; b < nb; ++b) {
-            const uint32_t hsa = smem_u32(sHs + b * C::kHsBytes), tD = tmem_base + C::kDS + b * 64, tG2 = tmem_base + C::kG2 + b * 64;
-            mbar_wait(&ds_full[b], phb[b]);
+            st[g] = 2;
+          } else if (st[g] == 2) {
+            // ---- G2[g] += Hs^T . Ds (K = rows; all 64 Ds columns are multiplied, the 32 of group g are meaningful and the only ones
+            //      read out), then MMA-3: D3 = do_hi.w1 + do_hi.w2 + do_lo.w1 ----
+            if (!mbar_try(&ds_full[g], ph[g])) continue;
             tc_fence_after();
-            const uint32_t da = dsa + b * 64;
+            const uint32_t da = dsa + g * 64;
+            const uint32_t first = (tile[g] < 2) ? 0u : 1u;
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < kTileM / 16; ++k)
-                tc_mma_bf16(tG2, desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), desc_mn(dsa + k * 2048, 0), idg2, (q | k) ? 1u : 0u);
+                tc_mma_bf16(tG2, desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), desc_mn(dsa + k * 2048, 0), idg2, (k ? 1u : first));
               tc_mma_bf16(tD, umma_desc_sw128(da), umma_desc_sw128(w2ta), id3, 0u);
               tc_mma_bf16(tD, umma_desc_sw128(da), umma_desc_sw128(w2ta + 32), id3, 1u);
               tc_mma_bf16(tD, umma_desc_sw128(da + 32), umma_desc_sw128(w2ta), id3, 1u);
-              tc_commit(&d3_full[b]);
+              tc_commit(&d3_full[g]);
             }
             __syncwarp();
-          }
-          // ---- G1 += X^T . Hs(dh) (K = rows) ----
-          for (int b = 0; b < nb; ++b) {
-            const uint32_t xa = smem_u32(sA + b * C::kAStage), hsa = smem_u32(sHs + b * C::kHsBytes);
-            mbar_wait(&dh_full[b], phb[b]);
-            phb[b] ^= 1;
+            st[g] = 3;
+          } else {
+            // ---- G1 += X^T . Hs(dh) (K = rows); the X stage is free afterwards ----
+            if (!mbar_try(&dh_full[g], ph[g])) continue;
             tc_fence_after();
+            const uint32_t first = g1_started ? 1u : 0u;
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < kTileM / 16; ++k)
-                tc_mma_bf16(tG1, desc_mn(xa + k * 2048, NSLOT > 1 ? kBlk : 0), desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), idg1, (q | b | k) ? 1u : 0u);
-              tc_commit(&empty_a[b]);
+                tc_mma_bf16(tG1, desc_mn(xa + k * 2048, NSLOT > 1 ? kBlk : 0), desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), idg1, (k ? 1u : first));
+              tc_commit(&empty_a[s]);
             }
             __syncwarp();
+            g1_started = true;
+            ph[g] ^= 1;
+            tile[g] += 2;
+            st[g] = (tile[g] < n_tiles) ? 0 : 4;
           }
         }
-        if (elect_one()) {
-          tc_commit(g_full);
-          tc_commit(w_free);
-        }
-        __syncwarp();
       }
+      if (elect_one()) {
+        tc_commit(g_full);
+        tc_commit(w_free);
+      }
+      __syncwarp();
+      n_base += (uint32_t)n_tiles;
     }
   } else {
-    // ================= epilogue warps =================
-    const int quarter = warp & 3, slice = warp >> 2;
+    // ================= epilogue warps: group g = warp / 8 (tile stream), quarter = TMEM lanes 32 q.., half hf = which half of
+    // the hidden units (P1, P3) and of the outputs (P2) =================
+    const int grp = warp >> 3, quarter = warp & 3, hf = (warp >> 2) & 1;
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int O = p.O, D = p.D, H = p.H;
     float* sGrad = reinterpret_cast<float*>(sHs);        // [P] fp32 at the end of a chain (Hs is idle then)
-    uint32_t phb[2] = {0, 0};
+    uint8_t* hs = sHs + grp * C::kHsBytes;
+    const uint32_t tScr = tmem_base + lane_base + (uint32_t)(C::kDS + grp * 64);
+    uint32_t ph = 0;
     for (int item = blockIdx.x, c = 0; item < n_items; item += gridDim.x, ++c) {
       const Item w = get_item(item);
-      const int pos = w.pos, n_tiles = w.n_tiles, n_pairs = w.n_pairs;
-      const int64_t t_begin = w.t_begin;
-      float accB2[NRL];
+      const int pos = w.pos, n_tiles = w.n_tiles;
+      float accB2[NQ];
 #pragma unroll
-      for (int o = 0; o < NRL; ++o) accB2[o] = 0.f;
-      for (int q = 0; q < n_pairs; ++q) {
-        const int nb = (2 * q + 1 < n_tiles) ? 2 : 1;
-        float h[2][HW];
-        int y[2];
-        // ---- P1: h = sigmoid(D1), pieces -> Hs ----
+      for (int o = 0; o < NQ; ++o) accB2[o] = 0.f;
+      for (int t = grp; t < n_tiles; t += 2) {
+        float h[HW];
+        const int y = __ldg(p.y + (w.t_begin + t) * kTileM + row_in_tile);
+        // ---- P1: h = sigmoid(D1), pieces -> Hs. The epilogue is SFU bound: one shared reciprocal per four sigmoids and an integer
+        //      bf16 split instead of conversion instructions (see split_pack_bf16x2) ----
+        mbar_wait(&d1_full[grp], ph);
+        tc_fence_after();
+        constexpr int HB = (HW > 16) ? 16 : HW;          // hidden units per register batch
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          if (b < nb) {
-            y[b] = __ldg(p.y + (t_begin + 2 * q + b) * kTileM + row_in_tile);
-            uint8_t* hs = sHs + b * C::kHsBytes;
-            mbar_wait(&d1_full[b], phb[b]);
-            tc_fence_after();
-            uint32_t zr[HW];
-            tmem_ldN<HW>(tmem_base + lane_base + (uint32_t)(C::kDS + b * 64 + slice * HW), zr);
-            tmem_ld_wait();
-            // The epilogue is SFU bound: one shared reciprocal per four sigmoids and an integer bf16 split instead of
-            // conversion instructions (16 hidden units: 20 SFU operations instead of 80, see split_pack_bf16x2)
-            uint32_t h1[HW / 2], h2[HW / 2];
+        for (int j0 = 0; j0 < HW; j0 += HB) {
+          uint32_t zr[HB];
+          tmem_ldN<HB>(tScr + (uint32_t)(hf * HW + j0), zr);
+          tmem_ld_wait();
+          uint32_t h1[HB / 2], h2[HB / 2];
 #pragma unroll
-            for (int j = 0; j < HW; j += 4) {
-              sigmoid4_from_neg_log2e(__uint_as_float(zr[j]), __uint_as_float(zr[j + 1]), __uint_as_float(zr[j + 2]), __uint_as_float(zr[j + 3]),
-                                      h[b][j], h[b][j + 1], h[b][j + 2], h[b][j + 3]);
-              split_pack_bf16x2(h[b][j], h[b][j + 1], h1[j / 2], h2[j / 2]);
-              split_pack_bf16x2(h[b][j + 2], h[b][j + 3], h1[j / 2 + 1], h2[j / 2 + 1]);
-            }
-            store_row_packed<HW>(hs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, h1);
-            store_row_packed<HW>(hs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, h2);
-            fence_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hs_full[b]);
+          for (int j = 0; j < HB; j += 4) {
+            sigmoid4_from_neg_log2e(__uint_as_float(zr[j]), __uint_as_float(zr[j + 1]), __uint_as_float(zr[j + 2]), __uint_as_float(zr[j + 3]),
+                                    h[j0 + j], h[j0 + j + 1], h[j0 + j + 2], h[j0 + j + 3]);
+            split_pack_bf16x2(h[j0 + j], h[j0 + j + 1], h1[j / 2], h2[j / 2]);
+            split_pack_bf16x2(h[j0 + j + 2], h[j0 + j + 3], h1[j / 2 + 1], h2[j / 2 + 1]);
           }
+          const int col = hf * HW + j0;
+          store_row_packed<HB>(hs + (col >> 6) * kBlk, row_in_tile, col & 63, h1);
+          store_row_packed<HB>(hs + ((HP + col) >> 6) * kBlk, row_in_tile, (HP + col) & 63, h2);
         }
-        // ---- P2 (one slice per tile): output layer and its delta -> Ds ----
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hs_full[grp]);
+        // ---- P2: output layer and its delta -> Ds; the two halves of the group split the outputs ----
+        {
+          mbar_wait(&d2_full[grp], ph);
+          tc_fence_after();
+          uint32_t d0[NQ], d1[NQ], d2[NQ];
+          tmem_ldN<NQ>(tScr + (uint32_t)(hf * NQ), d0); tmem_ldN<NQ>(tScr + (uint32_t)(ON + hf * NQ), d1); tmem_ldN<NQ>(tScr + (uint32_t)(2 * ON + hf * NQ), d2);
+          tmem_ld_wait();
+          uint32_t dhi[NQ / 2], dlo[NQ / 2];
+          const bool live = (y >= 0);
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          if (b < nb && slice == ((2 * q + b) & 3)) {
-            mbar_wait(&d2_full[b], phb[b]);
-            tc_fence_after();
-            uint32_t d0[NRL], d1[NRL], d2[NRL];
-            const uint32_t ta = tmem_base + lane_base + C::kDS + b * 64;
-            tmem_ldN<NRL>(ta, d0); tmem_ldN<NRL>(ta + ON, d1); tmem_ldN<NRL>(ta + 2 * ON, d2);
-            tmem_ld_wait();
-            uint32_t dhi[ON / 2], dlo[ON / 2];
+          for (int o4 = 0; o4 < NQ; o4 += 4) {
+            float tt[4], out[4], dv[4];
 #pragma unroll
-            for (int o = NRL / 2; o < ON / 2; ++o) { dhi[o] = 0u; dlo[o] = 0u; }
-            const bool live = (y[b] >= 0);
-#pragma unroll
-            for (int o4 = 0; o4 < NRL; o4 += 4) {
-              float tt[4], out[4], dv[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int o = o4 + j;
-                tt[j] = (__uint_as_float(d0[o]) + __uint_as_float(d1[o])) + __uint_as_float(d2[o]);
-                if (!p.fold_bias) tt[j] += __ldg(p.bias2 + (int64_t)pos * ON + o);
-              }
-              sigmoid4_from_neg_log2e(tt[0], tt[1], tt[2], tt[3], out[0], out[1], out[2], out[3]);   // columns >= O hold t = 0: finite, masked below
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int o = o4 + j;
-                dv[j] = (o < O && live) ? ((o == y[b] ? 1.0f : 0.0f) - out[j]) * (out[j] * (1.0f - out[j])) : 0.0f;     // LG:100
-                accB2[o] += dv[j];
-              }
-              split_pack_bf16x2(dv[0], dv[1], dhi[o4 / 2], dlo[o4 / 2]);
-              split_pack_bf16x2(dv[2], dv[3], dhi[o4 / 2 + 1], dlo[o4 / 2 + 1]);
+            for (int j = 0; j < 4; ++j) {
+              const int o = hf * NQ + o4 + j;
+              tt[j] = (__uint_as_float(d0[o4 + j]) + __uint_as_float(d1[o4 + j])) + __uint_as_float(d2[o4 + j]);
+              if (!p.fold_bias) tt[j] += __ldg(p.bias2 + (int64_t)pos * ON + o);
             }
-            store_row_packed<ON>(sDs, row_in_tile, 32 * b, dhi);
-            store_row_packed<ON>(sDs, row_in_tile, 32 * b + ON, dlo);
-            fence_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ds_full[b]);
+            sigmoid4_from_neg_log2e(tt[0], tt[1], tt[2], tt[3], out[0], out[1], out[2], out[3]);   // columns >= O hold t = 0: finite, masked below
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int o = hf * NQ + o4 + j;
+              dv[j] = (o < O && live) ? ((o == y ? 1.0f : 0.0f) - out[j]) * (out[j] * (1.0f - out[j])) : 0.0f;     // LG:100
+              accB2[o4 + j] += dv[j];
+            }
+            split_pack_bf16x2(dv[0], dv[1], dhi[o4 / 2], dlo[o4 / 2]);
+            split_pack_bf16x2(dv[2], dv[3], dhi[o4 / 2 + 1], dlo[o4 / 2 + 1]);
           }
+          store_row_packed<NQ>(sDs, row_in_tile, 32 * grp + hf * NQ, dhi);
+          store_row_packed<NQ>(sDs, row_in_tile, 32 * grp + ON + hf * NQ, dlo);
+          fence_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ds_full[grp]);
         }
         // ---- P3: dh = (do . W2^T) h (1 - h), pieces -> Hs ----
+        mbar_wait(&d3_full[grp], ph);
+        ph ^= 1;
+        tc_fence_after();
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          if (b < nb) {
-            uint8_t* hs = sHs + b * C::kHsBytes;
-            mbar_wait(&d3_full[b], phb[b]);
-            phb[b] ^= 1;
-            tc_fence_after();
-            uint32_t zr[HW];
-            tmem_ldN<HW>(tmem_base + lane_base + (uint32_t)(C::kDS + b * 64 + slice * HW), zr);
-            tmem_ld_wait();
-            uint32_t g1[HW / 2], g2[HW / 2];
+        for (int j0 = 0; j0 < HW; j0 += HB) {
+          uint32_t zr[HB];
+          tmem_ldN<HB>(tScr + (uint32_t)(hf * HW + j0), zr);
+          tmem_ld_wait();
+          uint32_t g1[HB / 2], g2[HB / 2];
 #pragma unroll
-            for (int j = 0; j < HW; j += 2)
-              split_pack_bf16x2(__uint_as_float(zr[j]) * (h[b][j] * (1.0f - h[b][j])),                 // LG:101
-                                __uint_as_float(zr[j + 1]) * (h[b][j + 1] * (1.0f - h[b][j + 1])), g1[j / 2], g2[j / 2]);
-            store_row_packed<HW>(hs + ((slice * HW) >> 6) * kBlk, row_in_tile, (slice * HW) & 63, g1);
-            store_row_packed<HW>(hs + ((HP + slice * HW) >> 6) * kBlk, row_in_tile, (HP + slice * HW) & 63, g2);
-            fence_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&dh_full[b]);
-          }
+          for (int j = 0; j < HB; j += 2)
+            split_pack_bf16x2(__uint_as_float(zr[j]) * (h[j0 + j] * (1.0f - h[j0 + j])),                 // LG:101
+                              __uint_as_float(zr[j + 1]) * (h[j0 + j + 1] * (1.0f - h[j0 + j + 1])), g1[j / 2], g2[j / 2]);
+          const int col = hf * HW + j0;
+          store_row_packed<HB>(hs + (col >> 6) * kBlk, row_in_tile, col & 63, g1);
+          store_row_packed<HB>(hs + ((HP + col) >> 6) * kBlk, row_in_tile, (HP + col) & 63, g2);
         }
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dh_full[grp]);
       }
-      // ---- end of the chain: fold the accumulators into one fp32 gradient vector ----
+      // ---- end of the chain: fold the accumulators into one fp32 gradient vector (all 16 warps) ----
       mbar_wait(g_full, c & 1);
       tc_fence_after();
       const int P = p.P;
       for (int i = threadIdx.x; i < P; i += 32 * kEpiWarps) sGrad[i] = 0.f;
       epi_sync();
       {
-        // G1: TMEM lane m = column m of the X image tile; this warp reads columns [slice * NG1/4, +NG1/4)
+        // G1: TMEM lane m = column m of the X image tile; warp (slice = warp / 4) reads columns [slice * NG1/4, +NG1/4)
+        const int slice = warp >> 2;
         const int m = row_in_tile;
         const int piece = m / DW, d = m - piece * DW;
         const bool is_w = (piece < (DKC <= 2 ? 3 : 2)) && (d < D);   // DKC = 1: lanes >= 64 repeat the block and fall out here
@@ -493,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
             }
           }
         }
-        // G2[b]: TMEM lane m = [h1 (HP) | h2 (HP)] hidden index; columns 32 b + [do_hi (16) | do_lo (16)]; slice s reads 8 of the 32
+        // G2[g]: TMEM lane m = [h1 (HP) | h2 (HP)] hidden index; columns 32 g + [do_hi (16) | do_lo (16)]; slice s reads 8 of the 32
         const int hh2 = m < HP ? m : m - HP;
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
@@ -511,9 +534,9 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
           }
         }
 #pragma unroll
-        for (int o = 0; o < NRL; ++o) {
+        for (int o = 0; o < NQ; ++o) {
           const float sres = warp_sum(accB2[o]);
-          if (lane == 0 && o < O) atomicAdd(&sGrad[D * H + H * O + H + o], -sres);       // LG:103: B2 += -do
+          if (lane == 0 && hf * NQ + o < O) atomicAdd(&sGrad[D * H + H * O + H + hf * NQ + o], -sres);       // LG:103: B2 += -do
         }
       }
       tc_fence_before();
@@ -589,7 +612,7 @@ int launch_langevin_tc(sapt_problem* p, const float* theta, float* theta_gd, int
   __nv_bfloat16* w2timg = reinterpret_cast<__nv_bfloat16*>(ws + up(part_bytes) + up(b1_bytes) + up(w2_bytes));
   float* bias2 = reinterpret_cast<float*>(ws + up(part_bytes) + up(b1_bytes) + up(w2_bytes) + up(w2t_bytes));
 
-  if ((rc = launch_tc2_pack(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, ON, 1, DKC, KROW, b1img, w2img, bias2, R, st))) return rc;
+  if ((rc = launch_tc2_pack(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, ON, 1, DKC, KROW, DKC >= 3 ? 1 : 0, b1img, w2img, bias2, R, st))) return rc;
   lt_pack_w2t_kernel<<<R, 256, 0, st>>>(theta, ld, rows, n_rows, R, p->D, p->H, p->O, HP, w2timg);
   SAPT_CHECK_LAUNCH();
   CUtensorMap mb1, mw2, mw2t;

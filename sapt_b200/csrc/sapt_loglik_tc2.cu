@@ -212,8 +212,8 @@ __global__ void tc2_pack_kernel(const float* theta, int64_t ld, const int32_t* r
 }
 
 int launch_tc2_pack(const float* theta, int64_t ld, const int32_t* rows, const int32_t* n_rows, int R, int D, int H, int O, int HP, int ON, int CH,
-                    int DKC, int KROW, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2, int n_blocks, cudaStream_t st) {
-  tc2_pack_kernel<<<n_blocks, 256, 0, st>>>(theta, ld, rows, n_rows, R, D, H, O, HP, ON, CH, DKC, KROW, 0, 0, b1img, w2img, bias2);   // three bf16 pieces
+                    int DKC, int KROW, int biasx, __nv_bfloat16* b1img, __nv_bfloat16* w2img, float* bias2, int n_blocks, cudaStream_t st) {
+  tc2_pack_kernel<<<n_blocks, 256, 0, st>>>(theta, ld, rows, n_rows, R, D, H, O, HP, ON, CH, DKC, KROW, biasx, 0, b1img, w2img, bias2);   // three bf16 pieces
   SAPT_CHECK_LAUNCH();
   return SAPT_OK;
 }
