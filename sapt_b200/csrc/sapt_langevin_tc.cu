@@ -26,6 +26,8 @@
 // Warp 16 lane 0: TMA producer (X tile ring; per-chain weight panels). Warp 17: TMEM alloc + MMA issue. Warps 0-15:
 // epilogue, warp (quarter q = TMEM lanes 32q.., slice s = HP/4 hidden units); P2 of tile t is done by slice t % 4.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 #include <vector>
 
@@ -44,8 +46,8 @@ int launch_langevin_batch_finalize(const float* part, int n_chunks, int R, int P
 namespace lt {
 constexpr int kTileM = 128;
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = 32 * (2 + kEpiWarps);
-constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int kThreads = 32 * (3 + kEpiWarps);
+constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;      // MMA issuers: warp kMmaWarp (tile stream 0) and kMmaWarp + 1 (stream 1)
 constexpr int ON = 16;                    // outputs padded (O <= 16)
 constexpr int N2 = 3 * ON;
 constexpr uint32_t kBlk = 128 * 128;      // one 64-column block of a 128-row tile
@@ -81,9 +83,9 @@ struct Cfg {
     return 1024u + NSTAGE * kAStage + 2 * kHsBytes + kBlk + ((kB1Bytes + 1023u) & ~1023u) + ((kW2TBytes + 1023u) & ~1023u) +
            ((kW2Bytes + 1023u) & ~1023u) + 512u;
   }
-  // TMEM columns: scratch D1/D2/D3 per group | G1 | G2 per group
-  static constexpr int kDS = 0, kG1 = 128, kG2 = 128 + NG1, kCols = 512;
-  static_assert(128 + NG1 + 128 <= kCols && HP <= 64 && N2 <= 64, "TMEM budget");
+  // TMEM columns: scratch D1/D2/D3 per group | G1 per group | G2 per group
+  static constexpr int kDS = 0, kG1 = 128, kG2 = 128 + 2 * NG1, kCols = 512;
+  static_assert(128 + 2 * NG1 + 128 <= kCols && HP <= 64 && N2 <= 64, "TMEM budget");
   // column of ones in the X image that turns -sum(dh) into a row of G1 (see tc_prepare_dataset)
   __host__ __device__ static constexpr int ones_col(int D) { return DKC <= 2 ? 3 * DW : D; }
 };
@@ -97,7 +99,11 @@ struct Params {
   int n_chunks;                       // work item = (chain, row chunk); item i runs on CTA i % gridDim.x
   float* part;                        // [chunk][R][P]
   int P;
+  long long* trace;                   // development: clock64 stamps of CTA 0 (SAPT_LT_TRACE=1), else null
 };
+// development trace: event e of tile-visit n (first 64) of a role; roles: 0 = epilogue group 0 warp 0, 1 = group 1 warp 8, 2 / 3 = MMA warp (group 0 / 1)
+#define LT_TRACE2(role, n, e) do { if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[((role) * 64 + (n)) * 8 + (e)] = clock64(); } while (0)
+#define LT_TRACE(role, n, e) do { if (p.trace && blockIdx.x == 0 && lane == 0 && c == 0 && (n) < 64) p.trace[((role) * 64 + (n)) * 8 + (e)] = clock64(); } while (0)
 
 __device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {   // MN-major, SWIZZLE_128B
   uint64_t d = 0;
@@ -120,21 +126,6 @@ __device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[N]) {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
-
-// one poll of an mbarrier phase with a short suspend hint (the MMA warp serves two tile streams and must not block on either)
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(done)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(64u)
-      : "memory");
-  return __all_sync(0xffffffffu, done != 0);
-}
 
 // writes n bf16 values (n = 4, 8 or 16; packed pairs, N/2 words) of one data row into a swizzled [128 rows][64 bf16] block at column col0
 template <int N>
@@ -185,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
                                                                   const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2t,
                                                                   Params p) {
   using C = Cfg<HP, DK>;
-  constexpr int DKC = C::DKC, NRL = C::NRL, NQ = C::NQ, NSTAGE = C::NSTAGE;
+  constexpr int DKC = C::DKC, NQ = C::NQ, NSTAGE = C::NSTAGE;
   constexpr int DW = C::DW, NSLOT = C::NSLOT, NBH = C::NBH, HW = C::HW, NG1 = C::NG1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -232,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
       mbar_init(&d1_full[g], 1); mbar_init(&hs_full[g], kEpiWarps / 2); mbar_init(&d2_full[g], 1); mbar_init(&ds_full[g], kEpiWarps / 2);
       mbar_init(&d3_full[g], 1); mbar_init(&dh_full[g], kEpiWarps / 2);
     }
-    mbar_init(w_full, 1); mbar_init(w_free, 1); mbar_init(g_full, 1); mbar_init(g_free, kEpiWarps);
+    mbar_init(w_full, 1); mbar_init(w_free, 2); mbar_init(g_full, 2); mbar_init(g_free, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // Ds columns that no output phase writes (outputs >= NRL, and the columns past [do_hi | do_lo]) are operands of MMA-3 / G2: zero once
@@ -272,110 +263,104 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
         __syncwarp();
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ================= MMA issuer: converged warp (polls, descriptor arithmetic on the uniform datapath), an elected lane issues
-    // tcgen05.mma / commit — under `if (lane == 0)` every MMA cost ~100 cycles of ELECT / R2UR.BROADCAST / BRA.U.ANY (see elect_one) ====
+  } else if (warp >= kMmaWarp) {
+    // ================= MMA issuers: one warp per tile stream (g = warp - kMmaWarp), each blocking on its own stream's barriers; the
+    // warp stays converged (waits, descriptor arithmetic on the uniform datapath) and an elected lane issues tcgen05.mma / commit —
+    // under `if (lane == 0)` every MMA cost ~100 cycles of ELECT / R2UR.BROADCAST / BRA.U.ANY (see elect_one). A single issuer
+    // serving both streams by polling was measured slower: tcgen05.mma issue blocks while the pipe is busy, so each stream's next
+    // batch waited for the other stream's batch to be ISSUED, and a failed timed poll costs ~450 cycles. ====
+    const int g = warp - kMmaWarp;
     const uint32_t id1 = idesc_bf16(kTileM, HP, false, false);
     const uint32_t id2a = idesc_bf16(kTileM, N2, false, false), id2b = idesc_bf16(kTileM, 2 * ON, false, false);
     const uint32_t id3 = idesc_bf16(kTileM, HP, false, false);
     const uint32_t idg2 = idesc_bf16(128, 64, true, true), idg1 = idesc_bf16(128, NG1, true, true);
-    const uint32_t b1a = smem_u32(sB1), w2a = smem_u32(sW2), w2ta = smem_u32(sW2T), dsa = smem_u32(sDs);
-    const uint32_t tG1 = tmem_base + C::kG1;
-    // shared-memory chunk (16 bf16 = 32 B) -> address inside a tile / panel made of 64-column blocks
-    auto a_chunk = [&](uint32_t base, int chunk) { return base + (uint32_t)(chunk >> 2) * kBlk + (uint32_t)(chunk & 3) * 32; };
-    auto b1_chunk = [&](int chunk) { return b1a + (uint32_t)(chunk >> 2) * (HP * 128) + (uint32_t)(chunk & 3) * 32; };
+    // Operand descriptors: the address field is the low 14 bits (address >> 4) and shared memory ends below 256 KB, so the descriptor
+    // of base + offset is descriptor(base) + (offset >> 4). The bases are built once; per tile one multiply-add selects the X stage,
+    // per MMA one add of a compile-time constant.
+    const uint64_t dXk0 = umma_desc_sw128(smem_u32(sA)), dXm0 = desc_mn(smem_u32(sA), NSLOT > 1 ? kBlk : 0);
+    const uint64_t hk = umma_desc_sw128(smem_u32(sHs + g * C::kHsBytes)), hm = desc_mn(smem_u32(sHs + g * C::kHsBytes), NBH > 1 ? kBlk : 0);
+    const uint64_t dB1 = umma_desc_sw128(smem_u32(sB1)), dW2 = umma_desc_sw128(smem_u32(sW2)), dW2T = umma_desc_sw128(smem_u32(sW2T));
+    const uint64_t da = umma_desc_sw128(smem_u32(sDs) + g * 64), dDsm = desc_mn(smem_u32(sDs), 0);   // da: the stream's 32 Ds columns
+    const uint32_t tD = tmem_base + C::kDS + g * 64, tG1 = tmem_base + C::kG1 + g * NG1, tG2 = tmem_base + C::kG2 + g * 64;
+    // shared-memory chunk (16 bf16 = 32 B) -> descriptor offset inside a tile / panel made of 64-column blocks
+    auto a_off = [](int chunk) { return (uint64_t)(((uint32_t)(chunk >> 2) * kBlk + (uint32_t)(chunk & 3) * 32) >> 4); };
+    auto b1_off = [](int chunk) { return (uint64_t)(((uint32_t)(chunk >> 2) * (HP * 128) + (uint32_t)(chunk & 3) * 32) >> 4); };
     uint32_t n_base = 0;                      // tiles of earlier items (the X ring runs across items)
-    uint32_t ph[2] = {0, 0};                  // parity of the per-group barriers: they complete once per tile of the group
+    uint32_t ph = 0;                          // parity of the stream's barriers: they complete once per tile of the stream
     for (int item = blockIdx.x, c = 0; item < n_items; item += gridDim.x, ++c) {
       const Item w = get_item(item);
       const int n_tiles = w.n_tiles;
       mbar_wait(w_full, c & 1);
+      if (c == 1) LT_TRACE2(2 + g, 62, 0);
       if (c > 0) mbar_wait(g_free, (c - 1) & 1);     // accumulators of the previous item have been read out
+      if (c == 1) LT_TRACE2(2 + g, 62, 1);
       tc_fence_after();
-      int tile[2] = {0, 1};
-      int st[2] = {n_tiles > 0 ? 0 : 4, n_tiles > 1 ? 0 : 4};   // 0: MMA-1, 1: MMA-2, 2: G2 + MMA-3, 3: G1, 4: done
-      bool g1_started = false;
-      while (st[0] != 4 || st[1] != 4) {
+      for (int t = g; t < n_tiles; t += 2) {
+        const uint32_t n = n_base + (uint32_t)t;
+        const uint32_t s = n % NSTAGE;
+        const uint64_t xk = dXk0 + (uint64_t)(s * (C::kAStage >> 4)), xm = dXm0 + (uint64_t)(s * (C::kAStage >> 4));
+        const uint32_t first = (t < 2) ? 0u : 1u;
+        // ---- MMA-1: x1w1 x1w2 x2w1 (+ bias chunk). x chunks: x1 = [0, DKC), x2 = [DKC, 2 DKC) ----
+        // Three piece products: the dropped x1w3 / x2w2 terms are 2^-16 |x w|, i.e. ~1e-4 absolute on a pre-activation, zero-mean
+        // over rows — far inside the 1e-4 (relative to max |g|) the gradient needs. (The likelihood kernel keeps fp32-grade
+        // products: an MH decision hangs on a difference of sums over all rows.) The scratch block is free (P3 of the stream's
+        // previous tile has read D3: dh_full was waited for) and Hs is not written before this batch — issued after that tile's
+        // G1 — has completed.
+        mbar_wait(&full_a[s], (n / NSTAGE) & 1);
+        LT_TRACE(2 + g, t >> 1, 0);
+        if (c == 1 && t < 2) LT_TRACE2(2 + g, 62, 2);
+        tc_fence_after();
+        constexpr int pa[3] = {0, 0, 1};
+        constexpr int pb[3] = {0, 1, 0};
+        if (elect_one()) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (st[g] == 4) continue;
-          const uint32_t n = n_base + (uint32_t)tile[g];
-          const uint32_t s = n % NSTAGE;
-          const uint32_t xa = smem_u32(sA + s * C::kAStage), hsa = smem_u32(sHs + g * C::kHsBytes);
-          const uint32_t tD = tmem_base + C::kDS + g * 64, tG2 = tmem_base + C::kG2 + g * 64;
-          if (st[g] == 0) {
-            // ---- MMA-1: x1w1 x1w2 x2w1 (+ bias chunk). x chunks: x1 = [0, DKC), x2 = [DKC, 2 DKC) ----
-            // Three piece products: the dropped x1w3 / x2w2 terms are 2^-16 |x w|, i.e. ~1e-4 absolute on a pre-activation, zero-mean
-            // over rows — far inside the 1e-4 (relative to max |g|) the gradient needs. (The likelihood kernel keeps fp32-grade
-            // products: an MH decision hangs on a difference of sums over all rows.) The scratch block is free (P3 of the group's
-            // previous tile has read D3: dh_full was seen in state 3) and Hs is not written before this batch — issued after that
-            // tile's G1 — has completed.
-            if (!mbar_try(&full_a[s], (n / NSTAGE) & 1)) continue;
-            tc_fence_after();
-            constexpr int pa[3] = {0, 0, 1};
-            constexpr int pb[3] = {0, 1, 0};
-            if (elect_one()) {
+          for (int k = 0; k < 3; ++k)
 #pragma unroll
-              for (int k = 0; k < 3; ++k)
-#pragma unroll
-                for (int j = 0; j < DKC; ++j)
-                  tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, pa[k] * DKC + j)), umma_desc_sw128(b1_chunk(pb[k] * DKC + j)), id1, (k | j) ? 1u : 0u);
-              if constexpr (!C::BIASX) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(xa, C::BIAS_CHUNK)), umma_desc_sw128(b1_chunk(C::BIAS_CHUNK)), id1, 1u);
-              tc_commit(&d1_full[g]);
-            }
-            __syncwarp();
-            st[g] = 1;
-          } else if (st[g] == 1) {
-            // ---- MMA-2: D2 = h1.[w1|w2|w3] + h2.[w1|w2], A = Hs read K-major ----
-            if (!mbar_try(&hs_full[g], ph[g])) continue;
-            tc_fence_after();
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, k)), umma_desc_sw128(w2a + k * 32), id2a, k ? 1u : 0u);
-#pragma unroll
-              for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, umma_desc_sw128(a_chunk(hsa, HP / 16 + k)), umma_desc_sw128(w2a + k * 32), id2b, 1u);
-              tc_commit(&d2_full[g]);
-            }
-            __syncwarp();
-            st[g] = 2;
-          } else if (st[g] == 2) {
-            // ---- G2[g] += Hs^T . Ds (K = rows; all 64 Ds columns are multiplied, the 32 of group g are meaningful and the only ones
-            //      read out), then MMA-3: D3 = do_hi.w1 + do_hi.w2 + do_lo.w1 ----
-            if (!mbar_try(&ds_full[g], ph[g])) continue;
-            tc_fence_after();
-            const uint32_t da = dsa + g * 64;
-            const uint32_t first = (tile[g] < 2) ? 0u : 1u;
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < kTileM / 16; ++k)
-                tc_mma_bf16(tG2, desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), desc_mn(dsa + k * 2048, 0), idg2, (k ? 1u : first));
-              tc_mma_bf16(tD, umma_desc_sw128(da), umma_desc_sw128(w2ta), id3, 0u);
-              tc_mma_bf16(tD, umma_desc_sw128(da), umma_desc_sw128(w2ta + 32), id3, 1u);
-              tc_mma_bf16(tD, umma_desc_sw128(da + 32), umma_desc_sw128(w2ta), id3, 1u);
-              tc_commit(&d3_full[g]);
-            }
-            __syncwarp();
-            st[g] = 3;
-          } else {
-            // ---- G1 += X^T . Hs(dh) (K = rows); the X stage is free afterwards ----
-            if (!mbar_try(&dh_full[g], ph[g])) continue;
-            tc_fence_after();
-            const uint32_t first = g1_started ? 1u : 0u;
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < kTileM / 16; ++k)
-                tc_mma_bf16(tG1, desc_mn(xa + k * 2048, NSLOT > 1 ? kBlk : 0), desc_mn(hsa + k * 2048, NBH > 1 ? kBlk : 0), idg1, (k ? 1u : first));
-              tc_commit(&empty_a[s]);
-            }
-            __syncwarp();
-            g1_started = true;
-            ph[g] ^= 1;
-            tile[g] += 2;
-            st[g] = (tile[g] < n_tiles) ? 0 : 4;
-          }
+            for (int j = 0; j < DKC; ++j)
+              tc_mma_bf16(tD, xk + a_off(pa[k] * DKC + j), dB1 + b1_off(pb[k] * DKC + j), id1, (k | j) ? 1u : 0u);
+          if constexpr (!C::BIASX) tc_mma_bf16(tD, xk + a_off(C::BIAS_CHUNK), dB1 + b1_off(C::BIAS_CHUNK), id1, 1u);
+          tc_commit(&d1_full[g]);
         }
+        __syncwarp();
+        // ---- MMA-2: D2 = h1.[w1|w2|w3] + h2.[w1|w2], A = Hs read K-major ----
+        mbar_wait(&hs_full[g], ph);
+        LT_TRACE(2 + g, t >> 1, 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, hk + a_off(k), dW2 + (uint64_t)(k * 2), id2a, k ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < HP / 16; ++k) tc_mma_bf16(tD, hk + a_off(HP / 16 + k), dW2 + (uint64_t)(k * 2), id2b, 1u);
+          tc_commit(&d2_full[g]);
+        }
+        __syncwarp();
+        // ---- G2[g] += Hs^T . Ds (K = rows; all 64 Ds columns are multiplied, the 32 of stream g are meaningful and the only ones
+        //      read out), then MMA-3: D3 = do_hi.w1 + do_hi.w2 + do_lo.w1 ----
+        mbar_wait(&ds_full[g], ph);
+        LT_TRACE(2 + g, t >> 1, 2);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kTileM / 16; ++k) tc_mma_bf16(tG2, hm + (uint64_t)(k * 128), dDsm + (uint64_t)(k * 128), idg2, (k ? 1u : first));
+          tc_mma_bf16(tD, da, dW2T, id3, 0u);
+          tc_mma_bf16(tD, da, dW2T + 2, id3, 1u);
+          tc_mma_bf16(tD, da + 2, dW2T, id3, 1u);
+          tc_commit(&d3_full[g]);
+        }
+        __syncwarp();
+        // ---- G1[g] += X^T . Hs(dh) (K = rows); the X stage is free afterwards ----
+        mbar_wait(&dh_full[g], ph);
+        LT_TRACE(2 + g, t >> 1, 3);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kTileM / 16; ++k) tc_mma_bf16(tG1, xm + (uint64_t)(k * 128), hm + (uint64_t)(k * 128), idg1, (k ? 1u : first));
+          tc_commit(&empty_a[s]);
+        }
+        __syncwarp();
+        ph ^= 1;
       }
-      if (elect_one()) {
+      if (elect_one()) {      // each issuer's commits cover its own MMAs: the barriers count both
         tc_commit(g_full);
         tc_commit(w_free);
       }
@@ -404,7 +389,10 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
         const int y = __ldg(p.y + (w.t_begin + t) * kTileM + row_in_tile);
         // ---- P1: h = sigmoid(D1), pieces -> Hs. The epilogue is SFU bound: one shared reciprocal per four sigmoids and an integer
         //      bf16 split instead of conversion instructions (see split_pack_bf16x2) ----
+        const bool tr = (quarter == 0 && hf == 0);
+        if (tr) LT_TRACE(grp, t >> 1, 6);
         mbar_wait(&d1_full[grp], ph);
+        if (tr) LT_TRACE(grp, t >> 1, 0);
         tc_fence_after();
         constexpr int HB = (HW > 16) ? 16 : HW;          // hidden units per register batch
 #pragma unroll
@@ -428,9 +416,11 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&hs_full[grp]);
+        if (tr) LT_TRACE(grp, t >> 1, 1);
         // ---- P2: output layer and its delta -> Ds; the two halves of the group split the outputs ----
         {
           mbar_wait(&d2_full[grp], ph);
+          if (tr) LT_TRACE(grp, t >> 1, 2);
           tc_fence_after();
           uint32_t d0[NQ], d1[NQ], d2[NQ];
           tmem_ldN<NQ>(tScr + (uint32_t)(hf * NQ), d0); tmem_ldN<NQ>(tScr + (uint32_t)(ON + hf * NQ), d1); tmem_ldN<NQ>(tScr + (uint32_t)(2 * ON + hf * NQ), d2);
@@ -462,9 +452,11 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&ds_full[grp]);
+          if (tr) LT_TRACE(grp, t >> 1, 3);
         }
         // ---- P3: dh = (do . W2^T) h (1 - h), pieces -> Hs ----
         mbar_wait(&d3_full[grp], ph);
+        if (tr) LT_TRACE(grp, t >> 1, 4);
         ph ^= 1;
         tc_fence_after();
 #pragma unroll
@@ -485,65 +477,110 @@ __global__ void __launch_bounds__(kThreads, 1) langevin_tc_kernel(const __grid_c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&dh_full[grp]);
+        if (tr) LT_TRACE(grp, t >> 1, 5);
       }
       // ---- end of the chain: fold the accumulators into one fp32 gradient vector (all 16 warps) ----
+      if (warp == 0 && c == 0) LT_TRACE2(0, 62, 0);
       mbar_wait(g_full, c & 1);
+      if (warp == 0 && c == 0) LT_TRACE2(0, 62, 1);
       tc_fence_after();
       const int P = p.P;
-      for (int i = threadIdx.x; i < P; i += 32 * kEpiWarps) sGrad[i] = 0.f;
-      epi_sync();
+      if (warp == 0 && c == 0) LT_TRACE2(0, 62, 2);
+      // Fold without atomics (shared-memory float atomics are compare-and-swap loops: the first version spent ~43 000 cycles per item
+      // here, 10 % of the kernel). Every (X piece, column d, hidden unit) / (h piece, hidden unit, output) has exactly ONE thread that
+      // holds all its accumulator columns (both tile streams, the hi and lo delta pieces), so each slot is written once with a plain
+      // store; the copy-out adds the pieces. Row strides are odd ([D][H|1], [H][O|1]): at a given instruction the lanes of a warp are
+      // different X columns / hidden units, and with the natural strides H / O (64, 16, 2 ...) their stores would share one bank.
+      constexpr int NPW = (DKC <= 2) ? 3 : 2;                 // X pieces among the 128 image columns of G1
+      const int HS = H | 1, OS = O | 1;
+      const int oW2 = NPW * D * HS, oB1 = oW2 + 2 * H * OS, oB2 = oB1 + H;      // then [16 warps][NQ] partial B2 sums
       {
-        // G1: TMEM lane m = column m of the X image tile; warp (slice = warp / 4) reads columns [slice * NG1/4, +NG1/4)
         const int slice = warp >> 2;
         const int m = row_in_tile;
+        // G1: TMEM lane m = column m of the X image tile; this warp sums, for its HP/4 hidden units, the dh_hi and dh_lo columns of both streams
         const int piece = m / DW, d = m - piece * DW;
-        const bool is_w = (piece < (DKC <= 2 ? 3 : 2)) && (d < D);   // DKC = 1: lanes >= 64 repeat the block and fall out here
+        const bool is_w = (piece < NPW) && (d < D);          // DKC = 1: lanes >= 64 repeat the block and fall out here
         const bool is_b = (m == C::ones_col(D));
-        constexpr int CW = NG1 / 4;       // 16 or 32 columns per warp
-        uint32_t r[CW];
-        const uint32_t ta = tmem_base + lane_base + (uint32_t)(C::kG1 + slice * CW);
-        if constexpr (CW == 32) tmem_ld32(ta, r); else tmem_ld16(ta, r);
-        tmem_ld_wait();
-        if (is_w || is_b) {
+        constexpr int CQ = HP / 4;
+        float acc[CQ];
 #pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const int n = slice * CW + j;                 // [dh_hi (HP) | dh_lo (HP)]
-            const int hh = n < HP ? n : n - HP;
-            if (n < 2 * HP && hh < H) {
-              const float v = __uint_as_float(r[j]);
-              if (is_w) atomicAdd(&sGrad[d * H + hh], v);                       // LG:104: W1 += x^T dh
-              else atomicAdd(&sGrad[D * H + H * O + hh], -v);                   // LG:105: B1 += -dh
-            }
-          }
-        }
-        // G2[g]: TMEM lane m = [h1 (HP) | h2 (HP)] hidden index; columns 32 g + [do_hi (16) | do_lo (16)]; slice s reads 8 of the 32
-        const int hh2 = m < HP ? m : m - HP;
+        for (int j = 0; j < CQ; ++j) acc[j] = 0.f;
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           if (b == 0 || n_tiles > 1) {
-            uint32_t r2[8];
-            tmem_ld8(tmem_base + lane_base + (uint32_t)(C::kG2 + b * 64 + 32 * b + slice * 8), r2);
-            tmem_ld_wait();
-            if (m < 2 * HP && hh2 < H) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int n = slice * 8 + j, o = n & 15;
-                if (o < O) atomicAdd(&sGrad[D * H + hh2 * O + o], __uint_as_float(r2[j]));   // LG:102: W2 += h^T do
-              }
+            for (int pc = 0; pc < 2; ++pc) {
+              uint32_t r[CQ];
+              tmem_ldN<CQ>(tmem_base + lane_base + (uint32_t)(C::kG1 + b * NG1 + pc * HP + slice * CQ), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < CQ; ++j) acc[j] += __uint_as_float(r[j]);
             }
           }
+        }
+        if (is_w || is_b) {
+#pragma unroll
+          for (int j = 0; j < CQ; ++j) {
+            const int hh = slice * CQ + j;
+            if (hh < H) {
+              if (is_w) sGrad[(piece * D + d) * HS + hh] = acc[j];                 // LG:104: W1 += x^T dh
+              else sGrad[oB1 + hh] = -acc[j];                                       // LG:105: B1 += -dh
+            }
+          }
+        }
+        // G2[g]: TMEM lane m = [h1 (HP) | h2 (HP)] hidden index; columns 32 g + [do_hi (16) | do_lo (16)]; this warp takes outputs 4 slice ..
+        const int hp2 = m < HP ? 0 : 1, hh2 = m - hp2 * HP;
+        float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          if (b == 0 || n_tiles > 1) {
+#pragma unroll
+            for (int pc = 0; pc < 2; ++pc) {
+              uint32_t r2[4];
+              tmem_ld4(tmem_base + lane_base + (uint32_t)(C::kG2 + b * 64 + 32 * b + pc * ON + slice * 4), r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc2[j] += __uint_as_float(r2[j]);
+            }
+          }
+        }
+        if (m < 2 * HP && hh2 < H) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (slice * 4 + j < O) sGrad[oW2 + (hp2 * H + hh2) * OS + slice * 4 + j] = acc2[j];   // LG:102: W2 += h^T do
         }
 #pragma unroll
         for (int o = 0; o < NQ; ++o) {
           const float sres = warp_sum(accB2[o]);
-          if (lane == 0 && hf * NQ + o < O) atomicAdd(&sGrad[D * H + H * O + H + hf * NQ + o], -sres);       // LG:103: B2 += -do
+          if (lane == 0) sGrad[oB2 + warp * NQ + o] = sres;                         // LG:103: B2 += -do (summed over the warps below)
         }
       }
       tc_fence_before();
       epi_sync();
+      if (warp == 0 && c == 0) LT_TRACE2(0, 62, 3);
       float* dst = p.part + ((int64_t)w.chunk * p.R + pos) * P;
-      for (int i = threadIdx.x; i < P; i += 32 * kEpiWarps) dst[i] = sGrad[i];
+      for (int i = threadIdx.x; i < P; i += 32 * kEpiWarps) {
+        int k = i;
+        float v = 0.f;
+        if (k < D * H) {
+          const int src = (k / H) * HS + (k % H);
+#pragma unroll
+          for (int pc = 0; pc < NPW; ++pc) v += sGrad[pc * D * HS + src];
+        } else if ((k -= D * H) < H * O) {
+          const int src = oW2 + (k / O) * OS + (k % O);
+          v = sGrad[src] + sGrad[src + H * OS];
+        } else if ((k -= H * O) < H) {
+          v = sGrad[oB1 + k];
+        } else {
+          k -= H;                                  // output k: warps with hf == k / NQ hold its partial sums
+          const int hfo = k / NQ, j = k - hfo * NQ;
+          for (int wq = 0; wq < kEpiWarps; ++wq)
+            if (((wq >> 2) & 1) == hfo) v -= sGrad[oB2 + wq * NQ + j];
+        }
+        dst[i] = v;
+      }
       epi_sync();
+      if (warp == 0 && c == 0) LT_TRACE2(0, 62, 4);
       fence_async_smem();     // Hs goes back to being an MMA operand
       if (lane == 0) mbar_arrive(g_free);
     }
@@ -623,6 +660,10 @@ int launch_langevin_tc(sapt_problem* p, const float* theta, float* theta_gd, int
   a.y = ds.y; a.bias2 = bias2; a.n_rows = n_rows; a.R = R; a.D = p->D; a.H = p->H; a.O = p->O; a.fold_bias = (p->H < HP) ? 1 : 0;
   a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.n_chunks = (int)n_chunks; a.part = part; a.P = P;
   dim3 grid((unsigned)std::min<int64_t>(p->num_sms, (int64_t)R * n_chunks));
+  static long long* d_trace = nullptr;
+  const bool want_trace = getenv("SAPT_LT_TRACE") != nullptr;
+  if (want_trace && !d_trace) { cudaMalloc(&d_trace, 4 * 64 * 8 * sizeof(long long)); }
+  if (want_trace) { cudaMemsetAsync(d_trace, 0, 4 * 64 * 8 * sizeof(long long), st); a.trace = d_trace; }
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(ds.tmap);
   const int DKX = (HP == 64 && p->O <= 8) ? DKC + 8 : DKC;   // narrow output phase, see Cfg
 #define SAPT_LT(H_, K_) if (HP == H_ && DKX == K_) rc = launch_variant<H_, K_>(ma, mb1, mw2, mw2t, a, grid, st); else
@@ -630,6 +671,24 @@ int launch_langevin_tc(sapt_problem* p, const float* theta, float* theta_gd, int
   SAPT_LT(64, 1) SAPT_LT(64, 2) SAPT_LT(64, 3) SAPT_LT(64, 4) SAPT_LT(64, 9) SAPT_LT(64, 10) SAPT_LT(64, 11) SAPT_LT(64, 12) { set_error("tcgen05 Langevin: no variant for HP=%d DKC=%d", HP, DKC); rc = SAPT_ERR_UNSUPPORTED; }
 #undef SAPT_LT
   if (rc) return rc;
+  if (want_trace) {
+    std::vector<long long> h(4 * 64 * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long t0 = h[(2 * 64 + 0) * 8 + 0];
+    const char* roles[4] = {"epi0", "epi1", "mma0", "mma1"};
+    for (int r = 0; r < 4; ++r) {
+      printf("trace %s e0 of visits 0..63:", roles[r]);
+      for (int n = 0; n < 64; ++n) { long long v = h[(r * 64 + n) * 8 + 0]; printf(" %lld", v ? v - t0 : -1); }
+      printf("\n");
+    }
+    for (int n = 6; n < 64; n += 8)
+      for (int r = 0; r < 4; ++r) {
+        printf("trace %s visit %2d:", roles[r], n);
+        for (int e = 0; e < 8; ++e) { long long v = h[(r * 64 + n) * 8 + e]; printf(" %8lld", v ? v - t0 : -1); }
+        printf("\n");
+      }
+  }
   return launch_langevin_batch_finalize(part, (int)n_chunks, R, P, theta, theta_gd, ld, rows, n_rows, lr_scale, st);
 }
 
