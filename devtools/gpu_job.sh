@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python devtools/lt_check.py > gpurun_out/j15_lt_check.txt 2>&1
-timeout 300 python devtools/lt_check.py 40-64-7 34-30-16 60-20-3 16-16-2 > gpurun_out/j15_lt_check2.txt 2>&1
-SAPT_LT_TRACE=1 timeout 300 python devtools/prof_kernels.py c4lt 64 > gpurun_out/j15_trace.txt 2>&1
-timeout 600 python devtools/ab_time.py c4 > gpurun_out/j15_ab.jsonl 2> gpurun_out/j15_ab.err
-grep -hv "^   " gpurun_out/j15_lt_check.txt gpurun_out/j15_lt_check2.txt; cat gpurun_out/j15_ab.jsonl
+timeout 1800 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 > gpurun_out/j22_pytest.txt
+timeout 600 python devtools/ab_time.py c3 c4 > gpurun_out/j22_ab.jsonl 2> gpurun_out/j22_ab.err
+python bench.py --steps 10 --warmup 3 > gpurun_out/j22_bench.json 2> gpurun_out/j22_bench.err
+tail -6 gpurun_out/j22_pytest.txt; cat gpurun_out/j22_ab.jsonl; tail -3 gpurun_out/j22_bench.err; cut -c1-400 gpurun_out/j22_bench.json

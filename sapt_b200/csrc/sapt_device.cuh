@@ -108,9 +108,11 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f
 
 // Four sigmoids s_i = scale / (1 + 2^min(t_i, lim)) with one reciprocal, packed: the results come out as the pairs
 // s10 = (s1, s0) and s32 = (s3, s2) (low lane first) — 4 FMNMX + 4 MUFU.EX2 + 2 FADD2 + 3 FMUL + MUFU.RCP + 3 FMUL2 (+1 FMUL for a scale)
+// (e0_out: the first 2^t, for callers that order successive groups on it)
 template <bool SCALED>
-__device__ __forceinline__ void sigmoid4_packed(float t0, float t1, float t2, float t3, float lim, float scale, f32x2& s10, f32x2& s32) {
+__device__ __forceinline__ void sigmoid4_packed_e(float t0, float t1, float t2, float t3, float lim, float scale, f32x2& s10, f32x2& s32, float& e0_out) {
   const float e0 = ex2_approx(fminf(t0, lim)), e1 = ex2_approx(fminf(t1, lim));
+  e0_out = e0;
   const float e2 = ex2_approx(fminf(t2, lim)), e3 = ex2_approx(fminf(t3, lim));
   const f32x2 one = pack2(1.0f, 1.0f);
   const f32x2 a01 = add2(pack2(e0, e1), one), a23 = add2(pack2(e2, e3), one);
@@ -123,6 +125,11 @@ __device__ __forceinline__ void sigmoid4_packed(float t0, float t1, float t2, fl
   unpack2(mul2(pack2(cd, ab), pack2(r, r)), rcd, rab);
   s10 = mul2(a01, pack2(rcd, rcd));   // (a0 r cd, a1 r cd) = (s1, s0)
   s32 = mul2(a23, pack2(rab, rab));   // (a2 r ab, a3 r ab) = (s3, s2)
+}
+template <bool SCALED>
+__device__ __forceinline__ void sigmoid4_packed(float t0, float t1, float t2, float t3, float lim, float scale, f32x2& s10, f32x2& s32) {
+  float e0;
+  sigmoid4_packed_e<SCALED>(t0, t1, t2, t3, lim, scale, s10, s32, e0);
 }
 
 // four sigmoids with ONE reciprocal:  s_i = 1 / a_i,  a_i = 1 + 2^min(t_i, 30)  (the clamp costs < 1e-9 and keeps the product of

@@ -33,6 +33,7 @@
 // pipelined (phase 1 of unit u+1 before phase 2 of unit u) so that every MMA has a full unit of slack before its
 // result is awaited.
 #include <algorithm>
+#include <cstdio>
 #include <type_traits>
 #include <vector>
 
@@ -56,7 +57,12 @@ namespace sapt {
 namespace v2 {
 constexpr int kTileM = 128;
 constexpr int kEpiWarps = 16;           // four per TMEM lane quarter
-constexpr int kThreads = 32 * (2 + kEpiWarps);
+#ifndef SAPT_MAXNREG
+#define SAPT_MAXNREG 0     // > 0: registers per epilogue thread after setmaxnreg (the producer warp group gives its share away)
+#endif
+// With SAPT_MAXNREG the two single-lane roles sit in a full warp group of their own (two idle warps added) so that setmaxnreg, a
+// warp-group instruction, can move registers from it to the four epilogue warp groups.
+constexpr int kThreads = 32 * ((SAPT_MAXNREG ? 4 : 2) + kEpiWarps);
 // The SMSP arbiter favours the highest warp id: the two single-thread roles that feed everyone else
 // (TMA producer, MMA issuer) sit above the epilogue warps so they are never starved by them. (Folding the
 // producer into the MMA thread was measured 2 % slower and frees no registers: warps are allocated in fours.)
@@ -121,9 +127,17 @@ struct Tc2Params {
   const float* bias2;            // [pos][ON] log2(e) * B2
   const int32_t* n_rows; int R;
   int O; int fold_bias;          // fold_bias: H < HP, the output bias is row H of the W2 image
+  uint32_t zero;                 // 0 at run time, unknown to the compiler: glues ordering-only dependencies (see phase 1)
   int tiles_per_chunk; int64_t n_tiles;
   double* partL; int32_t* partNc; int32_t* partSq;
+  long long* trace;              // development (-DSAPT_TC2_TRACE): clock64 stamps of CTA (0, 0)
 };
+// development trace: event e of unit u (first 64) of a role; roles 0..3 = epilogue warps 0, 4, 8, 12 (quarter 0, e = 0..3), 4 = MMA warp
+#ifdef SAPT_TC2_TRACE
+#define TC2_TRACE(role, u, e) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (u) < 64) p.trace[((role) * 64 + (u)) * 8 + (e)] = clock64(); } while (0)
+#else
+#define TC2_TRACE(role, u, e) do { } while (0)
+#endif
 
 // ---- per-step operand packing ------------------------------------------------------------------------
 // B1: [group][CH*HP rows][KBA*64] : row (chain, h) = [w1 (16 DKC) | w2 | w3 | b1 b2 b3 0..], w = -log2(e) W1[:, h]
@@ -252,8 +266,11 @@ __device__ __forceinline__ void sigmoid4_lim(float t0, float t1, float t2, float
 #ifndef SAPT_ELECT
 #define SAPT_ELECT 1      // single-thread instructions issued by an elected lane of a converged warp (0: `if (lane == 0)`, round 1)
 #endif
+#ifndef SAPT_P1_DEP
+#define SAPT_P1_DEP -1    // phase-1 ordering (see phase 1): 0 = groups ordered on a finished sigmoid, 1 = on the group's first 2^t, 2 = software
+#endif                    // pipeline over the quads; -1 = per shape (measured: 2 for HP <= 32, 1 with one-quad groups for HP = 64)
 #ifndef SAPT_P1_CHAIN
-#define SAPT_P1_CHAIN 2   // quads per ordered group in phase 1 (0: let ptxas schedule freely)
+#define SAPT_P1_CHAIN -1  // quads per ordered group in phase 1 (0: let ptxas schedule freely); -1 = per shape
 #endif
 
 // same, times a common factor: s_i = scale / a_i (the factor rides on the shared reciprocal)
@@ -344,6 +361,10 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_hv = tmem_base + kHvBase;
 
+#if SAPT_MAXNREG
+  if (warp >= kEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SAPT_MAXNREG));
+#endif
   if (warp == kTmaWarp) {
     // ================= TMA producer (the warp stays converged, one elected lane issues: see elect_one) =================
     if (SAPT_ELECT ? elect_one() : (lane == 0)) {
@@ -376,23 +397,25 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
       auto idesc = [](int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24); };
       const uint32_t idesc1 = C::XF16 ? ((1u << 4) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24)) : idesc(N1);
       const uint32_t idesc2a = idesc(N2), idesc2b = idesc(2 * ON), idesc2c = idesc(ON);
-      const uint32_t b1_addr = smem_u32(sB1);
-      const uint32_t w2_addr = smem_u32(sW2);
+      const uint64_t dA0 = umma_desc_sw128(smem_u32(sA)), dB10 = umma_desc_sw128(smem_u32(sB1)), dW20 = umma_desc_sw128(smem_u32(sW2));
       mbar_wait(b_full, 0);
       auto issue_mma1 = [&](int u) {
         const int it = u / UPT, uu = u - it * UPT;
         const int s = it % STAGES;
+        TC2_TRACE(4, u, 0);
         if (u > 0) mbar_wait(d1_empty, (u - 1) & 1);  // every warp holds D1(u-1) in registers
         if (uu == 0) mbar_wait(&full_a[s], (it / STAGES) & 1);
+        TC2_TRACE(4, u, 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + s * kAStage);
-        const uint32_t b_addr = b1_addr + (uint32_t)(uu * N1) * 128;
         // split product over (piece of x, piece of w): fp16 pieces x_hi w_hi, x_hi w_lo, x_lo w_hi; bf16 pieces x1w1 x1w2 x2w1 x1w3
         // x2w2 x3w1. DKC chunks of 16 features each, then the bias chunk. chunk c = 16 elements = 32 bytes inside K block c/4.
+        // Descriptors: the address field is the low 14 bits (address >> 4) and shared memory ends below 256 KB, so the descriptor of
+        // base + offset is descriptor(base) + (offset >> 4): one multiply-add per batch, one add of a constant per operand.
         constexpr int pa[6] = {0, 0, 1, 0, 1, 2};
         constexpr int pb[6] = {0, 1, 0, 2, 1, 0};
-        auto a_at = [&](int chunk) { return umma_desc_sw128(a_addr + (uint32_t)(chunk >> 2) * kABlock + (uint32_t)(chunk & 3) * 32); };
-        auto b_at = [&](int chunk) { return umma_desc_sw128(b_addr + (uint32_t)(chunk >> 2) * kB1Block + (uint32_t)(chunk & 3) * 32); };
+        const uint64_t a_base = dA0 + (uint64_t)((uint32_t)s * (kAStage >> 4)), b_base = dB10 + (uint64_t)((uint32_t)uu * ((N1 * 128) >> 4));
+        auto a_at = [&](int chunk) { return a_base + (uint64_t)(((uint32_t)(chunk >> 2) * kABlock + (uint32_t)(chunk & 3) * 32) >> 4); };
+        auto b_at = [&](int chunk) { return b_base + (uint64_t)(((uint32_t)(chunk >> 2) * kB1Block + (uint32_t)(chunk & 3) * 32) >> 4); };
         if (SAPT_ELECT ? elect_one() : true) {
 #pragma unroll
           for (int q = 0; q < C::NPROD; ++q)
@@ -413,31 +436,33 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
 #pragma unroll
         for (int c = 0; c < UC; ++c) {
           mbar_wait(&hv_full[(u & 1) * UC + c], (u >> 1) & 1);
+          if (c == 0) TC2_TRACE(4, u, 2);
+          if (c == UC - 1) TC2_TRACE(4, u, 3);
           tc_fence_after();
           const uint32_t d2 = tmem_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (UC * N2) + c * N2);
           const uint32_t hv = tmem_hv + (uint32_t)(c * HP);
-          const uint32_t wb = w2_addr + (uint32_t)(uu * UC + c) * kW2ChainBytes;
+          const uint64_t wb = dW20 + (uint64_t)((uint32_t)(uu * UC + c) * (kW2ChainBytes >> 4));
           // ON=16: D2[:, 0:3ON] = h1.[w1|w2|w3], D2[:, 0:2ON] += h2.[w1|w2]
           // ON=32: D2[:, 0:2ON] = h1.[w1|w2],    D2[:, 0:ON] += h1.w3,  D2[:, 0:2ON] += h2.[w1|w2]   (h piece = HP/2 columns)
           if (SAPT_ELECT ? elect_one() : true) {
 #pragma unroll
             for (int half = 0; half < HP / 16; ++half)
-              tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), umma_desc_sw128(wb + half * 32), idesc2a, half ? 1u : 0u);
+              tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), wb + (uint64_t)(half * 2), idesc2a, half ? 1u : 0u);
             if constexpr (ON == 32) {
 #pragma unroll
               for (int half = 0; half < HP / 16; ++half)
-                tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), umma_desc_sw128(wb + 2 * ON * 128 + half * 32), idesc2c, 1u);
+                tc_mma_bf16_ts(d2, hv + (uint32_t)(half * 8), wb + (uint64_t)((2 * ON * 128) >> 4) + (uint64_t)(half * 2), idesc2c, 1u);
             }
 #pragma unroll
             for (int half = 0; half < HP / 16; ++half)
-              tc_mma_bf16_ts(d2, hv + (uint32_t)(HP / 2 + half * 8), umma_desc_sw128(wb + half * 32), idesc2b, 1u);
+              tc_mma_bf16_ts(d2, hv + (uint32_t)(HP / 2 + half * 8), wb + (uint64_t)(half * 2), idesc2b, 1u);
             tc_commit(&d2_full[(u & 1) * UC + c]);
           }
           if (SAPT_ELECT) __syncwarp();
         }
       }
     }
-  } else {
+  } else if (warp < kEpiWarps) {
     // ================= epilogue warps =================
     // warp (quarter q, index e): TMEM lanes 32q.., chain c = e / HALVES of every unit, hidden units
     // [hf*HW, hf*HW + HW) with hf = e % HALVES. With HALVES = 2 the two warps of a chain alternate on phase 2.
@@ -453,33 +478,96 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
     // Software pipeline over units: phase 1 of unit u+1 (sigmoid + split, SIMT) runs while the tensor pipe
     // computes MMA-2 of unit u, so the warp never waits for D2 right after handing over its activations.
     uint32_t hv[HW];  // [h1 pairs (HW/2) | h2 pairs (HW/2)] of the unit whose phase 1 ran last
+    const bool trw = (quarter == 0) && (hf == 0);
     auto phase1 = [&](int u) {
+      if (trw) TC2_TRACE(c, u, 0);
       mbar_wait(d1_full, u & 1);
+      if (trw) TC2_TRACE(c, u, 1);
       tc_fence_after();
       uint32_t zr[HW];
       const uint32_t taddr = tmem_base + lane_base + (uint32_t)(c * HP + hf * HW);
-      if constexpr (HW == 32) tmem_ld32(taddr, zr); else tmem_ld16(taddr, zr);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d1_empty);  // D1 is in registers: the next MMA-1 may overwrite it
+      // (D1 in two halves when the quads are software pipelined: the second load's latency hides behind the first quads)
+      constexpr int kDep = (SAPT_P1_DEP >= 0) ? SAPT_P1_DEP : ((HP == 64) ? 1 : 2);
+      constexpr int kChain = (SAPT_P1_CHAIN >= 0) ? SAPT_P1_CHAIN : ((kDep == 1) ? 1 : 2);
+      constexpr bool kPipe = (kDep == 2) && (SAPT_F32X2 != 0);
+      constexpr bool kSplitD1 = kPipe && (HW == 32);
+      auto d1_loaded = [&]() {
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d1_empty);  // D1 is in registers: the next MMA-1 may overwrite it
+      };
+      if constexpr (kSplitD1) {
+        tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&zr[0]));
+        tmem_ld_wait();
+        tmem_ld16(taddr + 16, *reinterpret_cast<uint32_t(*)[16]>(&zr[HW / 2]));
+      } else {
+        if constexpr (HW == 32) tmem_ld32(taddr, zr); else tmem_ld16(taddr, zr);
+        d1_loaded();
+      }
       // ptxas would hoist all HW MUFU.EX2 to the front: a warp then monopolises the SFU queue for ~40 x 8 cycles
       // and leaves it idle for the ~200 instructions that follow, and so do its three SMSP neighbours. Chaining
       // the clamp limit of quad group k+1 to a result of group k (times zero: one FFMA per group, not foldable
       // under IEEE rules) keeps the groups in order, so SFU work and FP32/integer work alternate finely.
+      if constexpr (kPipe) {
+      // Software pipeline over the quads, in program order  A(0) A(1) B(0) A(2) B(1) A(3) ... B(7):  A(j) = clamp + four MUFU.EX2,
+      // B(j) = everything else of quad j (sum, shared reciprocal, products, bf16 split: ~27 instructions, one MUFU.RCP). The clamp
+      // limit of A(j+2) hangs on the first 2^t of A(j+1) (times zero: keeps the exponential groups in order) AND on the last word
+      // of B(j)'s split (and-ed with a run-time zero, one LOP3): so the SFU pipe gets five operations per ~35 instructions all the
+      // way through, instead of 40 in the first 140 instructions and none in the ~110 of the split that ptxas sinks to the end —
+      // the trace (SAPT_TC2_TRACE) showed the four warps of a scheduler in this phase together: 1 846 cycles for 1 280 of SFU work.
+      {
+        float ex[HW];
+        auto stage_a = [&](int j, float lim) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ex[4 * j + i] = ex2_approx(fminf(__uint_as_float(zr[4 * j + i]), lim));
+        };
+        auto stage_b = [&](int j) {
+          const f32x2 one = pack2(1.0f, 1.0f);
+          const f32x2 a01 = add2(pack2(ex[4 * j], ex[4 * j + 1]), one), a23 = add2(pack2(ex[4 * j + 2], ex[4 * j + 3]), one);
+          float a0, a1, a2, a3;
+          unpack2(a01, a0, a1); unpack2(a23, a2, a3);
+          const float ab = a0 * a1, cd = a2 * a3;
+          const float r = rcp_approx(ab * cd);
+          float rcd, rab;
+          unpack2(mul2(pack2(cd, ab), pack2(r, r)), rcd, rab);
+          const f32x2 s10 = mul2(a01, pack2(rcd, rcd));   // (a0 r cd, a1 r cd) = (s1, s0)
+          const f32x2 s32 = mul2(a23, pack2(rab, rab));   // (a2 r ab, a3 r ab) = (s3, s2)
+          float h0, h1, h2, h3;
+          unpack2(s10, h1, h0); unpack2(s32, h3, h2);
+          const uint32_t u0 = __float_as_uint(h0), u1 = __float_as_uint(h1), u2 = __float_as_uint(h2), u3 = __float_as_uint(h3);
+          hv[2 * j] = __byte_perm(u0, u1, 0x7632);
+          hv[2 * j + 1] = __byte_perm(u2, u3, 0x7632);
+          float r0, r1, r2, r3;
+          unpack2(sub2(s10, pack2(__uint_as_float(u1 & 0xffff0000u), __uint_as_float(u0 & 0xffff0000u))), r1, r0);
+          unpack2(sub2(s32, pack2(__uint_as_float(u3 & 0xffff0000u), __uint_as_float(u2 & 0xffff0000u))), r3, r2);
+          hv[HW / 2 + 2 * j] = __byte_perm(__float_as_uint(r0) + 0x8000u, __float_as_uint(r1) + 0x8000u, 0x7632);
+          hv[HW / 2 + 2 * j + 1] = __byte_perm(__float_as_uint(r2) + 0x8000u, __float_as_uint(r3) + 0x8000u, 0x7632);
+        };
+        constexpr int NQD = HW / 4;
+        stage_a(0, 30.0f);
+        if constexpr (NQD > 1) stage_a(1, fmaf(ex[0], 0.0f, 30.0f));
+#pragma unroll
+        for (int j = 0; j < NQD; ++j) {
+          stage_b(j);
+          if (kSplitD1 && j + 2 == NQD / 2) d1_loaded();      // A(NQD / 2) is the first stage that reads the second half
+          if (j + 2 < NQD)
+            stage_a(j + 2, __uint_as_float(__float_as_uint(fmaf(ex[4 * (j + 1)], 0.0f, 30.0f)) | ((hv[HW / 2 + 2 * j] ^ hv[HW / 2 + 2 * j + 1]) & p.zero)));
+        }
+      }
+      } else {
       float lim = 30.0f;
 #pragma unroll
       for (int j = 0; j < HW / 4; ++j) {
 #if SAPT_F32X2
         // packed fp32 pairs (FADD2 / FMUL2): 31 instead of 38 instructions per four hidden units
         f32x2 s10, s32;
-        sigmoid4_packed<false>(__uint_as_float(zr[4 * j]), __uint_as_float(zr[4 * j + 1]), __uint_as_float(zr[4 * j + 2]),
-                               __uint_as_float(zr[4 * j + 3]), lim, 1.0f, s10, s32);
+        float e0;
+        sigmoid4_packed_e<false>(__uint_as_float(zr[4 * j]), __uint_as_float(zr[4 * j + 1]), __uint_as_float(zr[4 * j + 2]),
+                                 __uint_as_float(zr[4 * j + 3]), lim, 1.0f, s10, s32, e0);
         float h0, h1, h2, h3;
         unpack2(s10, h1, h0); unpack2(s32, h3, h2);
-#if SAPT_P1_CHAIN > 0
-        if (j % SAPT_P1_CHAIN == SAPT_P1_CHAIN - 1) lim = fmaf(h0, 0.0f, 30.0f);
-#endif
+        if constexpr (kChain > 0) { if (j % kChain == kChain - 1) lim = fmaf(kDep ? e0 : h0, 0.0f, 30.0f); }
         const uint32_t u0 = __float_as_uint(h0), u1 = __float_as_uint(h1), u2 = __float_as_uint(h2), u3 = __float_as_uint(h3);
         hv[2 * j] = __byte_perm(u0, u1, 0x7632);
         hv[2 * j + 1] = __byte_perm(u2, u3, 0x7632);
@@ -492,9 +580,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
         float h0, h1, h2, h3;
         sigmoid4_lim(__uint_as_float(zr[4 * j]), __uint_as_float(zr[4 * j + 1]), __uint_as_float(zr[4 * j + 2]),
                      __uint_as_float(zr[4 * j + 3]), lim, h0, h1, h2, h3);
-#if SAPT_P1_CHAIN > 0
-        if (j % SAPT_P1_CHAIN == SAPT_P1_CHAIN - 1) lim = fmaf(h0, 0.0f, 30.0f);
-#endif
+        if constexpr (kChain > 0) { if (j % kChain == kChain - 1) lim = fmaf(h0, 0.0f, 30.0f); }
         // h1 piece = h truncated to bf16 (one PRMT packs two), h2 piece = the exact, non-negative residual
         // rounded half-up to bf16. The residual is not zero-mean, so MMA-2 also accumulates h2.w2.
         const uint32_t u0 = __float_as_uint(h0), u1 = __float_as_uint(h1), u2 = __float_as_uint(h2), u3 = __float_as_uint(h3);
@@ -508,26 +594,31 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
         hv[HW / 2 + 2 * j + 1] = __byte_perm(r2, r3, 0x7632);
 #endif
       }
+      }
     };
-    auto publish_hv = [&](int u) {  // activations of unit u -> TMEM (A operand of MMA-2), then tell the MMA warp
+    // activations of unit u -> TMEM (A operand of MMA-2): the stores are issued as soon as the buffer is free; the hand-over to the
+    // MMA warp (wait::st, fence, arrive) follows after phase 2 — MMA-2(u) has a whole unit of slack, and the store latency is no
+    // longer a bubble that all four warps of a scheduler sit through together
+    auto publish_issue = [&]() {
       // chain HV region = [h1 pairs of all HP hidden units (HP/2 cols) | h2 pairs (HP/2 cols)]
       const uint32_t hva = tmem_hv + lane_base + (uint32_t)(c * HP);
       if constexpr (HALVES == 1) {
         if constexpr (HW == 32) tmem_st32(hva, hv); else tmem_st16(hva, hv);
-        tmem_st_wait();
       } else {
         uint32_t lo[16], hi[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { lo[j] = hv[j]; hi[j] = hv[16 + j]; }
         tmem_st16(hva + (uint32_t)(hf * 16), lo);
         tmem_st16(hva + (uint32_t)(HP / 2 + hf * 16), hi);
-        tmem_st_wait();
       }
+    };
+    auto publish_commit = [&](int u) {
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&hv_full[(u & 1) * UC + c]);
     };
-    if (n_units > 0) { phase1(0); publish_hv(0); }
+    if (n_units > 0) { phase1(0); publish_issue(); publish_commit(0); }
     for (int it = 0; it < n_my_tiles; ++it) {
       const int64_t row = (t_begin + it) * kTileM + quarter * 32 + lane;
       const int y = __ldg(p.y + row);
@@ -537,11 +628,13 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
         const bool has_next = (u + 1 < n_units);
         const bool mine = (HALVES == 1) || ((u & 1) == hf);   // which of the chain's warps runs phase 2 of this unit
         if (has_next) phase1(u + 1);
+        if (trw) TC2_TRACE(c, u, 2);
         // ---- D2 of unit u: wait for MMA-2 (this also frees the HV buffer), pull it into registers ----
         // the partial sums of D2 (dr2 unused when PARTS == 2). ON = 32 serves O = 17..20: only 20 columns are read
         constexpr int NR = C::NR;
         uint32_t dr0[NR], dr1[NR], dr2[ON == 32 ? 1 : NR];
         mbar_wait(&d2_full[(u & 1) * UC + c], (u >> 1) & 1);
+        if (trw) TC2_TRACE(c, u, 3);
         tc_fence_after();
         if (mine) {
           const uint32_t taddr = tmem_base + lane_base + (uint32_t)(kD2Base + (u % kD2Bufs) * (UC * N2) + c * N2);
@@ -555,10 +648,11 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
             auto ld12 = [&](uint32_t ta, uint32_t* d) { tmem_ld8(ta, *reinterpret_cast<uint32_t(*)[8]>(d)); tmem_ld4(ta + 8, *reinterpret_cast<uint32_t(*)[4]>(d + 8)); };
             ld12(taddr, dr0); ld12(taddr + ON, dr1); ld12(taddr + 2 * ON, dr2);
           }
-          tmem_ld_wait();
         }
-        if (has_next) publish_hv(u + 1);
-        if (!mine) continue;
+        if (has_next) publish_issue();      // the HV buffer is free: MMA-2(u) has completed
+        if (mine) tmem_ld_wait();
+        if (trw) TC2_TRACE(c, u, 4);
+        if (!mine) { if (has_next) publish_commit(u + 1); continue; }
         // ---- phase 2: output layer (exactly O outputs: quads, then a pair and / or a single one) ----
         // s is kept as log2(e) * sigmoid. With FOLD the output bias rides in the MMA: hidden slot H is padding whose
         // activation is sigmoid(0) = 1/2, and its W2 row holds twice the bias (tc2_pack_kernel).
@@ -626,6 +720,8 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
           }
         };
         if (p.fold_bias) phase2(std::true_type{}); else phase2(std::false_type{});
+        if (has_next) publish_commit(u + 1);
+        if (trw) TC2_TRACE(c, u, 5);
         if (y >= 0) {
           accL[uu] += (double)(kLn2 * (oy - lg2_approx(sum)));
           accNc[uu] += (pm == y);
@@ -696,7 +792,7 @@ template <typename F>
 static int tc2_dispatch(int HP, int ON, int DKC, F&& fn) {
 #define SAPT_V(H, O, K) if (HP == H && ON == O && DKC == K) return fn(std::integral_constant<int, H>{}, std::integral_constant<int, O>{}, std::integral_constant<int, K>{});
 #ifdef SAPT_TC2_FEW   // development builds: only the BASELINE shapes (C3, C4, C5)
-  SAPT_V(32, 16, 1) SAPT_V(64, 8, 12) SAPT_V(32, 32, 9)
+  SAPT_V(32, 16, 1) SAPT_V(64, 8, 12) SAPT_V(64, 16, 12) SAPT_V(32, 32, 9)
 #else
   SAPT_V(16, 16, 1) SAPT_V(16, 16, 2) SAPT_V(16, 16, 3) SAPT_V(16, 16, 4)
   SAPT_V(32, 16, 1) SAPT_V(32, 16, 2) SAPT_V(32, 16, 3) SAPT_V(32, 16, 4)
@@ -810,9 +906,15 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   rc = tc_make_map_2d(&mw2, w2img, 64, (uint64_t)n_groups * CH * 3 * ON, (uint32_t)(g.W2BOX * 3 * ON));
   if (rc) return rc;
   Tc2Params a{};
-  a.y = ds.y; a.n_pad = ds.n_pad; a.bias2 = bias2; a.n_rows = n_rows; a.R = R; a.O = p->O; a.fold_bias = (p->H < HP) ? 1 : 0;
+  a.y = ds.y; a.n_pad = ds.n_pad; a.bias2 = bias2; a.n_rows = n_rows; a.R = R; a.O = p->O; a.fold_bias = (p->H < HP) ? 1 : 0; a.zero = 0u;
   a.tiles_per_chunk = tiles_per_chunk; a.n_tiles = n_tiles; a.partL = partL; a.partNc = partNc; a.partSq = partSq;
   dim3 grid((unsigned)n_chunks, (unsigned)n_groups);
+#ifdef SAPT_TC2_TRACE
+  static long long* d_trace = nullptr;
+  if (!d_trace) cudaMalloc(&d_trace, 5 * 64 * 8 * sizeof(long long));
+  cudaMemsetAsync(d_trace, 0, 5 * 64 * 8 * sizeof(long long), st);
+  a.trace = d_trace;
+#endif
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(SAPT_X_FP16 ? ds.tmap_f16 : ds.tmap);
 #if SAPT_CONST_O
   // output count known at compile time for the 32-wide shapes of the BASELINE configs (C3 16-30-10: 25.5 -> 25.0 ms, C5 6-25-18);
@@ -823,6 +925,21 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
 #endif
   rc = tc2_dispatch(HP, ONX, DKC, [&](auto h, auto o, auto k) { return launch_tc2<h(), o(), k()>(ma, mb1, mw2, a, grid, st); });
   if (rc) return rc;
+#ifdef SAPT_TC2_TRACE
+  {
+    std::vector<long long> h(5 * 64 * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    const long long t0 = h[(4 * 64 + 0) * 8 + 1];
+    const char* roles[5] = {"epi0", "epi1", "epi2", "epi3", "mma "};
+    for (int u = 16; u < 28; ++u)
+      for (int r = 0; r < 5; ++r) {
+        printf("trace %s unit %2d:", roles[r], u);
+        for (int e = 0; e < 6; ++e) { long long v = h[(r * 64 + u) * 8 + e]; printf(" %8lld", v ? v - t0 : -1); }
+        printf("\n");
+      }
+  }
+#endif
   return launch_loglik_finalize(partL, partNc, partSq, (int)n_chunks, R, rows, n_rows, L, nc, sq, st);
 }
 
