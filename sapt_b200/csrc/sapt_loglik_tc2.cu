@@ -288,7 +288,9 @@ __device__ __forceinline__ void sigmoid4_scaled(float t0, float t1, float t2, fl
 
 // OC: the number of outputs as a compile-time constant (0 = read it from the parameters). With a constant O the output phase has
 // no branches and ptxas schedules all its sigmoid groups together; instantiated for the topologies of the BASELINE configs.
-template <int HP, int ONX, int DK, int OC = 0>
+// HC: the number of hidden units as a compile-time constant (0 = all HP slots are computed): the padded slots HC.. of the hidden
+// layer cost no SFU work — slot HC is the bias slot (activation 1/2, see the header), the others meet zero rows of the W2 image.
+template <int HP, int ONX, int DK, int OC = 0, int HC = 0>
 __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b1,
                                                                      const __grid_constant__ CUtensorMap map_w2, Tc2Params p) {
@@ -518,9 +520,10 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
       // the trace (SAPT_TC2_TRACE) showed the four warps of a scheduler in this phase together: 1 846 cycles for 1 280 of SFU work.
       {
         float ex[HW];
+        constexpr int HREAL = (HC > 0 && HALVES == 1) ? HC : HP;       // hidden slots that hold a real unit
         auto stage_a = [&](int j, float lim) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) ex[4 * j + i] = ex2_approx(fminf(__uint_as_float(zr[4 * j + i]), lim));
+          for (int i = 0; i < 4; ++i) ex[4 * j + i] = (4 * j + i < HREAL) ? ex2_approx(fminf(__uint_as_float(zr[4 * j + i]), lim)) : 0.0f;
         };
         auto stage_b = [&](int j) {
           const f32x2 one = pack2(1.0f, 1.0f);
@@ -535,12 +538,19 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
           const f32x2 s32 = mul2(a23, pack2(rab, rab));   // (a2 r ab, a3 r ab) = (s3, s2)
           float h0, h1, h2, h3;
           unpack2(s10, h1, h0); unpack2(s32, h3, h2);
+          // padded slots: 1/2 in the bias slot, 0 elsewhere (compile-time; the products above fold away with their a = 1)
+          auto pad = [&](int i, float& h) { if (4 * j + i >= HREAL) h = (4 * j + i == HREAL) ? 0.5f : 0.0f; };
+          pad(0, h0); pad(1, h1); pad(2, h2); pad(3, h3);
           const uint32_t u0 = __float_as_uint(h0), u1 = __float_as_uint(h1), u2 = __float_as_uint(h2), u3 = __float_as_uint(h3);
           hv[2 * j] = __byte_perm(u0, u1, 0x7632);
           hv[2 * j + 1] = __byte_perm(u2, u3, 0x7632);
           float r0, r1, r2, r3;
-          unpack2(sub2(s10, pack2(__uint_as_float(u1 & 0xffff0000u), __uint_as_float(u0 & 0xffff0000u))), r1, r0);
-          unpack2(sub2(s32, pack2(__uint_as_float(u3 & 0xffff0000u), __uint_as_float(u2 & 0xffff0000u))), r3, r2);
+          r0 = h0 - __uint_as_float(u0 & 0xffff0000u); r1 = h1 - __uint_as_float(u1 & 0xffff0000u);
+          r2 = h2 - __uint_as_float(u2 & 0xffff0000u); r3 = h3 - __uint_as_float(u3 & 0xffff0000u);
+          if (4 * j + 3 < HREAL) {
+            unpack2(sub2(s10, pack2(__uint_as_float(u1 & 0xffff0000u), __uint_as_float(u0 & 0xffff0000u))), r1, r0);
+            unpack2(sub2(s32, pack2(__uint_as_float(u3 & 0xffff0000u), __uint_as_float(u2 & 0xffff0000u))), r3, r2);
+          }
           hv[HW / 2 + 2 * j] = __byte_perm(__float_as_uint(r0) + 0x8000u, __float_as_uint(r1) + 0x8000u, 0x7632);
           hv[HW / 2 + 2 * j + 1] = __byte_perm(__float_as_uint(r2) + 0x8000u, __float_as_uint(r3) + 0x8000u, 0x7632);
         };
@@ -771,7 +781,7 @@ static Tc2Geom geom_of() {
   return Tc2Geom{C::CH, C::KBA * 64, C::kW2Box, C::UPT, (size_t)C::smem_bytes(C::UPT > 0 ? C::UPT : 1)};
 }
 
-template <int HP, int ON, int DKC, int OC = 0>
+template <int HP, int ON, int DKC, int OC = 0, int HC = 0>
 static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb1, const CUtensorMap& mw2, const Tc2Params& a, dim3 grid, cudaStream_t st) {
   using C = TcCfg<HP, ON, DKC>;
   if constexpr (C::UPT < 1) {
@@ -779,7 +789,7 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb1, const CUten
     return SAPT_ERR_UNSUPPORTED;
   } else {
     const size_t smem = C::smem_bytes(C::UPT);
-    auto k = loglik_tc2_kernel<HP, ON, DKC, OC>;
+    auto k = loglik_tc2_kernel<HP, ON, DKC, OC, HC>;
     SAPT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, v2::kThreads, smem, st>>>(ma, mb1, mw2, a);
     SAPT_CHECK_LAUNCH();
@@ -837,12 +847,22 @@ bool tc2_supported(int D, int H, int O) {
 // model of what an ideal kernel would do): MUFU operations and tensor-pipe FLOPs including padding and the split products.
 //   phase 1: HP sigmoids = HP ex2 + HP/4 shared reciprocals (sigmoid4);  phase 2: O ex2 + (quads, pair, single) reciprocals for
 //   the output sigmoids, O ex2 for the softmax, one lg2.
+//   The variants with a compile-time hidden count (tc2_const_hidden) skip the padded slots: H ex2 + ceil(H / 4) reciprocals.
+static int tc2_const_hidden(int HP, int ONX, int DK, int H, int O) {   // HC of the kernel launch_loglik_tc2 picks for this topology, 0 = generic
+#if SAPT_CONST_O
+  if (HP == 32 && ONX == 16 && DK == 1 && O == 10 && H == 30) return 30;
+  if (HP == 32 && ONX == 32 && DK == 9 && O == 18 && H == 25) return 25;
+#endif
+  return 0;
+}
 void tc2_work_model(int D, int H, int O, double* mufu, double* mma_flops) {
   sapt_problem q{}; q.D = D; q.H = H; q.O = O;
   int HP, ON, DK; tc2_shape(&q, HP, ON, DK);
   const int DKC = DK & 7;
   const int rcp2 = O / 4 + ((O & 2) ? 1 : 0) + ((O & 1) ? 1 : 0);
-  *mufu = (double)HP + HP / 4 + O + rcp2 + O + 1;
+  const int hc = tc2_const_hidden(HP, ON, DK, H, O);
+  const int p1 = hc ? hc + (hc + 3) / 4 : HP + HP / 4;
+  *mufu = (double)p1 + O + rcp2 + O + 1;
   const int k1 = 16 * ((SAPT_X_FP16 ? 3 : 6) * DKC + (DK >= 8 ? 0 : 1));   // MMA-1: piece products (+ bias chunk) of 16 DKC features
   const int n2 = (ON == 16) ? (48 + 32) : (64 + 32 + 64);       // MMA-2: output columns summed over the passes h1.[w1|w2(|w3)], h2.[w1|w2]
   *mma_flops = 2.0 * k1 * HP + 2.0 * HP * n2;                   // every pass has K = HP
@@ -854,8 +874,6 @@ int tc2_a16_row_elems(int D) {                                                  
   return ((32 * dkc + (D < 16 * dkc ? 0 : 16) + 63) / 64) * 64;
 }
 int tc2_piece_width(int D) { return 16 * tc2_dkc(D); }
-
-static int gcd_int2(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
 int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld, int R, const int32_t* rows, const int32_t* n_rows,
                       double* L, int32_t* nc, double* sq, cudaStream_t st) {
@@ -875,10 +893,20 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   const int CH = g.CH;
   const int n_groups = (R + CH - 1) / CH;
   const int64_t n_tiles = ds.n_pad / v2::kTileM;
-  const int base = p->num_sms / gcd_int2(n_groups, p->num_sms);
-  int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_tiles / 16, ((int64_t)p->num_sms * 8 + n_groups - 1) / n_groups));
-  if (n_chunks >= base) n_chunks = (n_chunks / base) * base;
-  n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, n_tiles));
+  // Row chunks: one CTA per (chunk, chain group), one CTA per SM at a time. The chunk count that minimises the makespan
+  //   waves(n) x (tiles per chunk + ~1 tile of per-CTA start-up), waves(n) = ceil(groups x n / SMs)
+  // is taken: with a fixed "about 8 CTAs per SM" rule C3 (128 groups) ran 1280 CTAs = 8.65 waves and C4 (64 groups) 1216 = 8.2 waves,
+  // i.e. the last wave left a third / four fifths of the GPU idle (4 % / 9 % of the kernel).
+  int64_t n_chunks = 1;
+  {
+    const int64_t max_chunks = std::max<int64_t>(1, std::min<int64_t>(n_tiles / 16, 2 * (int64_t)p->num_sms));
+    double best = 1e300;
+    for (int64_t n = 1; n <= max_chunks; ++n) {
+      const int64_t waves = ((int64_t)n_groups * n + p->num_sms - 1) / p->num_sms;
+      const double cost = (double)waves * ((double)((n_tiles + n - 1) / n) + 1.0);
+      if (cost < best * 0.999) { best = cost; n_chunks = n; }
+    }
+  }
   const int tiles_per_chunk = (int)((n_tiles + n_chunks - 1) / n_chunks);
   n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
 
@@ -919,8 +947,8 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
 #if SAPT_CONST_O
   // output count known at compile time for the 32-wide shapes of the BASELINE configs (C3 16-30-10: 25.5 -> 25.0 ms, C5 6-25-18);
   // at HP = 64 the kernel is bound by the tensor pipe and the specialisation measured 3 % slower (54-64-7: 7.45 -> 7.70 ms)
-  if (HP == 32 && ONX == 16 && DKC == 1 && p->O == 10) rc = launch_tc2<32, 16, 1, 10>(ma, mb1, mw2, a, grid, st);
-  else if (HP == 32 && ONX == 32 && DKC == 9 && p->O == 18) rc = launch_tc2<32, 32, 9, 18>(ma, mb1, mw2, a, grid, st);
+  if (HP == 32 && ONX == 16 && DKC == 1 && p->O == 10 && p->H == 30) rc = launch_tc2<32, 16, 1, 10, 30>(ma, mb1, mw2, a, grid, st);
+  else if (HP == 32 && ONX == 32 && DKC == 9 && p->O == 18 && p->H == 25) rc = launch_tc2<32, 32, 9, 18, 25>(ma, mb1, mw2, a, grid, st);
   else
 #endif
   rc = tc2_dispatch(HP, ONX, DKC, [&](auto h, auto o, auto k) { return launch_tc2<h(), o(), k()>(ma, mb1, mw2, a, grid, st); });
