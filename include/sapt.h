@@ -68,8 +68,10 @@ enum {
   SAPT_F_REDRAW_ON_SURROGATE = 1 << 4, /* surrogate branch redraws the proposal from stream Z2 (LG:560) */
   SAPT_F_RECORD_POS = 1 << 5,      /* keep the full pos_w history on the device */
   SAPT_F_LOCAL_SURROGATE = 1 << 6, /* surrogate steps take sapt_local_surrogate_predict's value as is (LS:598,615-617) */
-  SAPT_F_SWEEP_PARALLEL = 1 << 7   /* sapt_swap_sweep: use the parallel (sparse table + pointer doubling) kernel even for a short ladder
+  SAPT_F_SWEEP_PARALLEL = 1 << 7,  /* sapt_swap_sweep: use the parallel (sparse table + pointer doubling) kernel even for a short ladder
                                       (default: R_global >= 4096); same decisions as the serial walk */
+  SAPT_F_SWEEP_GRID = 1 << 8       /* with SAPT_F_SWEEP_PARALLEL: run its phases as grid-wide launches even for a short ladder (default:
+                                      R_global >= 16384; the one-CTA kernel is latency bound: 1.6 ms at 65 536 chains); same decisions */
 };
 
 typedef struct sapt_problem sapt_problem_t; /* opaque: topology + device-resident data sets */

@@ -16,6 +16,7 @@ PATH_AUTO, PATH_F32, PATH_TC = 0, 1, 2
 STREAM_Z1, STREAM_Z2, STREAM_LX1, STREAM_KU, STREAM_LX2, STREAM_U, STREAM_SWAP, STREAM_LS_INIT = range(8)
 F_POST_TEMPERED, F_TAKE_POST_LIK, F_DENORM_HALF_MIN, F_COMPARE_SURROGATE, F_REDRAW_ON_SURROGATE, F_RECORD_POS, F_LOCAL_SURROGATE, F_SWEEP_PARALLEL = (
     1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6, 1 << 7)
+F_SWEEP_GRID = 1 << 8
 
 vp = C.c_void_p
 i32, i64, u32, f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_double

@@ -23,8 +23,11 @@
 // output layer), h, do, dh = two pieces each; the cross terms kept are listed at each MMA (gradient accuracy: 2e-6 max|g|).
 //
 // Work item = (chain, row chunk); one CTA per SM takes items round-robin, one after the other (the accumulators are per item).
-// Warp 16 lane 0: TMA producer (X tile ring; per-chain weight panels). Warp 17: TMEM alloc + MMA issue. Warps 0-15:
-// epilogue, warp (quarter q = TMEM lanes 32q.., slice s = HP/4 hidden units); P2 of tile t is done by slice t % 4.
+// Inside an item TWO tile streams run independently: epilogue warps 0-7 take the even tiles, warps 8-15 the odd ones; a stream owns one
+// Hs buffer, one TMEM scratch block, its G1 / G2 accumulators and its own MMA-issuer warp (17 / 18; warp 17 also allocates TMEM).
+// Warp 16: TMA producer (ring of three X tiles shared by the streams; per-chain weight panels). Epilogue warp = (stream, quarter q =
+// TMEM lanes 32q.., half = HP/2 hidden units in P1 / P3 and half the outputs in P2). Single-thread instructions are issued by an
+// elected lane of a converged warp (elect_one).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

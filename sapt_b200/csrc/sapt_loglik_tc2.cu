@@ -900,8 +900,11 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   int64_t n_chunks = 1;
   {
     const int64_t max_chunks = std::max<int64_t>(1, std::min<int64_t>(n_tiles / 16, 2 * (int64_t)p->num_sms));
+    // at least ~8 CTAs per SM when the rows allow it: CTAs do not all take the same time, and many small ones even that out
+    // (C5, 512 groups x 132 tiles: 3 chunks measured 5 % faster than the 2 a pure wave count prefers)
+    const int64_t min_chunks = std::min<int64_t>(max_chunks, ((int64_t)8 * p->num_sms + n_groups - 1) / n_groups);
     double best = 1e300;
-    for (int64_t n = 1; n <= max_chunks; ++n) {
+    for (int64_t n = min_chunks; n <= max_chunks; ++n) {
       const int64_t waves = ((int64_t)n_groups * n + p->num_sms - 1) / p->num_sms;
       const double cost = (double)waves * ((double)((n_tiles + n - 1) / n) + 1.0);
       if (cost < best * 0.999) { best = cost; n_chunks = n; }
@@ -945,10 +948,11 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
 #endif
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(SAPT_X_FP16 ? ds.tmap_f16 : ds.tmap);
 #if SAPT_CONST_O
-  // output count known at compile time for the 32-wide shapes of the BASELINE configs (C3 16-30-10: 25.5 -> 25.0 ms, C5 6-25-18);
-  // at HP = 64 the kernel is bound by the tensor pipe and the specialisation measured 3 % slower (54-64-7: 7.45 -> 7.70 ms)
+  // output count (and hidden count, see HC) known at compile time for the shapes of the BASELINE configs: C3 16-30-10, C5 6-25-18,
+  // C4 54-64-7 (5.69 -> 5.39 ms; while that kernel was still bound by MMA issue the specialisation had measured 3 % slower)
   if (HP == 32 && ONX == 16 && DKC == 1 && p->O == 10 && p->H == 30) rc = launch_tc2<32, 16, 1, 10, 30>(ma, mb1, mw2, a, grid, st);
   else if (HP == 32 && ONX == 32 && DKC == 9 && p->O == 18 && p->H == 25) rc = launch_tc2<32, 32, 9, 18, 25>(ma, mb1, mw2, a, grid, st);
+  else if (HP == 64 && ONX == 8 && DKC == 12 && p->O == 7) rc = launch_tc2<64, 8, 12, 7, 0>(ma, mb1, mw2, a, grid, st);
   else
 #endif
   rc = tc2_dispatch(HP, ONX, DKC, [&](auto h, auto o, auto k) { return launch_tc2<h(), o(), k()>(ma, mb1, mw2, a, grid, st); });

@@ -286,6 +286,7 @@ __global__ void swap_sweep_kernel(int R, double* lik_post, const double* tempera
 // the two kernels agree bit for bit; pairs that need the literal formula (u <= 0) make the kernel fall back to it.
 // One CTA of 1024 threads; all phases are O(R log R / 1024) with R-sized global scratch.
 constexpr int kParThreads = 1024;
+constexpr int kSweepGridMin = 16384;      // from here on the grid-wide phase kernels (below) replace the one-CTA kernel
 constexpr long long kKeyMin = (long long)0x8000000000000000ULL, kKeyMax = 0x7fffffffffffffffLL;
 
 __global__ void __launch_bounds__(kParThreads) swap_sweep_parallel_kernel(
@@ -402,6 +403,148 @@ __global__ void __launch_bounds__(kParThreads) swap_sweep_parallel_kernel(
   }
 }
 
+// -------------------------------------------------------------------------------------------
+// The same algorithm over the whole GPU for very long ladders (multi-GPU runs: every rank replays the sweep of ALL chains, 65 536 at
+// 8 x 8192). The one-CTA kernel above is bound by global-memory latency (~25 cycles per chain and phase: 1.6 ms at 65 536 chains);
+// here every phase is its own grid-wide launch — ~40 short kernels, stream ordered, capturable. Same integer keys, same decisions.
+struct SweepGrid {
+  int R; double* lik_post; const double* temperature; int32_t* row_of_slot; uint32_t flags, seed; int sweep_base; const int32_t* sweep_dev;
+  const double* u_inject; uint8_t* swapped; int32_t* num_swap; int32_t* src_slot; int row0, R_local; int32_t* slot_of_row_local;
+  int32_t* scratch_src; double* scratch_post; long long* st; long long* kp; int32_t* jmp; uint8_t* mark; int32_t* literal_flag; int32_t* blk;
+};
+__device__ __forceinline__ double sweep_posted(const SweepGrid& a, int k) {
+  return (a.flags & SAPT_F_POST_TEMPERED) ? a.lik_post[k] : a.lik_post[k] * a.temperature[k];
+}
+constexpr int kScanBlock = 1024;
+
+__global__ void sweep_grid_keys_kernel(SweepGrid a) {
+  const int sweep = a.sweep_base + (a.sweep_dev ? *a.sweep_dev : 0);
+  const int NP = a.R - 1;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= a.R; k += gridDim.x * blockDim.x) {
+    if (k < a.R) {
+      const double pk = sweep_posted(a, k);
+      a.kp[k] = (pk != pk) ? kKeyMin : order_key(pk);
+    }
+    if (k < NP) {
+      const double pk = sweep_posted(a, k + 1);
+      const double u = a.u_inject ? a.u_inject[k] : (double)philox_uniform(a.seed, SAPT_STREAM_SWAP, sweep, 0u, (uint32_t)k);
+      if (!(u > 0.0)) *a.literal_flag = 1;
+      const double t = pk - log(2.0 * u);
+      long long kt = (t != t) ? kKeyMax : order_key(t);
+      if (!(u < 1.0)) kt = kKeyMin;
+      a.st[k] = kt;
+    }
+  }
+}
+__global__ void sweep_grid_level_kernel(SweepGrid a, int l) {
+  if (*a.literal_flag) return;
+  const int NP = a.R - 1;
+  const long long* lo = a.st + (int64_t)(l - 1) * a.R;
+  long long* hi = a.st + (int64_t)l * a.R;
+  const int half = 1 << (l - 1), span = 1 << l;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j + span <= NP; j += gridDim.x * blockDim.x) hi[j] = min(lo[j], lo[j + half]);
+}
+__global__ void sweep_grid_next_kernel(SweepGrid a, int levels) {
+  if (*a.literal_flag) return;
+  const int R = a.R, NP = R - 1;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m <= R; m += gridDim.x * blockDim.x) {
+    int nx = R;
+    if (m < NP) {
+      const long long c = a.kp[m];
+      int j = m;
+      for (int l = levels - 1; l >= 0; --l)
+        if (j + (1 << l) <= NP && a.st[(int64_t)l * R + j] > c) j += (1 << l);
+      nx = (j < NP) ? j + 1 : R;
+    }
+    a.jmp[m] = nx;
+    a.mark[m] = (m == 0) ? 1 : 0;
+  }
+}
+// one round of pointer doubling. The marks are monotone (a state, once known to be on the list, stays), so they are updated in place:
+// a mark read before or after a concurrent set both give a subset of the true list and a superset of the synchronous round.
+__global__ void sweep_grid_double_kernel(SweepGrid a, int32_t* j0, int32_t* j1) {
+  if (*a.literal_flag) return;
+  const int R = a.R;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m <= R; m += gridDim.x * blockDim.x) {
+    if (m == R) { j1[R] = R; continue; }
+    const int t = j0[m];
+    if (t < R && a.mark[m]) a.mark[t] = 1;
+    j1[m] = (t < R) ? j0[t] : R;
+  }
+}
+__global__ void __launch_bounds__(kScanBlock) sweep_grid_blockmax_kernel(SweepGrid a) {   // last list state inside each block of kScanBlock chains
+  if (*a.literal_flag) return;
+  __shared__ int s_w[32];
+  const int k = blockIdx.x * kScanBlock + threadIdx.x;
+  int v = (k < a.R && a.mark[k]) ? k : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = s_w[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if (threadIdx.x == 0) a.blk[blockIdx.x] = w;
+  }
+}
+__global__ void sweep_grid_blockscan_kernel(SweepGrid a, int n_blk) {   // exclusive prefix maximum over the blocks (a few hundred at most)
+  if (*a.literal_flag) return;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int carry = -1;
+    for (int b = 0; b < n_blk; ++b) { const int v = a.blk[b]; a.blk[b] = carry; carry = max(carry, v); }
+  }
+}
+__global__ void __launch_bounds__(kScanBlock) sweep_grid_decide_kernel(SweepGrid a) {
+  if (*a.literal_flag) return;
+  __shared__ int s_w[32];
+  __shared__ int s_ns;
+  const int R = a.R, NP = R - 1;
+  const int k = blockIdx.x * kScanBlock + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_ns = 0;
+  int v = (k < R && a.mark[k]) ? k : -1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = max(v, t); }
+  if (lane == 31) s_w[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_w[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w = max(w, t); }
+    s_w[lane] = w;
+  }
+  __syncthreads();
+  const int last = max(max(a.blk[blockIdx.x], warp > 0 ? s_w[warp - 1] : -1), v);    // last list state <= k
+  if (k < R) {
+    int src;
+    if (k < NP) {
+      const bool sw = !a.mark[k + 1];                  // pair k swapped <=> no reset at k+1
+      src = sw ? k + 1 : last;
+      if (a.swapped) a.swapped[k] = sw ? 1 : 0;
+      if (sw) atomicAdd(&s_ns, 1);
+    } else {
+      src = last;                                      // the message carried out of the last pair
+    }
+    a.scratch_src[k] = src;
+    a.scratch_post[k] = sweep_posted(a, src);
+    a.scratch_src[R + k] = a.row_of_slot[k];           // old binding
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && a.num_swap && s_ns) atomicAdd(a.num_swap, s_ns);
+}
+__global__ void sweep_grid_bind_kernel(SweepGrid a) {
+  if (*a.literal_flag) return;
+  const int R = a.R;
+  const int32_t* old_rows = a.scratch_src + R;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < R; k += gridDim.x * blockDim.x) {
+    const int newrow = old_rows[a.scratch_src[k]];
+    a.row_of_slot[k] = newrow;
+    if (a.src_slot) a.src_slot[k] = a.scratch_src[k];
+    if (a.flags & SAPT_F_TAKE_POST_LIK) a.lik_post[k] = a.scratch_post[k];  // LG:813-815
+    if (a.slot_of_row_local && newrow >= a.row0 && newrow < a.row0 + a.R_local) a.slot_of_row_local[newrow - a.row0] = k;
+  }
+}
+
 __global__ void philox_fill_kernel(uint32_t seed, int kind, int step, int chain, int n, int normal, float* out) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (normal) {
@@ -511,13 +654,31 @@ extern "C" int sapt_swap_sweep_dev(int R_global, double* lik_post, const double*
       int lv = 1;
       while ((1 << lv) <= cap) ++lv;
       SAPT_CUDA(cudaMalloc(&sc.sp_st, sizeof(long long) * (size_t)(lv + 1) * cap));       // table levels + kp
-      SAPT_CUDA(cudaMalloc(&sc.sp_i, sizeof(int32_t) * (2 * (size_t)(cap + 1) + 4)));      // jump arrays + the literal flag
+      SAPT_CUDA(cudaMalloc(&sc.sp_i, sizeof(int32_t) * (2 * (size_t)(cap + 1) + 4 + cap / kScanBlock + 8)));      // the literal flag, jump arrays, block maxima
       SAPT_CUDA(cudaMalloc(&sc.sp_m, 2 * (size_t)(cap + 1)));
-      SAPT_CUDA(cudaMemsetAsync(sc.sp_i, 0, sizeof(int32_t) * (2 * (size_t)(cap + 1) + 4), (cudaStream_t)stream));
+      SAPT_CUDA(cudaMemsetAsync(sc.sp_i, 0, sizeof(int32_t) * (2 * (size_t)(cap + 1) + 4 + cap / kScanBlock + 8), (cudaStream_t)stream));
       sc.sp_cap = cap;
     }
     long long* kp = sc.sp_st + (size_t)levels * R_global;
     int32_t* lit = sc.sp_i;                    // fixed slot; the jump arrays follow it
+    if (R_global >= kSweepGridMin || (flags & SAPT_F_SWEEP_GRID)) {
+      cudaStream_t cs = (cudaStream_t)stream;
+      SweepGrid a{R_global, lik_post, temperature, row_of_slot, flags, seed, sweep, sweep_dev, u_inject, swapped, num_swap, src_slot, row0, R_local,
+                  slot_of_row_local, sc_i, sc_d, sc.sp_st, kp, sc.sp_i + 4, sc.sp_m, lit, sc.sp_i + 4 + 2 * ((size_t)sc.sp_cap + 1)};
+      const int tpb = 256;
+      const int grid = std::max(1, std::min((R_global + tpb) / tpb, 4 * 148));
+      const int n_blk = (R_global + kScanBlock - 1) / kScanBlock;
+      sweep_grid_keys_kernel<<<grid, tpb, 0, cs>>>(a);
+      for (int l = 1; l < levels; ++l) sweep_grid_level_kernel<<<grid, tpb, 0, cs>>>(a, l);
+      sweep_grid_next_kernel<<<grid, tpb, 0, cs>>>(a, levels);
+      int32_t* j0 = a.jmp; int32_t* j1 = a.jmp + (R_global + 1);
+      for (int l = 0; l < levels + 1; ++l) { sweep_grid_double_kernel<<<grid, tpb, 0, cs>>>(a, j0, j1); std::swap(j0, j1); }
+      sweep_grid_blockmax_kernel<<<n_blk, kScanBlock, 0, cs>>>(a);
+      sweep_grid_blockscan_kernel<<<1, 32, 0, cs>>>(a, n_blk);
+      sweep_grid_decide_kernel<<<n_blk, kScanBlock, 0, cs>>>(a);
+      sweep_grid_bind_kernel<<<grid, tpb, 0, cs>>>(a);
+      SAPT_CHECK_LAUNCH();
+    } else
     swap_sweep_parallel_kernel<<<1, kParThreads, 0, (cudaStream_t)stream>>>(R_global, lik_post, temperature, row_of_slot, flags, seed, sweep,
                                                                             sweep_dev, u_inject, swapped, num_swap, src_slot, row0, R_local,
                                                                             slot_of_row_local, sc_i, sc_d, sc.sp_st, kp, sc.sp_i + 4, sc.sp_m, lit);

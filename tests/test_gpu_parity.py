@@ -209,7 +209,7 @@ def test_langevin_batch_gradient(lib):
 def test_swap_sweep_matches_reference(lib):
     g = gu.load("swap_ladder")
     L = lib.lib()
-    for n, fl in [(n, fl) for n in range(int(g["n_swap_cases"])) for fl in (0, lib.F_SWEEP_PARALLEL)]:
+    for n, fl in [(n, fl) for n in range(int(g["n_swap_cases"])) for fl in (0, lib.F_SWEEP_PARALLEL, lib.F_SWEEP_PARALLEL | lib.F_SWEEP_GRID)]:
         lik = g[f"swap{n}_lik"]; u = g[f"swap{n}_u"]; R = len(lik)
         lik_d = torch.as_tensor(lik.copy()).cuda(); T = torch.ones(R, dtype=torch.float64).cuda()
         ros = torch.arange(R, dtype=torch.int32).cuda(); u_d = torch.as_tensor(u.copy()).cuda()
@@ -228,9 +228,9 @@ def test_swap_sweep_matches_reference(lib):
 
 @pytest.mark.parametrize("R", [3, 4, 17, 1000, 5001, 70000])
 def test_swap_sweep_parallel_kernel_equals_serial_walk_and_oracle(lib, R):
-    """The parallel sweep (range-minimum table + pointer doubling, the default for >= 4096 chains) against the serial walk
-    and, for moderate R, the oracle's swap_sweep: tempered and untempered posts, ties, u >= 1, NaN likelihoods, a
-    shuffled binding, a rank-local window, injected and Philox uniforms."""
+    """The parallel sweep (range-minimum table + pointer doubling, the default for >= 4096 chains) — as one CTA and as grid-wide
+    phase launches (the default for >= 16384 chains) — against the serial walk: tempered and untempered posts, ties, u >= 1,
+    NaN likelihoods, a shuffled binding, a rank-local window, injected and Philox uniforms."""
     L = lib.lib()
     rs = np.random.RandomState(R)
     lik = -np.abs(rs.standard_normal(R)) * 30.0 - 300.0
@@ -245,7 +245,7 @@ def test_swap_sweep_parallel_kernel_equals_serial_walk_and_oracle(lib, R):
     for flags0 in (0, lib.F_POST_TEMPERED | lib.F_TAKE_POST_LIK):
         for inj in (True, False):
             outs = []
-            for par in (0, lib.F_SWEEP_PARALLEL):
+            for par in (0, lib.F_SWEEP_PARALLEL, lib.F_SWEEP_PARALLEL | lib.F_SWEEP_GRID):
                 lik_d = torch.as_tensor(lik.copy()).cuda(); T_d = torch.as_tensor(T.copy()).cuda()
                 ros = torch.as_tensor(perm.copy()).cuda(); u_d = torch.as_tensor(u.copy()).cuda()
                 sw = torch.zeros(R - 1, dtype=torch.uint8).cuda(); ns = torch.zeros(1, dtype=torch.int32).cuda()
@@ -255,10 +255,11 @@ def test_swap_sweep_parallel_kernel_equals_serial_walk_and_oracle(lib, R):
                                             sor.data_ptr(), None))
                 torch.cuda.synchronize()
                 outs.append((sw.cpu().numpy(), int(ns.item()), src.cpu().numpy(), ros.cpu().numpy(), sor.cpu().numpy(), lik_d.cpu().numpy()))
-            a, b = outs
-            assert np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[2], b[2])
-            assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
-            assert np.array_equal(np.isnan(a[5]), np.isnan(b[5])) and np.array_equal(a[5][~np.isnan(a[5])], b[5][~np.isnan(b[5])])
+            a = outs[0]
+            for b in outs[1:]:
+                assert np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[2], b[2])
+                assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+                assert np.array_equal(np.isnan(a[5]), np.isnan(b[5])) and np.array_equal(a[5][~np.isnan(a[5])], b[5][~np.isnan(b[5])])
             assert a[1] == int(a[0].sum()) and (R < 1000 or 0 < a[1] < R - 1)
             if inj and R <= 5001 and not np.isnan(lik).any():
                 post = lik.copy() if (flags0 & lib.F_POST_TEMPERED) else lik * T
