@@ -1,5 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x -k "swap or sweep or full_run or graph" 2>&1 | tail -8 > gpurun_out/j28_pytest.txt
-timeout 300 python devtools/time_rendezvous.py 65536 > gpurun_out/j28_rdv.txt 2>&1
-tail -6 gpurun_out/j28_pytest.txt; tail -4 gpurun_out/j28_rdv.txt
+rm -f gpurun_out/j29_ab.jsonl
+for v in h2s0 h2s8 h2s5; do
+  SAPT_LIB=$PWD/sapt_b200/variants/libsapt_$v.so timeout 300 python devtools/ab_time.py c3 acc >> gpurun_out/j29_ab.jsonl 2>> gpurun_out/j29_ab.err
+done
+SAPT_LIB=$PWD/sapt_b200/variants/libsapt_trh2s8.so timeout 300 python devtools/prof_kernels.py c3 > gpurun_out/j29_trace_c3.txt 2>&1
+cut -c1-330 gpurun_out/j29_ab.jsonl; tail -3 gpurun_out/j29_ab.err
