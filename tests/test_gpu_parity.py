@@ -574,6 +574,29 @@ def test_c4_langevin_batch_and_exact_at_covtype_topology(lib):
         assert np.max(np.abs(got - g)) <= 1e-4 * np.max(np.abs(g)) + 2e-4
 
 
+@pytest.mark.parametrize("n", [100, 250, 300, 9000])
+@pytest.mark.parametrize("topo", [[54, 64, 7], [16, 30, 10]])
+def test_langevin_tc_tile_count_edges(lib, topo, n):
+    """The tcgen05 batch-Langevin kernel runs two tile streams per CTA (even / odd tiles of an item's row chunk): one tile (the second
+    stream idles), two, three (ragged streams), and several row chunks per chain (9000 rows = 71 tiles in two chunks) must all give the
+    gradient of the CUDA-core kernel (mode 2) and of the oracle."""
+    from sapt_b200.problem import Problem
+    R = 5
+    data = _synthetic(topo[0], topo[2], n, 33)
+    P = so.num_param(topo)
+    W = (np.random.RandomState(8).standard_normal((R, P)) * 0.4).astype(np.float32)
+    prob = Problem(topo, data, None)
+    th = torch.as_tensor(W).cuda()
+    lr = 0.002
+    o1 = prob.langevin(th, lr, mode=1, batch_scale=1.0 / n).cpu().numpy().astype(np.float64)
+    o2 = prob.langevin(th, lr, mode=2, batch_scale=1.0 / n).cpu().numpy().astype(np.float64)
+    for k in range(R):
+        g = so.langevin_batch_gradient(data, W[k].astype(np.float64), topo) / n
+        tol = 1e-4 * np.max(np.abs(g)) + 6e-5
+        assert np.max(np.abs((o1[k] - W[k]) / lr - g)) <= tol, (topo, n, k)
+        assert np.max(np.abs((o2[k] - W[k]) / lr - g)) <= tol, (topo, n, k)
+
+
 @pytest.mark.parametrize("topo", [[9, 12, 2], [16, 30, 10], [34, 50, 2], [54, 64, 7], [20, 50, 2], [4, 8, 3]])
 def test_langevin_batch_tensor_core_path(lib, topo):
     """sapt_langevin mode 1 = the tcgen05 kernel (forward, back-propagation and both row contractions as MMAs,
