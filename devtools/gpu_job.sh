@@ -1,6 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python devtools/lt_check.py > gpurun_out/j30_lt_check.txt 2>&1
-timeout 600 python -m pytest tests -m gpu -q -x -k "langevin or lg or c4" 2>&1 | tail -6 > gpurun_out/j30_pytest.txt
-timeout 600 python devtools/ab_time.py c4 > gpurun_out/j30_ab.jsonl 2> gpurun_out/j30_ab.err
-grep -hv "^   " gpurun_out/j30_lt_check.txt; tail -4 gpurun_out/j30_pytest.txt; cat gpurun_out/j30_ab.jsonl
+python devtools/c5_steps.py 8 > gpurun_out/j31_c5_plain.log 2>&1 && \
+  ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_c5_launches.csv python devtools/c5_steps.py 8 > gpurun_out/j31_c5_ncu.log 2>&1
+tail -2 gpurun_out/j31_c5_plain.log

@@ -497,8 +497,9 @@ class PTEngine:
         """(theta', L_untempered) rows of the interval's true steps, chain by chain (RW:1105-1116), as ONE device tensor
         [n, P+1] (fp64) on the trainer rank: the training set never visits the host (the reference pickles it through
         queues). Every rank packs the rows it owns with their final batch position (sapt_train_rows_pack), the fixed-size
-        payloads are gathered on the trainer rank and scattered into the batch (sapt_train_rows_scatter). All shapes are
-        static: no host synchronisation. Returns a TrainingBatch on the trainer rank, None elsewhere; `self.last_n_out`
+        payloads are gathered on the trainer rank and scattered into the batch (sapt_train_rows_scatter). One GPU: all shapes
+        are static, no host synchronisation; several ranks: one host read per rendezvous (how many payload rows carry data), so
+        that the padding does not travel. Returns a TrainingBatch on the trainer rank, None elsewhere; `self.last_n_out`
         is the device scalar with the number of rows (known on every rank)."""
         self._sync_training_counts()
         src, dest, zero_rows, n_out = parallel.training_row_plan(self.train_count, self.train_mine, self.train_npad,
@@ -508,7 +509,7 @@ class PTEngine:
         st = current_stream_ptr()
         _lib.check(self.L.sapt_train_rows_pack(_ptr(self.train_theta), _ptr(self.train_L), _ptr(src), _ptr(dest), self.train_npad, self.P,
                                                _ptr(self.train_payload), st), "sapt_train_rows_pack")
-        allp = parallel.gather_payloads(self.train_payload, self.trainer_rank, self.cfg.world, self.pg)
+        allp = parallel.gather_payloads(self.train_payload, self.trainer_rank, self.cfg.world, self.pg, n_owned=(src >= 0).sum())
         batch = None
         if self.cfg.rank == self.trainer_rank:
             if self._batch_buf is None:

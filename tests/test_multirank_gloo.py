@@ -116,9 +116,14 @@ def _worker(rank, world, port, q):
                 pi[i_, P] = ((bits & 0xffffffff) - (1 << 32) * ((bits >> 31) & 1)).to(torch.int32)
                 pi[i_, P + 1] = (bits >> 32).to(torch.int32)
                 pi[i_, P + 2] = dest[i_]
+            # with the row count only the front of the payloads travels (here exactly max over ranks of the owned rows)
+            allp_short = parallel.gather_payloads(payload, 0, world, n_owned=(src >= 0).sum(), round_rows=1)
             allp = parallel.gather_payloads(payload, 0, world)
             if rank == 0:
                 assert allp.shape == (world * n_pad, P + 4)
+                m_ = allp_short.shape[0] // world
+                assert m_ <= n_pad and all(torch.equal(allp_short.view(torch.int32)[r_ * m_:(r_ + 1) * m_], allp.view(torch.int32)[r_ * n_pad:r_ * n_pad + m_]) for r_ in range(world))
+                assert all(int((allp.view(torch.int32)[r_ * n_pad + m_:(r_ + 1) * n_pad, P + 2] >= 0).sum()) == 0 for r_ in range(world))
                 batch = torch.full((Rg * (cap + zero), P + 1), 99.0, dtype=torch.float64)
                 ai = allp.view(torch.int32)
                 for i_ in range(allp.shape[0]):
@@ -132,7 +137,7 @@ def _worker(rank, world, port, q):
                     batch[z_] = 0.0
                 assert torch.equal(batch[: int(n_out)], want), (skip_first, zero_row)
             else:
-                assert allp is None
+                assert allp is None and allp_short is None
         # every entry is owned by exactly one rank
         owned = mine.to(torch.int32)
         dist.all_reduce(owned)
