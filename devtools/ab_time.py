@@ -72,4 +72,11 @@ if "c4" in which:
             gk = so.langevin_batch_gradient(data, th[k].cpu().numpy().astype(np.float64), [D, H, O]) / n
             err = max(err, float(np.max(np.abs((og[k] - th[k].cpu().numpy().astype(np.float64)) / 0.01 - gk)) / np.max(np.abs(gk))))
         out["c4_langevin_grad_rel_err"] = err
+if "c5" in which:
+    D, H, O, N, R = 6, 25, 18, 16_833, 8192
+    x, y = synth(D, O, N, 5)
+    prob = Problem.from_f32([D, H, O], x, y)
+    th = torch.as_tensor((np.random.RandomState(1).randn(R, prob.P) * 0.5).astype(np.float32)).cuda()
+    out["c5_loglik_ms"] = t_alone(lambda: prob.loglik(th, 0, path=_lib.PATH_TC))
+    out["c5_evals_per_s"] = R * N / (out["c5_loglik_ms"][1] * 1e-3)
 print(json.dumps(out), flush=True)

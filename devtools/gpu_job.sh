@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python devtools/c5_steps.py 8 > gpurun_out/j31_c5_plain.log 2>&1 && \
-  ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_c5_launches.csv python devtools/c5_steps.py 8 > gpurun_out/j31_c5_ncu.log 2>&1
-tail -2 gpurun_out/j31_c5_plain.log
+rm -f gpurun_out/j34_ab.jsonl
+for v in base c3hc0; do
+  SAPT_LIB=$PWD/sapt_b200/variants/libsapt_$v.so timeout 300 python devtools/ab_time.py c3 c5 >> gpurun_out/j34_ab.jsonl 2>> gpurun_out/j34_ab.err
+done
+cat gpurun_out/j34_ab.jsonl; tail -3 gpurun_out/j34_ab.err

@@ -266,6 +266,12 @@ __device__ __forceinline__ void sigmoid4_lim(float t0, float t1, float t2, float
 #ifndef SAPT_ELECT
 #define SAPT_ELECT 1      // single-thread instructions issued by an elected lane of a converged warp (0: `if (lane == 0)`, round 1)
 #endif
+#ifndef SAPT_C3_HC
+#define SAPT_C3_HC 30   // compile-time hidden count of the C3 / C5 specialisations (0: compute all padded slots), for A/B builds
+#endif
+#ifndef SAPT_C5_HC
+#define SAPT_C5_HC 0
+#endif
 #ifndef SAPT_P1_DEP
 #define SAPT_P1_DEP -1    // phase-1 ordering (see phase 1): 0 = groups ordered on a finished sigmoid, 1 = on the group's first 2^t, 2 = software
 #endif                    // pipeline over the quads; -1 = per shape (measured: 2 for HP <= 32, 1 with one-quad groups for HP = 64)
@@ -850,8 +856,8 @@ bool tc2_supported(int D, int H, int O) {
 //   The variants with a compile-time hidden count (tc2_const_hidden) skip the padded slots: H ex2 + ceil(H / 4) reciprocals.
 static int tc2_const_hidden(int HP, int ONX, int DK, int H, int O) {   // HC of the kernel launch_loglik_tc2 picks for this topology, 0 = generic
 #if SAPT_CONST_O
-  if (HP == 32 && ONX == 16 && DK == 1 && O == 10 && H == 30) return 30;
-  if (HP == 32 && ONX == 32 && DK == 9 && O == 18 && H == 25) return 25;
+  if (HP == 32 && ONX == 16 && DK == 1 && O == 10 && H == 30) return SAPT_C3_HC;
+  if (HP == 32 && ONX == 32 && DK == 9 && O == 18 && H == 25) return SAPT_C5_HC;   // 0: at 6-25-18 the skipped slots measured 6 % SLOWER (3.86 vs 3.62 ms)
 #endif
   return 0;
 }
@@ -950,8 +956,8 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
 #if SAPT_CONST_O
   // output count (and hidden count, see HC) known at compile time for the shapes of the BASELINE configs: C3 16-30-10, C5 6-25-18,
   // C4 54-64-7 (5.69 -> 5.39 ms; while that kernel was still bound by MMA issue the specialisation had measured 3 % slower)
-  if (HP == 32 && ONX == 16 && DKC == 1 && p->O == 10 && p->H == 30) rc = launch_tc2<32, 16, 1, 10, 30>(ma, mb1, mw2, a, grid, st);
-  else if (HP == 32 && ONX == 32 && DKC == 9 && p->O == 18 && p->H == 25) rc = launch_tc2<32, 32, 9, 18, 25>(ma, mb1, mw2, a, grid, st);
+  if (HP == 32 && ONX == 16 && DKC == 1 && p->O == 10 && p->H == 30) rc = launch_tc2<32, 16, 1, 10, SAPT_C3_HC>(ma, mb1, mw2, a, grid, st);
+  else if (HP == 32 && ONX == 32 && DKC == 9 && p->O == 18 && p->H == 25) rc = launch_tc2<32, 32, 9, 18, SAPT_C5_HC>(ma, mb1, mw2, a, grid, st);
   else if (HP == 64 && ONX == 8 && DKC == 12 && p->O == 7) rc = launch_tc2<64, 8, 12, 7, 0>(ma, mb1, mw2, a, grid, st);
   else
 #endif
