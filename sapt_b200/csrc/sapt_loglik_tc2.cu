@@ -266,6 +266,9 @@ __device__ __forceinline__ void sigmoid4_lim(float t0, float t1, float t2, float
 #ifndef SAPT_ELECT
 #define SAPT_ELECT 1      // single-thread instructions issued by an elected lane of a converged warp (0: `if (lane == 0)`, round 1)
 #endif
+#ifndef SAPT_SPLIT_D1_ANY
+#define SAPT_SPLIT_D1_ANY 1   // D1 in two halves also for the ordered one-quad groups (HP = 64: 5.39 -> 5.36 ms)
+#endif
 #ifndef SAPT_C3_HC
 #define SAPT_C3_HC 30   // compile-time hidden count of the C3 / C5 specialisations (0: compute all padded slots), for A/B builds
 #endif
@@ -498,7 +501,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
       constexpr int kDep = (SAPT_P1_DEP >= 0) ? SAPT_P1_DEP : ((HP == 64) ? 1 : 2);
       constexpr int kChain = (SAPT_P1_CHAIN >= 0) ? SAPT_P1_CHAIN : ((kDep == 1) ? 1 : 2);
       constexpr bool kPipe = (kDep == 2) && (SAPT_F32X2 != 0);
-      constexpr bool kSplitD1 = kPipe && (HW == 32);
+      constexpr bool kSplitD1 = (kPipe || (SAPT_SPLIT_D1_ANY && kChain == 1 && SAPT_F32X2)) && (HW == 32);
       auto d1_loaded = [&]() {
         tmem_ld_wait();
         tc_fence_before();
@@ -576,6 +579,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
 #pragma unroll
       for (int j = 0; j < HW / 4; ++j) {
 #if SAPT_F32X2
+        if (kSplitD1 && j == HW / 8) d1_loaded();      // the second half of D1 (ordered groups of one quad: quad HW/8 is the first to read it)
         // packed fp32 pairs (FADD2 / FMUL2): 31 instead of 38 instructions per four hidden units
         f32x2 s10, s32;
         float e0;
