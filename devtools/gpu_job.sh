@@ -1,7 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-rm -f gpurun_out/j36_ab.jsonl
-for v in x; do
-  timeout 300 python devtools/ab_time.py c4 >> gpurun_out/j36_ab.jsonl 2>> gpurun_out/j36_ab.err
-done
-cut -c1-200 gpurun_out/j36_ab.jsonl; tail -3 gpurun_out/j36_ab.err
+timeout 600 python devtools/tc_shapes.py > gpurun_out/j37_tc_shapes.txt 2>&1
+cat gpurun_out/j37_tc_shapes.txt

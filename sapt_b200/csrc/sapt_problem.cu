@@ -140,12 +140,13 @@ extern "C" int64_t sapt_problem_rows(const sapt_problem_t* p, int which) { retur
 extern "C" int sapt_problem_tc_supported(const sapt_problem_t* p) { return (p && p->tc_ok) ? 1 : 0; }
 
 namespace sapt { void tc2_work_model(int D, int H, int O, double* mufu, double* mma_flops); }
+static constexpr int kTcAutoMinMacs = 128;   // SAPT_PATH_AUTO: D*H + H*O from which the tcgen05 likelihood kernel is used (see sapt_loglik)
 
 // see sapt.h: the per-evaluation work the selected likelihood kernel EXECUTES
 extern "C" int sapt_loglik_work_model(const sapt_problem_t* p, int path, double* out, int n_out) {
   SAPT_REQUIRE(p && out && n_out >= SAPT_WORK_COUNT, "problem / out[SAPT_WORK_COUNT]");
   if (path == SAPT_PATH_TC && !p->tc_ok) { set_error("tcgen05 path unavailable for topology %d-%d-%d", p->D, p->H, p->O); return SAPT_ERR_UNSUPPORTED; }
-  const bool tc = (path == SAPT_PATH_TC) || (path == SAPT_PATH_AUTO && p->tc_ok && p->set[0].f16_range_ok && p->D * p->H + p->H * p->O >= 220);
+  const bool tc = (path == SAPT_PATH_TC) || (path == SAPT_PATH_AUTO && p->tc_ok && p->set[0].f16_range_ok && p->D * p->H + p->H * p->O >= kTcAutoMinMacs);
   const int D = p->D, H = p->H, O = p->O;
   out[SAPT_WORK_PATH] = tc ? SAPT_PATH_TC : SAPT_PATH_F32;
   out[SAPT_WORK_FLOPS_ALGORITHMIC] = 2.0 * D * H + 2.0 * H * O;
@@ -168,9 +169,10 @@ extern "C" int sapt_loglik(sapt_problem_t* p, int which, const float* theta, int
   SAPT_REQUIRE(theta && L && R >= 0 && ld_theta >= p->P, "theta / outputs");
   SAPT_REQUIRE((rows == nullptr) == (n_rows == nullptr), "rows and n_rows come together");
   if (path == SAPT_PATH_TC && !p->tc_ok) { set_error("tcgen05 path unavailable for topology %d-%d-%d on this device", p->D, p->H, p->O); return SAPT_ERR_UNSUPPORTED; }
-  // AUTO: below ~220 multiply-adds per evaluation (9-12-2, 8-16-4 ...) the fp32 tiles win (measured crossover:
-  // 8-16-4 fp32 +10 %, 12-16-2 tcgen05 +16 %), above it the tensor-core path is 1.1x-4x faster.
-  const bool tc = (path == SAPT_PATH_TC) || (path == SAPT_PATH_AUTO && p->tc_ok && p->set[which].f16_range_ok && p->D * p->H + p->H * p->O >= 220);
+  // AUTO: below kTcAutoMinMacs multiply-adds per evaluation the fp32 tiles win (measured crossover, devtools/tc_shapes.py, end of
+  // round 2: 9-8-2 (88) and 4-12-3 (84) fp32 +20 %, 9-12-2 (132) tcgen05 +12 %, 8-16-4 (192) +6 %), above it the tensor-core path is
+  // 1.1x-9x faster.
+  const bool tc = (path == SAPT_PATH_TC) || (path == SAPT_PATH_AUTO && p->tc_ok && p->set[which].f16_range_ok && p->D * p->H + p->H * p->O >= kTcAutoMinMacs);
   if (tc) return launch_loglik_tc(p, which, theta, ld_theta, R, rows, n_rows, L, ncorrect, sqerr, (cudaStream_t)stream);
   return launch_loglik_f32(p, which, theta, ld_theta, R, rows, n_rows, L, ncorrect, sqerr, (cudaStream_t)stream);
 }
