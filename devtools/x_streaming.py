@@ -12,7 +12,7 @@ prob = Problem.from_f32([D, H, O], x, y)
 P = prob.P
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 n_pad = ((N + 255) // 256) * 256
-bytes_tc = n_pad * 4 * 128 + n_pad * 4       # bf16 image: 4 blocks x 128 B per row, + labels
+bytes_tc = n_pad * 2 * 128 + n_pad * 4       # fp16 two-piece image [x_hi | x_lo] (bias in the spare x_hi column): 2 blocks x 128 B per row, + labels
 bytes_f32 = n_pad * 64 * 4 + n_pad * 4       # fp32 X padded to 64 columns, + labels
 for R in (1, 2, 4, 8, 16):
     th = torch.as_tensor((rs.standard_normal((R, P)) * 0.3).astype(np.float32)).cuda()

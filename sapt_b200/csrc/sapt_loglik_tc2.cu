@@ -912,7 +912,9 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
     const int64_t max_chunks = std::max<int64_t>(1, std::min<int64_t>(n_tiles / 16, 2 * (int64_t)p->num_sms));
     // at least ~8 CTAs per SM when the rows allow it: CTAs do not all take the same time, and many small ones even that out
     // (C5, 512 groups x 132 tiles: 3 chunks measured 5 % faster than the 2 a pure wave count prefers)
-    const int64_t min_chunks = std::min<int64_t>(max_chunks, ((int64_t)8 * p->num_sms + n_groups - 1) / n_groups);
+    // (with so few chain groups that 8 waves are out of reach anyway — the X-streaming regime — every count is a candidate)
+    const int64_t want = ((int64_t)8 * p->num_sms + n_groups - 1) / n_groups;
+    const int64_t min_chunks = (want <= max_chunks) ? want : 1;
     double best = 1e300;
     for (int64_t n = min_chunks; n <= max_chunks; ++n) {
       const int64_t waves = ((int64_t)n_groups * n + p->num_sms - 1) / p->num_sms;
