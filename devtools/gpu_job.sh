@@ -1,11 +1,7 @@
 #!/bin/bash
-# Job 40: ncu captures of the likelihood kernel after the last edit of its source file (traffic.json is keyed on the file hash) + bench line
 mkdir -p gpurun_out
-sha256sum sapt_b200/csrc/sapt_loglik_tc2.cu sapt_b200/csrc/sapt_langevin_tc.cu sapt_b200/libsapt.so > gpurun_out/j40_src_sha.txt
 NCU="ncu --set full --clock-control none --import-source on"
 reduce() { ncu -i gpurun_out/$1.ncu-rep --page raw --csv > gpurun_out/$1_raw.csv 2>/dev/null; ncu -i gpurun_out/$1.ncu-rep --page source --csv > gpurun_out/$1_source.csv 2>/dev/null; rm -f gpurun_out/$1.ncu-rep; }
-python devtools/prof_kernels.py c3 > gpurun_out/j40_plain_c3.log 2>&1 && \
-  $NCU -k regex:loglik_tc2_kernel -s 1 -c 1 -f -o gpurun_out/r2h_c3_prof python devtools/prof_kernels.py c3 > gpurun_out/j40_ncu_c3.log 2>&1 && reduce r2h_c3_prof
-python devtools/prof_kernels.py c4ll > gpurun_out/j40_plain_c4.log 2>&1 && \
-  $NCU -k regex:loglik_tc2_kernel -s 1 -c 1 -f -o gpurun_out/r2h_c4_prof python devtools/prof_kernels.py c4ll > gpurun_out/j40_ncu_c4.log 2>&1 && reduce r2h_c4_prof
-tail -2 gpurun_out/j40_ncu_c4.log
+python devtools/prof_kernels.py c5ll > gpurun_out/j41_plain_c5.log 2>&1 && \
+  $NCU -k regex:loglik_tc2_kernel -s 1 -c 1 -f -o gpurun_out/r2_c5_prof python devtools/prof_kernels.py c5ll > gpurun_out/j41_ncu_c5.log 2>&1 && reduce r2_c5_prof
+tail -2 gpurun_out/j41_ncu_c5.log

@@ -1,4 +1,4 @@
-"""Small single-kernel workloads for ncu. usage: python devtools/prof_kernels.py c3|c4ll|c4lt|c5sp [chains]"""
+"""Small single-kernel workloads for ncu. usage: python devtools/prof_kernels.py c3|c4ll|c4lt|c5ll|c5sp [chains]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -27,6 +27,13 @@ elif which in ("c4ll", "c4lt"):
             prob.loglik(th, 0, path=_lib.PATH_TC)
         else:
             prob.langevin(th, 0.5, mode=1, batch_scale=1.0 / N)
+elif which == "c5ll":
+    D, H, O, N, R = 6, 25, 18, 16_833, int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+    x, y = synth(D, O, N, 5)
+    prob = Problem.from_f32([D, H, O], x, y)
+    th = torch.as_tensor((np.random.RandomState(1).randn(R, prob.P) * 0.5).astype(np.float32)).cuda()
+    for _ in range(2):
+        prob.loglik(th, 0, path=_lib.PATH_TC)
 elif which == "c5sp":
     import ctypes as C, time
     P, R, h1, h2 = 643, int(sys.argv[2]) if len(sys.argv) > 2 else 32768, 200, 50
