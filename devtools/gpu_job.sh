@@ -1,7 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-NCU="ncu --set full --clock-control none --import-source on"
-reduce() { ncu -i gpurun_out/$1.ncu-rep --page raw --csv > gpurun_out/$1_raw.csv 2>/dev/null; ncu -i gpurun_out/$1.ncu-rep --page source --csv > gpurun_out/$1_source.csv 2>/dev/null; rm -f gpurun_out/$1.ncu-rep; }
-python devtools/prof_kernels.py c5ll > gpurun_out/j41_plain_c5.log 2>&1 && \
-  $NCU -k regex:loglik_tc2_kernel -s 1 -c 1 -f -o gpurun_out/r2_c5_prof python devtools/prof_kernels.py c5ll > gpurun_out/j41_ncu_c5.log 2>&1 && reduce r2_c5_prof
-tail -2 gpurun_out/j41_ncu_c5.log
+rm -f gpurun_out/j42_ab.jsonl
+for v in w0 w20 w50 w100; do
+  SAPT_LIB=$PWD/sapt_b200/variants/libsapt_$v.so timeout 300 python devtools/ab_time.py c3 c4 c5 >> gpurun_out/j42_ab.jsonl 2>> gpurun_out/j42_ab.err
+done
+python - <<'PY'
+import json
+for l in open('gpurun_out/j42_ab.jsonl'):
+    j=json.loads(l); print(j['lib'], 'c3', j['c3_loglik_ms'][0], 'c4', j['c4_loglik_ms'][0], 'c5', j['c5_loglik_ms'][0])
+PY
+tail -3 gpurun_out/j42_ab.err
