@@ -1,12 +1,7 @@
 #!/bin/bash
+# last job of round 2: smoke(), the plain-C host, and the bench line of the final build (traffic.json is current)
 mkdir -p gpurun_out
-rm -f gpurun_out/j42_ab.jsonl
-for v in w0 w20 w50 w100; do
-  SAPT_LIB=$PWD/sapt_b200/variants/libsapt_$v.so timeout 300 python devtools/ab_time.py c3 c4 c5 >> gpurun_out/j42_ab.jsonl 2>> gpurun_out/j42_ab.err
-done
-python - <<'PY'
-import json
-for l in open('gpurun_out/j42_ab.jsonl'):
-    j=json.loads(l); print(j['lib'], 'c3', j['c3_loglik_ms'][0], 'c4', j['c4_loglik_ms'][0], 'c5', j['c5_loglik_ms'][0])
-PY
-tail -3 gpurun_out/j42_ab.err
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/j43_smoke.txt 2>&1
+(cd examples/c_host && ./run_pt) > gpurun_out/j43_chost.txt 2>&1
+python bench.py --steps 10 --warmup 3 > gpurun_out/j43_bench.json 2> gpurun_out/j43_bench.err
+tail -2 gpurun_out/j43_smoke.txt; tail -3 gpurun_out/j43_chost.txt; tail -c 200 gpurun_out/j43_bench.err
