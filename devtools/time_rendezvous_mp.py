@@ -49,7 +49,8 @@ for i in range(12, 28):
         t, _ = timed(lambda: _lib.check(eng.L.sapt_train_rows_pack(_ptr(eng.train_theta), _ptr(eng.train_L), _ptr(src), _ptr(dest), eng.train_npad, eng.P, _ptr(eng.train_payload), current_stream_ptr()))); acc("train.pack", t)
         t, allp = timed(lambda: parallel.gather_payloads(eng.train_payload, eng.trainer_rank, world, eng.pg)); acc("train.gather", t)
         del allp
-        t, _ = timed(lambda: eng.surrogate_rendezvous(i)); acc("train.surrogate_rendezvous (whole, again)", t)
+        t, _ = timed(lambda: eng.gather_training_rows()); acc("train.gather_training_rows (plan + pack + gather + scatter, again)", t)
+        t, _ = timed(lambda: eng.surrogate_rendezvous(i)); acc("train.surrogate_rendezvous (whole, on the emptied buffers: trainer + broadcast)", t)
 if rank == 0:
     print(f"world {world}, {Rl} chains per GPU, payload {eng.train_payload.numel() * 4 / 1e6:.0f} MB per rank, valid rows fraction {float(n_out) / (Rl * world * (W['swap_interval'] + 1)):.2f}")
     for k, v in out.items():

@@ -192,6 +192,13 @@ int sapt_surrogate_predict(const float* theta, int64_t ld, int R, int P,
  *       RW / LG forks ship (RW:496,626). batch is fp64 [.][P + 1], the reference trainer's input layout (RV:976-985). */
 int sapt_train_rows_pack(const float* train_theta, const double* train_L, const int32_t* src, const int32_t* dest, int n_rows, int P,
                          float* payload, void* stream);
+/* plan: the index vectors above in one launch, from the per-chain row counts train_count[R_global] (clamped to cap) and the ownership
+ *       mask train_mine[R_global][cap] (one byte per entry: this rank wrote it). Valid entries of chain s are j in [skip_first, count);
+ *       the batch lists the chains in order, each preceded by an all-zero row when zero_row (RW:496,626); skip_first drops entry 0
+ *       (RV:683). Writes src / dest [n_pad] (-1 from n_owned on), zero_rows[R_global] (when zero_row), n_out = rows of the batch,
+ *       n_owned = rows of this rank's payload that carry data. Device pointers throughout; nothing is read back. */
+int sapt_train_rows_plan(const int32_t* train_count, const uint8_t* train_mine, int R_global, int cap, int n_pad, int skip_first, int zero_row,
+                         int32_t* src, int32_t* dest, int64_t* zero_rows, int64_t* n_out, int64_t* n_owned, void* stream);
 int sapt_train_rows_scatter(const float* payload, int64_t n_payload, int P, const int64_t* zero_rows, int n_zero, double* batch,
                             void* stream);
 

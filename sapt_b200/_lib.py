@@ -132,6 +132,7 @@ def lib():
     L.sapt_loglik_work_model.argtypes = [vp, C.c_int, C.POINTER(f64), C.c_int]
     L.sapt_train_rows_pack.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
     L.sapt_train_rows_scatter.argtypes = [vp, i64, C.c_int, vp, C.c_int, vp, vp]
+    L.sapt_train_rows_plan.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
     sizes = (i32 * 8)()
     L.sapt_struct_sizes(sizes)
     mine = [C.sizeof(t) for t in (ProposeArgs, ChainState, History, AcceptArgs, LgFirstArgs, FusedArgs, LocalSurrogate, StepArgs)]
@@ -156,7 +157,7 @@ EXPORTS = [
     "sapt_problem_rows", "sapt_problem_tc_supported", "sapt_loglik", "sapt_loglik_host", "sapt_evaluate_proposal",
     "sapt_prior", "sapt_propose", "sapt_fused_steps", "sapt_langevin", "sapt_surrogate_predict", "sapt_mh_accept", "sapt_lg_first_eval",
     "sapt_swap_sweep", "sapt_swap_sweep_dev", "sapt_advance", "sapt_philox_host", "sapt_philox_fill",
-    "sapt_local_surrogate_train", "sapt_local_surrogate_predict", "sapt_step", "sapt_measure_pipes", "sapt_loglik_work_model", "sapt_train_rows_pack", "sapt_train_rows_scatter",
+    "sapt_local_surrogate_train", "sapt_local_surrogate_predict", "sapt_step", "sapt_measure_pipes", "sapt_loglik_work_model", "sapt_train_rows_pack", "sapt_train_rows_scatter", "sapt_train_rows_plan",
 ]
 
 

@@ -58,6 +58,51 @@ __global__ void train_rows_scatter_kernel(const float* __restrict__ payload, int
   }
 }
 
+// The index vectors of the rendezvous in ONE launch (parallel.training_row_plan is the torch restatement the CPU tests run; on the
+// device it was two dozen small kernels, 0.4 ms per rendezvous at 8192 chains). One CTA: every thread owns a contiguous range of
+// chains, counts the batch rows and the owned rows of its range, a block scan turns the counts into offsets, a second walk writes
+//   src[pos] = slot * cap + j, dest[pos] = batch row      for every owned valid entry (pos = 0, 1, ... in chain-major order),
+//   zero_rows[slot] = first batch row of the chain        (the all-zero row RW:496,626 ship), n_out = rows of the batch,
+//   n_owned = entries this rank owns; src / dest are -1 from n_owned on.
+constexpr int kPlanThreads = 1024;
+__global__ void __launch_bounds__(kPlanThreads) train_rows_plan_kernel(const int32_t* __restrict__ count, const uint8_t* __restrict__ mine, int Rg, int cap,
+                                                                      int n_pad, int lo, int zero, int32_t* __restrict__ src, int32_t* __restrict__ dest,
+                                                                      int64_t* __restrict__ zero_rows, int64_t* __restrict__ n_out, int64_t* __restrict__ n_owned) {
+  __shared__ long long s_rows[kPlanThreads], s_own[kPlanThreads];
+  const int tid = threadIdx.x;
+  const int per = (Rg + kPlanThreads - 1) / kPlanThreads;
+  const int s0 = min(Rg, tid * per), s1 = min(Rg, s0 + per);
+  for (int i = tid; i < n_pad; i += kPlanThreads) { src[i] = -1; dest[i] = -1; }
+  long long rows = 0, own = 0;
+  for (int s = s0; s < s1; ++s) {
+    const int cnt = min(max(count[s], 0), cap);
+    rows += max(cnt - lo, 0) + zero;
+    for (int j = lo; j < cnt; ++j) own += mine[(int64_t)s * cap + j] ? 1 : 0;
+  }
+  s_rows[tid] = rows; s_own[tid] = own;
+  __syncthreads();
+  for (int off = 1; off < kPlanThreads; off <<= 1) {      // inclusive Hillis-Steele scan of both sums
+    const long long a = (tid >= off) ? s_rows[tid - off] : 0, b = (tid >= off) ? s_own[tid - off] : 0;
+    __syncthreads();
+    s_rows[tid] += a; s_own[tid] += b;
+    __syncthreads();
+  }
+  long long start = s_rows[tid] - rows, pos = s_own[tid] - own;   // exclusive offsets of this thread's range
+  if (tid == kPlanThreads - 1) { *n_out = s_rows[tid]; *n_owned = s_own[tid]; }
+  for (int s = s0; s < s1; ++s) {
+    const int cnt = min(max(count[s], 0), cap);
+    if (zero_rows) zero_rows[s] = start;
+    for (int j = lo; j < cnt; ++j) {
+      if (mine[(int64_t)s * cap + j] && pos < n_pad) {     // more owned rows than n_pad cannot happen (see engine); never write out of range
+        src[pos] = s * cap + j;
+        dest[pos] = (int32_t)(start + zero + (j - lo));
+        ++pos;
+      }
+    }
+    start += max(cnt - lo, 0) + zero;
+  }
+}
+
 }  // namespace sapt
 
 using namespace sapt;
@@ -78,6 +123,17 @@ extern "C" int sapt_train_rows_scatter(const float* payload, int64_t n_payload, 
   if (grid == 0) return SAPT_OK;
   SAPT_REQUIRE(grid < (int64_t)1 << 31, "too many rows for one launch");
   train_rows_scatter_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(payload, n_payload, P, zero_rows, n_zero, batch);
+  SAPT_CHECK_LAUNCH();
+  return SAPT_OK;
+}
+
+extern "C" int sapt_train_rows_plan(const int32_t* train_count, const uint8_t* train_mine, int R_global, int cap, int n_pad, int skip_first, int zero_row,
+                                    int32_t* src, int32_t* dest, int64_t* zero_rows, int64_t* n_out, int64_t* n_owned, void* stream) {
+  SAPT_REQUIRE(train_count && train_mine && src && dest && n_out && n_owned && R_global >= 0 && cap >= 1 && n_pad >= 0, "sapt_train_rows_plan");
+  SAPT_REQUIRE(!zero_row || zero_rows, "sapt_train_rows_plan: zero_rows");
+  SAPT_REQUIRE((int64_t)R_global * cap < ((int64_t)1 << 31), "sapt_train_rows_plan: slot * cap + j must fit 32 bits");
+  train_rows_plan_kernel<<<1, kPlanThreads, 0, (cudaStream_t)stream>>>(train_count, train_mine, R_global, cap, n_pad, skip_first ? 1 : 0, zero_row ? 1 : 0, src, dest,
+                                                                       zero_row ? zero_rows : nullptr, n_out, n_owned);
   SAPT_CHECK_LAUNCH();
   return SAPT_OK;
 }

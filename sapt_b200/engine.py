@@ -502,14 +502,15 @@ class PTEngine:
         that the padding does not travel. Returns a TrainingBatch on the trainer rank, None elsewhere; `self.last_n_out`
         is the device scalar with the number of rows (known on every rank)."""
         self._sync_training_counts()
-        src, dest, zero_rows, n_out = parallel.training_row_plan(self.train_count, self.train_mine, self.train_npad,
-                                                                 skip_first=(self.spec.name == "rv"),      # RV ships surr_train_set[1:count_real] (RV:683)
-                                                                 zero_row=self.spec.ship_zero_row)          # RW:496,626 / LG:543,822
+        src, dest, zero_rows, n_out, n_owned = parallel.training_row_plan(self.train_count, self.train_mine, self.train_npad,
+                                                                          skip_first=(self.spec.name == "rv"),      # RV ships surr_train_set[1:count_real] (RV:683)
+                                                                          zero_row=self.spec.ship_zero_row,         # RW:496,626 / LG:543,822
+                                                                          return_owned=True)
         self.last_n_out = n_out
         st = current_stream_ptr()
         _lib.check(self.L.sapt_train_rows_pack(_ptr(self.train_theta), _ptr(self.train_L), _ptr(src), _ptr(dest), self.train_npad, self.P,
                                                _ptr(self.train_payload), st), "sapt_train_rows_pack")
-        allp = parallel.gather_payloads(self.train_payload, self.trainer_rank, self.cfg.world, self.pg, n_owned=(src >= 0).sum())
+        allp = parallel.gather_payloads(self.train_payload, self.trainer_rank, self.cfg.world, self.pg, n_owned=n_owned)
         batch = None
         if self.cfg.rank == self.trainer_rank:
             if self._batch_buf is None:

@@ -1104,6 +1104,28 @@ def test_train_rows_pack_scatter_kernels(lib, skip_first, zero_row):
     assert np.all(got[want.shape[0]:] == 99.0)
 
 
+@pytest.mark.parametrize("Rg,cap", [(1, 1), (7, 3), (1000, 5), (70000, 4)])
+def test_train_rows_plan_kernel_equals_torch_restatement(lib, Rg, cap):
+    """sapt_train_rows_plan (one launch) against parallel.training_row_plan's torch code run on the CPU — the version the gloo tests
+    pin against the reference's batch order: all three fork conventions, counts beyond the capacity, ragged ownership, a payload
+    that is larger than, equal to and (clamped) smaller than the owned rows."""
+    from sapt_b200 import parallel
+    rs = np.random.RandomState(Rg + cap)
+    cnt = torch.as_tensor(rs.randint(0, cap + 3, Rg).astype(np.int32))
+    mine = torch.as_tensor(rs.rand(Rg, cap) < 0.6)
+    n_owned_max = int(mine.sum())
+    for skip_first, zero_row in ((False, True), (True, False), (False, False)):
+        for n_pad in (Rg * (cap + 1), max(1, n_owned_max), max(1, n_owned_max // 2)):
+            want = parallel.training_row_plan(cnt, mine, n_pad, skip_first, zero_row, return_owned=True)
+            got = parallel.training_row_plan(cnt.cuda(), mine.cuda(), n_pad, skip_first, zero_row, return_owned=True)
+            torch.cuda.synchronize()
+            n_own = min(int(want[4]), n_pad)
+            assert int(got[3]) == int(want[3]) and min(int(got[4]), n_pad) == n_own
+            assert torch.equal(got[0].cpu()[:n_own], want[0][:n_own]) and torch.equal(got[1].cpu()[:n_own], want[1][:n_own])
+            assert bool((got[0].cpu()[n_own:] == -1).all()) and bool((got[1].cpu()[n_own:] == -1).all())
+            assert torch.equal(got[2].cpu(), want[2])
+
+
 @pytest.mark.parametrize("topology_id,P,R", [(3, 643, 1000), (3, 3975, 300), (1, 146, 513), (2, 820, 257)])
 def test_surrogate_predict_tcgen05(lib, topology_id, P, R):
     """Layer 1 of the surrogate MLP on the tensor cores (sapt_surrogate_tc.cu: fp16 two-piece operands, fp32 accumulation in TMEM,
