@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 LIB=sapt_b200/libsapt.so
 echo "# $(date -u +%Y-%m-%dT%H:%MZ)  cuobjdump -sass $LIB  (sha256 $(sha256sum $LIB | cut -c1-16))"
-for pat in 'loglik_tc2_kernelILi32ELi16ELi1E' 'loglik_tc2_kernelILi64ELi8ELi12E' 'langevin_tc_kernelILi64ELi12E' 'surrogate_tc_kernelILi13E'; do
+for pat in 'loglik_tc2_kernelILi32ELi16ELi1ELi10ELi30E' 'loglik_tc2_kernelILi64ELi8ELi12ELi7E' 'loglik_tc2_kernelILi32ELi32ELi9ELi18E' 'langevin_tc_kernelILi64ELi12E' 'surrogate_tc_kernelILi13E'; do
   fn=$(cuobjdump -sass $LIB 2>/dev/null | grep -o "Function : [^ ]*${pat}[^ ]*" | head -1 | sed 's/Function : //')
   [ -z "$fn" ] && continue
   echo; echo "== $fn"
