@@ -33,6 +33,7 @@
 // pipelined (phase 1 of unit u+1 before phase 2 of unit u) so that every MMA has a full unit of slack before its
 // result is awaited.
 #include <algorithm>
+#include <cstdlib>
 #include <cstdio>
 #include <type_traits>
 #include <vector>
@@ -299,7 +300,11 @@ __device__ __forceinline__ void sigmoid4_scaled(float t0, float t1, float t2, fl
 // no branches and ptxas schedules all its sigmoid groups together; instantiated for the topologies of the BASELINE configs.
 // HC: the number of hidden units as a compile-time constant (0 = all HP slots are computed): the padded slots HC.. of the hidden
 // layer cost no SFU work — slot HC is the bias slot (activation 1/2, see the header), the others meet zero rows of the W2 image.
-template <int HP, int ONX, int DK, int OC = 0, int HC = 0>
+// DYN: the CTA walks only the units of a tile that hold a chain (run-time count). For launches whose single chain group is far from
+// full — a handful of chains on a large data set, the reference's usual 8-10 replicas, the X-streaming regime — the empty chain
+// slots then cost nothing (6 chains at 16-30-10: two of four units). A run-time loop bound costs the full-group kernels 4-6 %, so
+// this is a separate set of instantiations that the launcher picks only then.
+template <int HP, int ONX, int DK, int OC = 0, int HC = 0, bool DYN = false>
 __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b1,
                                                                      const __grid_constant__ CUtensorMap map_w2, Tc2Params p) {
@@ -346,7 +351,8 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
   const int64_t t_begin = (int64_t)blockIdx.x * p.tiles_per_chunk;
   const int64_t t_end = min(t_begin + (int64_t)p.tiles_per_chunk, p.n_tiles);
   const int n_my_tiles = (int)max((int64_t)0, t_end - t_begin);
-  const int n_units = n_my_tiles * UPT;
+  const int upt = DYN ? (min(CH, nact - g0) + UC - 1) / UC : UPT;   // units per tile that are walked (the same in every role)
+  const int n_units = n_my_tiles * upt;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
       const uint64_t dA0 = umma_desc_sw128(smem_u32(sA)), dB10 = umma_desc_sw128(smem_u32(sB1)), dW20 = umma_desc_sw128(smem_u32(sW2));
       mbar_wait(b_full, 0);
       auto issue_mma1 = [&](int u) {
-        const int it = u / UPT, uu = u - it * UPT;
+        const int it = u / upt, uu = u - it * upt;
         const int s = it % STAGES;
         TC2_TRACE(4, u, 0);
         if (u > 0) mbar_wait(d1_empty, (u - 1) & 1);  // every warp holds D1(u-1) in registers
@@ -434,14 +440,14 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
             for (int j = 0; j < DKC; ++j)
               tc_mma_bf16(tmem_base, a_at(pa[q] * DKC + j), b_at(pb[q] * DKC + j), idesc1, (q | j) ? 1u : 0u);
           if constexpr (!C::BIASX) tc_mma_bf16(tmem_base, a_at(C::XP * DKC), b_at(C::XP * DKC), idesc1, 1u);
-          if (uu == UPT - 1) tc_commit(&empty_a[s]);
+          if (uu == upt - 1) tc_commit(&empty_a[s]);
           tc_commit(d1_full);
         }
         if (SAPT_ELECT) __syncwarp();
       };
       if (n_units > 0) issue_mma1(0);
       for (int u = 0; u < n_units; ++u) {
-        const int uu = u % UPT;
+        const int uu = u % upt;
         // D1(u+1) first: its trigger (all warps loaded D1(u)) precedes the HV(u) hand-over in every warp
         if (u + 1 < n_units) issue_mma1(u + 1);
 #pragma unroll
@@ -644,7 +650,8 @@ __global__ void __launch_bounds__(v2::kThreads, 1) loglik_tc2_kernel(const __gri
       const int y = __ldg(p.y + row);
 #pragma unroll
       for (int uu = 0; uu < UPT; ++uu) {
-        const int u = it * UPT + uu;
+        if (DYN && uu >= upt) break;
+        const int u = it * upt + uu;
         const bool has_next = (u + 1 < n_units);
         const bool mine = (HALVES == 1) || ((u & 1) == hf);   // which of the chain's warps runs phase 2 of this unit
         if (has_next) phase1(u + 1);
@@ -791,7 +798,7 @@ static Tc2Geom geom_of() {
   return Tc2Geom{C::CH, C::KBA * 64, C::kW2Box, C::UPT, (size_t)C::smem_bytes(C::UPT > 0 ? C::UPT : 1)};
 }
 
-template <int HP, int ON, int DKC, int OC = 0, int HC = 0>
+template <int HP, int ON, int DKC, int OC = 0, int HC = 0, bool DYN = false>
 static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb1, const CUtensorMap& mw2, const Tc2Params& a, dim3 grid, cudaStream_t st) {
   using C = TcCfg<HP, ON, DKC>;
   if constexpr (C::UPT < 1) {
@@ -799,7 +806,7 @@ static int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb1, const CUten
     return SAPT_ERR_UNSUPPORTED;
   } else {
     const size_t smem = C::smem_bytes(C::UPT);
-    auto k = loglik_tc2_kernel<HP, ON, DKC, OC, HC>;
+    auto k = loglik_tc2_kernel<HP, ON, DKC, OC, HC, (DYN && (C::UPT > 1))>;
     SAPT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, v2::kThreads, smem, st>>>(ma, mb1, mw2, a);
     SAPT_CHECK_LAUNCH();
@@ -959,6 +966,16 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   a.trace = d_trace;
 #endif
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(SAPT_X_FP16 ? ds.tmap_f16 : ds.tmap);
+  // a single chain group with at least one whole unit of empty chain slots: the instantiations that walk only the occupied units
+  // (see DYN). SAPT_TC2_UNITS=static / dynamic overrides the choice (tests run both).
+  const int UC = CH / g.UPT;
+  bool use_dyn = (n_groups == 1) && (g.UPT > 1) && (R <= CH - UC);
+  if (const char* e = getenv("SAPT_TC2_UNITS")) {
+    if (e[0] == 's') use_dyn = false;
+    else if (e[0] == 'd') use_dyn = (n_groups == 1) && (g.UPT > 1);
+  }
+  if (use_dyn) rc = tc2_dispatch(HP, ONX, DKC, [&](auto h, auto o, auto k) { return launch_tc2<h(), o(), k(), 0, 0, true>(ma, mb1, mw2, a, grid, st); });
+  else
 #if SAPT_CONST_O
   // output count (and hidden count, see HC) known at compile time for the shapes of the BASELINE configs: C3 16-30-10, C5 6-25-18,
   // C4 54-64-7 (5.69 -> 5.39 ms; while that kernel was still bound by MMA issue the specialisation had measured 3 % slower)

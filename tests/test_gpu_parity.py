@@ -28,8 +28,12 @@ def _paths(lib, prob):
     return [lib.PATH_F32] + ([lib.PATH_TC] if prob.tc_supported else [])
 
 
+@pytest.mark.parametrize("units", ["static", "dynamic"])
 @pytest.mark.parametrize("problem", ["cancer", "ions", "pendigit"])
-def test_loglik_matches_reference(lib, problem):
+def test_loglik_matches_reference(lib, problem, units, monkeypatch):
+    # the tcgen05 kernel has two sets of instantiations (compile-time / run-time units per tile, see DYN in sapt_loglik_tc2.cu):
+    # with so few chains the launcher would pick the second; SAPT_TC2_UNITS forces either
+    monkeypatch.setenv("SAPT_TC2_UNITS", units)
     from sapt_b200.problem import Problem
     g = gu.load(f"unit_{problem}")
     topo = [int(v) for v in g["topology"]]
@@ -50,6 +54,31 @@ def test_loglik_matches_reference(lib, problem):
             assert np.array_equal(sq.cpu().numpy(), np.array([r[2] for r in ref])), f"sqerr path {path}"
             rm = np.sqrt(sq.cpu().numpy() / data.shape[0])
             np.testing.assert_allclose(rm, g[f"rmse_{name}"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("topo", [[16, 30, 10], [54, 64, 7], [6, 25, 18], [9, 12, 2]])
+def test_loglik_few_chains_dynamic_units_equal_static(lib, topo, monkeypatch):
+    """1 .. CH chains in one group: the instantiations that walk only the occupied units of a tile (picked automatically when at
+    least one unit of chain slots is empty) give the sums and counts of the compile-time-unit kernels."""
+    from sapt_b200.problem import Problem
+    data = _synthetic(topo[0], topo[2], 3000, 12)
+    prob = Problem(topo, data, None)
+    assert prob.tc_supported
+    rs = np.random.RandomState(2)
+    for R in (1, 2, 3, 4, 5, 8, 9, 12, 13, 16):
+        th = torch.as_tensor((rs.standard_normal((R, prob.P)) * 0.6).astype(np.float32)).cuda()
+        outs = {}
+        for units in ("static", "dynamic", None):
+            if units is None: monkeypatch.delenv("SAPT_TC2_UNITS", raising=False)
+            else: monkeypatch.setenv("SAPT_TC2_UNITS", units)
+            outs[units] = [t.cpu().numpy() for t in prob.loglik(th, 0, path=lib.PATH_TC)]
+        for k in ("dynamic", None):
+            # same per-chain arithmetic, but the BASELINE shapes have specialised compile-time-unit kernels (exact 1/2 in the bias
+            # slot, constant output count): the sums agree to fp64 rounding of fp32-grade terms, the counts exactly
+            np.testing.assert_allclose(outs[k][0], outs["static"][0], rtol=1e-8, err_msg=str((topo, R, k)))
+            assert np.array_equal(outs[k][1], outs["static"][1]) and np.array_equal(outs[k][2], outs["static"][2]), (topo, R, k)
+        ref = np.array([so.loglik_stats(data, th[k].cpu().numpy().astype(np.float64), topo)[0] for k in range(R)])
+        np.testing.assert_allclose(outs["static"][0], ref, rtol=3e-6)
 
 
 def test_loglik_row_subset_and_ragged_sizes(lib):
@@ -532,9 +561,11 @@ def _synthetic(D, O, n, seed):
     return np.concatenate([x, y[:, None].astype(np.float64)], axis=1)
 
 
+@pytest.mark.parametrize("units", ["static", "dynamic"])
 @pytest.mark.parametrize("topo,name", [([54, 64, 7], "C4 covtype-shape"), ([6, 25, 18], "C5 chess-shape"), ([34, 50, 2], "C2 ionosphere"),
                                        ([9, 12, 2], "C1 cancer"), ([16, 30, 10], "C3 pendigit-shape")])
-def test_config_topologies_loglik_and_prior(lib, topo, name):
+def test_config_topologies_loglik_and_prior(lib, topo, name, units, monkeypatch):
+    monkeypatch.setenv("SAPT_TC2_UNITS", units)
     from sapt_b200.problem import Problem, prior
     data = _synthetic(topo[0], topo[2], 777, 5)
     test = _synthetic(topo[0], topo[2], 130, 6)
