@@ -966,13 +966,15 @@ int launch_loglik_tc2(sapt_problem* p, int which, const float* theta, int64_t ld
   a.trace = d_trace;
 #endif
   const CUtensorMap& ma = *reinterpret_cast<const CUtensorMap*>(SAPT_X_FP16 ? ds.tmap_f16 : ds.tmap);
-  // a single chain group with at least one whole unit of empty chain slots: the instantiations that walk only the occupied units
-  // (see DYN). SAPT_TC2_UNITS=static / dynamic overrides the choice (tests run both).
+  // empty chain slots in the last (or only) chain group: when at least ~8 % of the launch's units would be padding, the
+  // instantiations that walk only the occupied units (see DYN: they cost a full group 4-6 %). SAPT_TC2_UNITS=static / dynamic
+  // overrides the choice (tests run both).
   const int UC = CH / g.UPT;
-  bool use_dyn = (n_groups == 1) && (g.UPT > 1) && (R <= CH - UC);
+  const int units_all = n_groups * g.UPT, units_used = (R + UC - 1) / UC;
+  bool use_dyn = (g.UPT > 1) && ((units_all - units_used) * 12 >= units_all);
   if (const char* e = getenv("SAPT_TC2_UNITS")) {
     if (e[0] == 's') use_dyn = false;
-    else if (e[0] == 'd') use_dyn = (n_groups == 1) && (g.UPT > 1);
+    else if (e[0] == 'd') use_dyn = (g.UPT > 1);
   }
   if (use_dyn) rc = tc2_dispatch(HP, ONX, DKC, [&](auto h, auto o, auto k) { return launch_tc2<h(), o(), k(), 0, 0, true>(ma, mb1, mw2, a, grid, st); });
   else

@@ -58,14 +58,15 @@ def test_loglik_matches_reference(lib, problem, units, monkeypatch):
 
 @pytest.mark.parametrize("topo", [[16, 30, 10], [54, 64, 7], [6, 25, 18], [9, 12, 2]])
 def test_loglik_few_chains_dynamic_units_equal_static(lib, topo, monkeypatch):
-    """1 .. CH chains in one group: the instantiations that walk only the occupied units of a tile (picked automatically when at
-    least one unit of chain slots is empty) give the sums and counts of the compile-time-unit kernels."""
+    """Chain counts that leave chain slots of the last (or only) group empty: the instantiations that walk only the occupied units of
+    a tile (picked automatically when >= ~8 % of the launch's units would be padding) give the sums and counts of the
+    compile-time-unit kernels."""
     from sapt_b200.problem import Problem
     data = _synthetic(topo[0], topo[2], 3000, 12)
     prob = Problem(topo, data, None)
     assert prob.tc_supported
     rs = np.random.RandomState(2)
-    for R in (1, 2, 3, 4, 5, 8, 9, 12, 13, 16):
+    for R in (1, 2, 3, 4, 5, 8, 9, 12, 13, 16, 17, 20, 37):          # the last three: a full group followed by a mostly empty one
         th = torch.as_tensor((rs.standard_normal((R, prob.P)) * 0.6).astype(np.float32)).cuda()
         outs = {}
         for units in ("static", "dynamic", None):
