@@ -189,7 +189,8 @@ int sapt_surrogate_predict(const float* theta, int64_t ld, int R, int P,
  *       src[i] = slot * cap + j >= 0; src[i] < 0 marks a padding row (destination -1).
  * scatter: batch[dest][0..P] = (double) payload row for every row with dest >= 0 of `payload` (the rows of all ranks,
  *       gathered on the trainer rank), and batch[zero_rows[k]][:] = 0 for the all-zero first row of every chain that the
- *       RW / LG forks ship (RW:496,626). batch is fp64 [.][P + 1], the reference trainer's input layout (RV:976-985). */
+ *       RW / LG forks ship (RW:496,626). batch is fp64 [.][P + 1], the reference trainer's input layout (RV:976-985).
+ *       n_payload = 0 (payload may then be NULL) writes the zero rows only. */
 int sapt_train_rows_pack(const float* train_theta, const double* train_L, const int32_t* src, const int32_t* dest, int n_rows, int P,
                          float* payload, void* stream);
 /* plan: the index vectors above in one launch, from the per-chain row counts train_count[R_global] (clamped to cap) and the ownership

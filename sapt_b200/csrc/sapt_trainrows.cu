@@ -118,7 +118,7 @@ extern "C" int sapt_train_rows_pack(const float* train_theta, const double* trai
 
 extern "C" int sapt_train_rows_scatter(const float* payload, int64_t n_payload, int P, const int64_t* zero_rows, int n_zero, double* batch,
                                        void* stream) {
-  SAPT_REQUIRE(payload && batch && n_payload >= 0 && P > 0 && n_zero >= 0 && (n_zero == 0 || zero_rows), "sapt_train_rows_scatter");
+  SAPT_REQUIRE((payload || n_payload == 0) && batch && n_payload >= 0 && P > 0 && n_zero >= 0 && (n_zero == 0 || zero_rows), "sapt_train_rows_scatter");   // no payload rows at all (an interval of surrogate steps only, several ranks): only the zero rows are written
   const int64_t grid = n_payload + n_zero;
   if (grid == 0) return SAPT_OK;
   SAPT_REQUIRE(grid < (int64_t)1 << 31, "too many rows for one launch");

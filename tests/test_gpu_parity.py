@@ -1136,6 +1136,20 @@ def test_train_rows_pack_scatter_kernels(lib, skip_first, zero_row):
     assert np.all(got[want.shape[0]:] == 99.0)
 
 
+def test_train_rows_scatter_without_payload_rows(lib):
+    """An interval in which no chain made a true evaluation: with several ranks the gather then moves nothing (parallel.gather_payloads)
+    and the scatter gets an empty payload — it still writes the all-zero first row of every chain that RW / LG ship."""
+    L = lib.lib()
+    P, Rg = 37, 6
+    batch = torch.full((Rg * 2, P + 1), 5.0, dtype=torch.float64).cuda()
+    zero_rows = torch.arange(Rg, dtype=torch.int64).cuda()
+    lib.check(L.sapt_train_rows_scatter(None, 0, P, zero_rows.data_ptr(), Rg, batch.data_ptr(), None))
+    torch.cuda.synchronize()
+    got = batch.cpu().numpy()
+    assert np.all(got[:Rg] == 0.0) and np.all(got[Rg:] == 5.0)
+    lib.check(L.sapt_train_rows_scatter(None, 0, P, None, 0, batch.data_ptr(), None))     # nothing at all: a no-op
+
+
 @pytest.mark.parametrize("Rg,cap", [(1, 1), (7, 3), (1000, 5), (70000, 4)])
 def test_train_rows_plan_kernel_equals_torch_restatement(lib, Rg, cap):
     """sapt_train_rows_plan (one launch) against parallel.training_row_plan's torch code run on the CPU — the version the gloo tests

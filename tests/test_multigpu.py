@@ -25,6 +25,9 @@ def _cfg(world, rank, variant="rw"):
     if variant == "rw_sur":   # global surrogate: the interval's training rows of all chains are assembled on every rank
         return EngineConfig(variant="rw", samples=40, swap_interval=4, surrogate_interval=4, surrogate_prob=0.5, use_surrogate=True,
                             surrogate_topology=1, seed=23, record_history=True, record_pos=True, rank=rank, world=world)
+    if variant == "rw_sur_all":   # surrogate_prob = 1: once a model exists no chain makes a true evaluation, so the rendezvous moves NO rows
+        return EngineConfig(variant="rw", samples=24, swap_interval=4, surrogate_interval=4, surrogate_prob=1.0, use_surrogate=True,
+                            surrogate_topology=1, seed=25, record_history=True, record_pos=True, rank=rank, world=world)
     if variant == "lg_sur":   # Langevin fork: exchanges fall INSIDE a surrogate interval, training rows are captured by lg_first_eval
         return EngineConfig(variant="lg", samples=36, swap_interval=3, surrogate_interval=5, surrogate_prob=0.4, use_surrogate=True,
                             use_langevin=True, learn_rate=0.05, surrogate_topology=1, seed=24, record_history=True, record_pos=True,
@@ -46,7 +49,7 @@ def _run(rank, world, port, q, variant="rw"):
     topo = [int(v) for v in g["topology"]]
     prob = Problem(topo, g["train"], g["test"], device=rank)
     trainer = None
-    if variant in ("rw_sur", "lg_sur"):
+    if variant in ("rw_sur", "lg_sur", "rw_sur_all"):
         from oracle import sapt_oracle as so      # fixed MLPs stand in for the trained surrogate (one per signature)
         ws = [so.make_surrogate_weights(prob.P, 1, 50 + s) for s in range(12)]
         trainer = lambda batch, sig: ws[sig - 1]
@@ -59,10 +62,10 @@ def _run(rank, world, port, q, variant="rw"):
     if variant == "ls":
         keys = ("accepted", "accept_list", "lhood_list", "acc_train", "naccept", "row_of_slot", "surg_likeh_list", "is_surrogate_step",
                 "ls_weights", "ls_limit")
-    if variant in ("rw_sur", "lg_sur"):
+    if variant in ("rw_sur", "lg_sur", "rw_sur_all"):
         keys = keys + ("is_surrogate_step", "surg_likeh_list")
     out = {k: res[k] for k in keys}
-    if variant in ("rw_sur", "lg_sur"):
+    if variant in ("rw_sur", "lg_sur", "rw_sur_all"):
         out["surr_batches"] = res["surr_batches"]
     out["swaps"] = np.array([s for s in res["swap_decisions"]])
     out["num_swap"] = res["num_swap"]
@@ -116,7 +119,7 @@ def test_two_gpu_local_surrogate_equals_one_gpu():
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("variant", ["rw_sur", "lg_sur"])
+@pytest.mark.parametrize("variant", ["rw_sur", "lg_sur", "rw_sur_all"])
 def test_two_gpu_global_surrogate_equals_one_gpu(variant):
     """PT with the global surrogate over two ranks (random-walk fork: exchange and training share the rendezvous;
     Langevin fork: exchanges inside a surrogate interval): the training rows every rank assembles at the
@@ -131,6 +134,8 @@ def test_two_gpu_global_surrogate_equals_one_gpu(variant):
     two = q.get(timeout=300)
     for p in procs: p.join()
     assert one["is_surrogate_step"].sum() > 0 and one["swaps"].sum() > 0
+    if variant == "rw_sur_all":      # from the first model on every step is a surrogate step: later batches hold the zero rows only
+        assert one["is_surrogate_step"][:, 8:20].all() and any(not np.any(b) for b in one["surr_batches"][1:])
     for k in ("accepted", "is_surrogate_step", "swaps", "row_of_slot", "naccept", "pos_w"):
         assert np.array_equal(one[k], two[k]), k
     assert len(one["surr_batches"]) == len(two["surr_batches"]) > 0
